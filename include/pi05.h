@@ -1,0 +1,132 @@
+/* pi05.h — C ABI of libpi05.so, the B200-native (sm_100a) engine for the pi0.5 hot path of OpenDriveLab/kai0.
+ *
+ * The reference has no FFI for this path: its boundary is the Python class
+ *   openpi.models_pytorch.pi0_pytorch.PI0Pytorch   (src/openpi/models_pytorch/pi0_pytorch.py:84-461)
+ * reached from scripts/train_pytorch.py:417,540 and src/openpi/policies/policy.py:110.  This header is the
+ * C boundary a maintainer would bind underneath that class (see INTEGRATION.md for the ctypes stub); each entry
+ * point names the reference method it replaces.
+ *
+ * Conventions: every pointer in a call is a DEVICE pointer owned by the caller (torch allocations) unless it
+ * says "host"; nothing here synchronises the device; all work is enqueued on the cudaStream_t passed in (as a
+ * void*).  Return value 0 = ok; otherwise pi05_last_error() holds a message (thread-local, host string).
+ */
+#ifndef PI05_H_
+#define PI05_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PI05_ABI_VERSION 1
+
+typedef struct pi05_engine pi05_engine; /* opaque */
+
+/* ---- model description: mirrors what PI0Pytorch.__init__ reads from its config (pi0_pytorch.py:85-109) and
+ *      openpi.models.gemma.get_config (src/openpi/models/gemma.py:58-110) ------------------------------------ */
+typedef struct pi05_gemma_cfg {
+  int32_t width, depth, mlp_dim, num_heads, num_kv_heads, head_dim;
+} pi05_gemma_cfg;
+
+typedef struct pi05_config {
+  pi05_gemma_cfg paligemma; /* gemma_2b  */
+  pi05_gemma_cfg expert;    /* gemma_300m, adaRMS conditioned (pi05 = True) */
+  /* SigLIP-So400m/14 vision tower (gemma_pytorch.py:38-41 + HF SiglipVisionConfig defaults) */
+  int32_t vit_width, vit_depth, vit_mlp_dim, vit_heads, vit_patch, image_size;
+  int32_t vocab_size;     /* 257152 */
+  int32_t action_dim;     /* 32  */
+  int32_t action_horizon; /* 50  */
+  int32_t max_token_len;  /* 200 */
+  int32_t num_images;     /* 3 for PI0Pytorch; up to 6 for AdvantageEstimator */
+  int32_t max_batch;      /* largest per-GPU batch the workspace is sized for */
+  int32_t train;          /* 1: size the activation stash for backward */
+  int32_t value_head;     /* 1: AdvantageEstimator value head (pi0_pytorch.py:473-481) */
+} pi05_config;
+
+/* dtype codes used in tensor descriptors */
+enum { PI05_F32 = 0, PI05_BF16 = 1 };
+
+/* One named parameter (reference state_dict key), its data and (optionally) its gradient buffer.
+ * The Python module owns both as torch tensors; the engine only keeps the pointers. */
+typedef struct pi05_param {
+  const char* name; /* host string, e.g. "paligemma_with_expert.paligemma.model.language_model.layers.0.self_attn.q_proj.weight" */
+  int32_t dtype;
+  int64_t numel;
+  void* data;
+  void* grad; /* may be NULL (inference) */
+} pi05_param;
+
+/* One preprocessed batch = what PI0Pytorch._preprocess_observation returns (pi0_pytorch.py:161-170). */
+typedef struct pi05_batch {
+  int32_t batch;
+  const float* images;         /* [num_images][batch,3,H,W] fp32 in [-1,1], image-major (one pointer, contiguous) */
+  const uint8_t* image_masks;  /* [num_images][batch] bool */
+  const int64_t* tokens;       /* [batch, max_token_len] */
+  const uint8_t* token_mask;   /* [batch, max_token_len] bool */
+} pi05_batch;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+int pi05_abi_version(void);
+const char* pi05_last_error(void);
+
+/* Bytes of device workspace pi05_create will carve up for this config (activations, stash, KV cache). */
+size_t pi05_workspace_bytes(const pi05_config* cfg);
+/* `workspace` must stay alive and 256B-aligned for the life of the engine. */
+int pi05_create(const pi05_config* cfg, int device, void* workspace, size_t workspace_bytes, pi05_engine** out);
+void pi05_destroy(pi05_engine* e);
+/* Bind every parameter by reference name; unknown or missing names are an error (lists them). */
+int pi05_bind_params(pi05_engine* e, const pi05_param* params, int n);
+/* Called after the optimiser changed weights in place (refreshes derived tables). */
+int pi05_params_updated(pi05_engine* e, void* stream);
+
+/* ---- training: replaces PI0Pytorch.forward (pi0_pytorch.py:316-373) and its autograd backward ----------- */
+/* x_t / time are produced by the caller exactly as the reference does (noise, Beta time: pi0_pytorch.py:320-328).
+ * v_t_out: [batch, action_horizon, action_dim] fp32  (the caller forms (u_t - v_t)^2).                        */
+int pi05_forward(pi05_engine* e, const pi05_batch* b, const float* x_t, const float* time, float* v_t_out,
+                 void* stream);
+/* dv_t: gradient w.r.t. v_t_out, same shape.  Writes every bound .grad buffer (overwrites, does not accumulate). */
+int pi05_backward(pi05_engine* e, const float* dv_t, void* stream);
+
+/* ---- inference: replaces PI0Pytorch.sample_actions (pi0_pytorch.py:375-419) ----------------------------- */
+/* prefix pass + KV cache (gemma_pytorch.py:102-113) */
+int pi05_prefill(pi05_engine* e, const pi05_batch* b, void* stream);
+/* `num_steps` Euler steps from `noise` [batch,H,A] fp32 -> actions_out (pi0_pytorch.py:401-419,421-461) */
+int pi05_denoise(pi05_engine* e, const float* noise, int num_steps, float* actions_out, void* stream);
+
+/* AdvantageEstimator.sample_values / value head on suffix_out[:,0] (pi0_pytorch.py:596-644) */
+int pi05_forward_value(pi05_engine* e, float* value_out, void* stream);
+
+/* Debug taps: copy a named intermediate of the last forward into `dst` (fp32 or bf16 as stored). Returns its
+ * element count through *numel and dtype through *dtype; dst may be NULL to query.  Used by parity tests only. */
+int pi05_get_tap(pi05_engine* e, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream);
+
+/* ---- stand-alone operator: the tcgen05 GEMM that every nn.Linear / matmul of the path maps to ----------- */
+typedef struct pi05_gemm_desc {
+  int32_t M, N, K, batch;
+  const void* A; /* bf16 */
+  const void* B; /* bf16 */
+  int32_t a_major, b_major; /* 0: [rows,K] K contiguous; 1: [K,rows] rows contiguous */
+  int64_t lda, ldb, a_batch_stride, b_batch_stride; /* elements */
+  int32_t epilogue; /* see GemmEpilogue in csrc/gemm.h */
+  void* D;
+  int64_t ldd, d_batch_stride;
+  void* D2;
+  int64_t ldd2, d2_batch_stride;
+  const void* bias;
+  const void* res;
+  int64_t ldres, res_batch_stride;
+  const void* gate;
+  int32_t gate_rows;
+  int64_t ldgate;
+  float scale;
+  int32_t accumulate;
+  int32_t block_n;
+} pi05_gemm_desc;
+int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PI05_H_ */

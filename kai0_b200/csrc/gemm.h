@@ -1,0 +1,51 @@
+// Internal interface of the tcgen05 bf16 GEMM engine (see gemm_sm100.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pi05 {
+
+// Epilogue applied while draining the fp32 accumulator out of TMEM.  Every "bf(...)" below is a
+// round-to-nearest-even bf16 rounding, placed where the reference materialises a bf16 tensor.
+enum GemmEpilogue : int {
+  EPI_STORE = 0,      // D = bf(acc)
+  EPI_SCALE = 1,      // D = bf(bf(acc) * scale)                      (attention scores, modeling_gemma.py:243)
+  EPI_BIAS = 2,       // D = bf(acc + bias[n])                        (nn.Linear with bias)
+  EPI_BIAS_GELU = 3,  // D = bf(acc + bias[n]); D2 = bf(gelu_tanh(D)) (SiglipMLP fc1 + activation)
+  EPI_RES = 4,        // t = bf(acc [+ bias[n]]); if gate: t = bf(t * gate[row / gate_rows, n]); D = bf(res + t)
+  EPI_GEGLU = 5,      // B tile = [gate rows | up rows]; g = bf(acc_g), u = bf(acc_u), D[:, n] = g, D[:, N + n] = u,
+                      // D2[:, n] = bf(bf(gelu_tanh(g)) * u)          (GemmaMLP, modeling_gemma.py:125)
+  EPI_F32 = 6,        // Df32 = acc (+ Df32 if accumulate)
+  EPI_COUNT = 7,
+};
+
+struct GemmArgs {
+  // Problem: for every batch index z: D[z][M,N] = A[z][M,K] * B[z][N,K]^T
+  int M = 0, N = 0, K = 0, batch = 1;
+  // Operands (bf16).  major 0: row-major [rows, K] (K contiguous).  major 1: row-major [K, rows] (rows contiguous).
+  const void* A = nullptr;
+  const void* B = nullptr;
+  int a_major = 0, b_major = 0;
+  int64_t lda = 0, ldb = 0;                      // elements between consecutive rows of the stored matrix
+  int64_t a_batch_stride = 0, b_batch_stride = 0;  // elements; 0 = operand shared by all batches
+  // Output
+  int epilogue = EPI_STORE;
+  void* D = nullptr;
+  int64_t ldd = 0, d_batch_stride = 0;
+  void* D2 = nullptr;
+  int64_t ldd2 = 0, d2_batch_stride = 0;
+  const void* bias = nullptr;  // bf16 [N]
+  const void* res = nullptr;   // bf16 [M, ldres]
+  int64_t ldres = 0, res_batch_stride = 0;
+  const void* gate = nullptr;  // bf16 [ceil(M / gate_rows), ldgate]
+  int gate_rows = 1;
+  int64_t ldgate = 0;
+  float scale = 1.0f;
+  int accumulate = 0;  // EPI_F32 only
+  int block_n = 0;     // 0 = auto (256 when N >= 256 else 128)
+};
+
+// Enqueue on `stream`.  Returns 0 on success; on failure returns non-zero and fills `err` (if given).
+int gemm_bf16(const GemmArgs& args, cudaStream_t stream, char* err = nullptr, int err_len = 0);
+
+}  // namespace pi05

@@ -1,0 +1,576 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (fp32 accumulators in TMEM,
+//   double-buffered) -> tcgen05.ld epilogue with the fused element-wise tails listed in gemm.h.
+//
+// It replaces every bf16 nn.Linear / torch.matmul call site of the reference hot path
+// (modeling_gemma.py:125,243,250,295-297,328; modeling_siglip.py:333-341,378-380,412,429-431;
+//  modeling_paligemma.py:96-99) and all of their autograd counterparts (dgrad / wgrad), which is why both
+// operands may be K-major or MN-major.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer (1 thread)   warp 1 = MMA issuer (1 thread) + TMEM owner
+//                            warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3)
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace pi05 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int GROUP_M = 8;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int TILE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages
+};
+
+struct KParams {
+  int M, N, K, batch;
+  int a_mn, b_mn, a_batched, b_batched;
+  int num_m, num_n, num_kb;
+  uint32_t idesc;
+  void* D;
+  long long ldd, dbs;
+  void* D2;
+  long long ldd2, d2bs;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* res;
+  long long ldres, resbs;
+  const __nv_bfloat16* gate;
+  int gate_rows;
+  long long ldgate;
+  float scale;
+  int accumulate;
+  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor geometry (overridable for bring-up: PI05_DBG_MN_LBO/SBO)
+};
+
+struct TileCoord {
+  int z, m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int tile, const KParams& p) {
+  const int per_batch = p.num_m * p.num_n;
+  TileCoord c;
+  c.z = tile / per_batch;
+  const int t = tile - c.z * per_batch;
+  const int group_span = GROUP_M * p.num_n;
+  const int group = t / group_span;
+  const int first_m = group * GROUP_M;
+  const int gsz = min(GROUP_M, p.num_m - first_m);
+  const int r = t - group * group_span;
+  c.m_blk = first_m + r % gsz;
+  c.n_blk = r / gsz;
+  return c;
+}
+
+// ---- epilogue helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, int nvalid, float (&out)[32]) {
+  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 v = q[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        out[i * 8 + j * 2 + 0] = __uint_as_float(w[j] << 16);
+        out[i * 8 + j * 2 + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = (i < nvalid) ? __bfloat162float(p[i]) : 0.0f;
+  }
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, int nvalid, const float (&v)[32]) {
+  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+      o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+      o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+      o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+      q[i] = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) p[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+__device__ __forceinline__ void regs_to_float(const uint32_t (&r)[32], float (&f)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B-aligned tiles
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + C::STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + C::TILE_BYTES;
+  // barrier slots (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  const uint32_t full_bar0 = bar_base;
+  const uint32_t empty_bar0 = bar_base + 8 * C::STAGES;
+  const uint32_t tfull_bar0 = bar_base + 16 * C::STAGES;
+  const uint32_t tempty_bar0 = tfull_bar0 + 16;
+  const uint32_t tmem_slot = tempty_bar0 + 16;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar0 + 8 * s, 1);
+      mbar_init(empty_bar0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar0 + 8 * a, 1);
+      mbar_init(tempty_bar0 + 8 * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.num_m * p.num_n * p.batch;
+  constexpr int BN_OUT = (EPI == EPI_GEGLU) ? BN / 2 : BN;  // output columns covered by one tile
+
+  if (warp_idx == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(tile, p);
+        const int m0 = tc.m_blk * BM;
+        const int n0 = tc.n_blk * BN_OUT;
+        const int za = p.a_batched ? tc.z : 0;
+        const int zb = p.b_batched ? tc.z : 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+          const uint32_t full = full_bar0 + 8 * stage;
+          mbar_arrive_expect_tx(full, A_STAGE_BYTES + C::B_STAGE_BYTES);
+          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b0 + stage * C::B_STAGE_BYTES;
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_3d(sa, &tma_a, full, k0, m0, za);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * (BK * 128), &tma_a, full, m0 + 64 * i, k0, za);
+          }
+          if (EPI == EPI_GEGLU) {
+            tma_load_3d(sb, &tma_b, full, k0, n0, zb);
+            tma_load_3d(sb + (BN / 2) * 128, &tma_b, full, k0, p.N + n0, zb);
+          } else if (!p.b_mn) {
+            tma_load_3d(sb, &tma_b, full, k0, n0, zb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (BK * 128), &tma_b, full, n0 + 64 * i, k0, zb);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      // Per-operand descriptor geometry.  K-major: rows of 128 B, 8-row groups 1024 B apart, k-step = 32 B.
+      // MN-major: 64-element (128 B) MN atoms, k rows 128 B apart, 8-k groups 1024 B apart (SBO),
+      //           MN atoms BK*128 B apart (LBO), k-step (16 k rows) = 2048 B.
+      const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, a_sbo = p.a_mn ? p.mn_sbo : 1024, a_kstep = p.a_mn ? 2048 : 32;
+      const uint32_t b_lbo = p.b_mn ? p.mn_lbo : 16, b_sbo = p.b_mn ? p.mn_sbo : 1024, b_kstep = p.b_mn ? 2048 : 32;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b0 + stage * C::B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t da = make_smem_desc_sw128(sa + j * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = make_smem_desc_sw128(sb + j * b_kstep, b_lbo, b_sbo);
+            umma_bf16(d_tmem, da, db, p.idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar0 + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(tfull_bar0 + 8 * acc);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int row = tc.m_blk * BM + q * 32 + lane;
+      const int n0 = tc.n_blk * BN_OUT;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN_OUT / 32; ++c) {
+        const int col = n0 + c * 32;
+        if (col >= p.N) break;  // warp-uniform
+        const int nvalid = min(32, p.N - col);
+        uint32_t r[32];
+        float v[32];
+        tmem_ld32(t_base + c * 32, r);
+        tmem_ld_wait();
+        regs_to_float(r, v);
+
+        if constexpr (EPI == EPI_GEGLU) {
+          uint32_t r2[32];
+          float u[32];
+          tmem_ld32(t_base + BN / 2 + c * 32, r2);
+          tmem_ld_wait();
+          regs_to_float(r2, u);
+          if (row_ok) {
+            float h[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float g = bf16_round(v[i]);
+              const float uu = bf16_round(u[i]);
+              const float a = bf16_round(gelu_tanh_f(g));
+              v[i] = g;
+              u[i] = uu;
+              h[i] = a * uu;
+            }
+            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd;
+            store_bf16x32(d + col, nvalid, v);
+            store_bf16x32(d + p.N + col, nvalid, u);
+            __nv_bfloat16* d2 =
+                static_cast<__nv_bfloat16*>(p.D2) + tc.z * p.d2bs + static_cast<long long>(row) * p.ldd2;
+            store_bf16x32(d2 + col, nvalid, h);
+          }
+        } else if constexpr (EPI == EPI_F32) {
+          if (row_ok) {
+            float* d = static_cast<float*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd + col;
+            if (p.accumulate) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) d[i] += v[i];
+            } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(d)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) d[i] = v[i];
+            }
+          }
+        } else {
+          if (row_ok) {
+            if constexpr (EPI == EPI_SCALE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]) * p.scale;
+            }
+            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+              float b[32];
+              load_bf16x32(p.bias + col, nvalid, b);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += b[i];
+            }
+            if constexpr (EPI == EPI_RES) {
+              if (p.bias != nullptr) {
+                float b[32];
+                load_bf16x32(p.bias + col, nvalid, b);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += b[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+              if (p.gate != nullptr) {
+                float gt[32];
+                load_bf16x32(p.gate + static_cast<long long>(row / p.gate_rows) * p.ldgate + col, nvalid, gt);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] * gt[i]);
+              }
+              float rs[32];
+              load_bf16x32(p.res + tc.z * p.resbs + static_cast<long long>(row) * p.ldres + col, nvalid, rs);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += rs[i];
+            }
+            __nv_bfloat16* d =
+                static_cast<__nv_bfloat16*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd + col;
+            store_bf16x32(d, nvalid, v);
+            if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_f(bf16_round(v[i]));
+              __nv_bfloat16* d2 =
+                  static_cast<__nv_bfloat16*>(p.D2) + tc.z * p.d2bs + static_cast<long long>(row) * p.ldd2 + col;
+              store_bf16x32(d2, nvalid, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar0 + 8 * acc);  // 128 arrivals release this accumulator stage to the MMA warp
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+using EncodeFn = PFN_cuTensorMapEncodeTiled_v12000;
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) ptr = nullptr;
+    return reinterpret_cast<EncodeFn>(ptr);
+  }();
+  return fn;
+}
+
+using TmapKey = std::tuple<const void*, int, long long, long long, long long, long long, long long, int>;
+std::map<TmapKey, CUtensorMap>& tmap_cache() {
+  static std::map<TmapKey, CUtensorMap> c;
+  return c;
+}
+std::mutex& tmap_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+// major 0: stored [rows, K] (K contiguous)  -> dims {K, rows, batch}, box {64, box_rows, 1}
+// major 1: stored [K, rows] (rows contiguous) -> dims {rows, K, batch}, box {64, 64, 1}
+bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, long long K, long long ld, long long batch,
+               long long batch_stride, int box_rows, char* err, int err_len) {
+  const bool batched = batch > 1 && batch_stride != 0;
+  const long long nb = batched ? batch : 1;
+  TmapKey key{ptr, major, rows, K, ld, nb, batch_stride, box_rows};
+  {
+    std::lock_guard<std::mutex> g(tmap_mutex());
+    auto it = tmap_cache().find(key);
+    if (it != tmap_cache().end()) {
+      *out = it->second;
+      return true;
+    }
+  }
+  EncodeFn enc = get_encode_fn();
+  if (!enc) {
+    if (err) snprintf(err, err_len, "cuTensorMapEncodeTiled entry point unavailable");
+    return false;
+  }
+  cuuint64_t dims[3];
+  cuuint64_t strides[2];
+  cuuint32_t box[3];
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (major == 0) {
+    dims[0] = K;
+    dims[1] = rows;
+    box[0] = BK;
+    box[1] = box_rows;
+  } else {
+    dims[0] = rows;
+    dims[1] = K;
+    box[0] = 64;
+    box[1] = BK;
+  }
+  dims[2] = nb;
+  box[2] = 1;
+  strides[0] = static_cast<cuuint64_t>(ld) * 2;
+  strides[1] = batched ? static_cast<cuuint64_t>(batch_stride) * 2 : strides[0] * dims[1];
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+    if (err)
+      snprintf(err, err_len, "gemm operand not 16B aligned (ptr %p ld %lld batch_stride %lld)", ptr, ld, batch_stride);
+    return false;
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err)
+      snprintf(err, err_len, "cuTensorMapEncodeTiled failed (%d): major %d rows %lld K %lld ld %lld batch %lld bs %lld",
+               static_cast<int>(r), major, rows, K, ld, nb, batch_stride);
+    return false;
+  }
+  std::lock_guard<std::mutex> g(tmap_mutex());
+  tmap_cache()[key] = *out;
+  return true;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+template <int BN, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t stream, char* err,
+           int err_len) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      if (err) snprintf(err, err_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  const int total = kp.num_m * kp.num_n * kp.batch;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) snprintf(err, err_len, "gemm launch: %s", cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+template <int BN>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t s, char* err,
+                 int err_len) {
+  switch (epi) {
+    case EPI_STORE: return launch<BN, EPI_STORE>(ta, tb, kp, s, err, err_len);
+    case EPI_SCALE: return launch<BN, EPI_SCALE>(ta, tb, kp, s, err, err_len);
+    case EPI_BIAS: return launch<BN, EPI_BIAS>(ta, tb, kp, s, err, err_len);
+    case EPI_BIAS_GELU: return launch<BN, EPI_BIAS_GELU>(ta, tb, kp, s, err, err_len);
+    case EPI_RES: return launch<BN, EPI_RES>(ta, tb, kp, s, err, err_len);
+    case EPI_GEGLU: return launch<BN, EPI_GEGLU>(ta, tb, kp, s, err, err_len);
+    case EPI_F32: return launch<BN, EPI_F32>(ta, tb, kp, s, err, err_len);
+    default:
+      if (err) snprintf(err, err_len, "unknown epilogue %d", epi);
+      return 1;
+  }
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) {
+    if (err) snprintf(err, err_len, "gemm: empty problem M=%d N=%d K=%d batch=%d", a.M, a.N, a.K, a.batch);
+    return 1;
+  }
+  if (a.epilogue == EPI_GEGLU && a.b_major != 0) {
+    if (err) snprintf(err, err_len, "gemm: GEGLU epilogue needs a K-major [2N,K] weight");
+    return 1;
+  }
+  int bn = a.block_n;
+  if (bn == 0) bn = (a.epilogue == EPI_GEGLU) ? 256 : (a.N > 128 ? 256 : 128);
+  if (bn != 128 && bn != 256) {
+    if (err) snprintf(err, err_len, "gemm: unsupported block_n %d", bn);
+    return 1;
+  }
+  const int bn_out = (a.epilogue == EPI_GEGLU) ? bn / 2 : bn;
+  const long long b_rows = (a.epilogue == EPI_GEGLU) ? 2LL * a.N : a.N;
+  const int b_box_rows = (a.epilogue == EPI_GEGLU) ? bn / 2 : bn;
+
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, a.A, a.a_major, a.M, a.K, a.lda, a.batch, a.a_batch_stride, BM, err, err_len)) return 4;
+  if (!make_tmap(&tb, a.B, a.b_major, b_rows, a.K, a.ldb, a.batch, a.b_batch_stride, b_box_rows, err, err_len))
+    return 4;
+
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = a.M;
+  kp.N = a.N;
+  kp.K = a.K;
+  kp.batch = a.batch;
+  kp.a_mn = a.a_major;
+  kp.b_mn = a.b_major;
+  kp.a_batched = (a.batch > 1 && a.a_batch_stride != 0) ? 1 : 0;
+  kp.b_batched = (a.batch > 1 && a.b_batch_stride != 0) ? 1 : 0;
+  kp.num_m = (a.M + BM - 1) / BM;
+  kp.num_n = (a.N + bn_out - 1) / bn_out;
+  kp.num_kb = (a.K + BK - 1) / BK;
+  kp.idesc = make_idesc_bf16(BM, bn, a.a_major, a.b_major);
+  kp.D = a.D;
+  kp.ldd = a.ldd;
+  kp.dbs = a.d_batch_stride;
+  kp.D2 = a.D2;
+  kp.ldd2 = a.ldd2;
+  kp.d2bs = a.d2_batch_stride;
+  kp.bias = static_cast<const __nv_bfloat16*>(a.bias);
+  kp.res = static_cast<const __nv_bfloat16*>(a.res);
+  kp.ldres = a.ldres;
+  kp.resbs = a.res_batch_stride;
+  kp.gate = static_cast<const __nv_bfloat16*>(a.gate);
+  kp.gate_rows = a.gate_rows > 0 ? a.gate_rows : 1;
+  kp.ldgate = a.ldgate;
+  kp.scale = a.scale;
+  kp.accumulate = a.accumulate;
+  kp.mn_lbo = BK * 128;
+  kp.mn_sbo = 1024;
+  if (const char* e = getenv("PI05_DBG_MN_LBO")) kp.mn_lbo = static_cast<uint32_t>(atoi(e));
+  if (const char* e = getenv("PI05_DBG_MN_SBO")) kp.mn_sbo = static_cast<uint32_t>(atoi(e));
+  if (bn == 256) return dispatch_epi<256>(a.epilogue, ta, tb, kp, stream, err, err_len);
+  return dispatch_epi<128>(a.epilogue, ta, tb, kp, stream, err, err_len);
+}
+
+}  // namespace pi05
