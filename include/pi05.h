@@ -82,12 +82,15 @@ int pi05_bind_params(pi05_engine* e, const pi05_param* params, int n);
 int pi05_params_updated(pi05_engine* e, void* stream);
 
 /* ---- training: replaces PI0Pytorch.forward (pi0_pytorch.py:316-373) and its autograd backward ----------- */
-/* x_t / time are produced by the caller exactly as the reference does (noise, Beta time: pi0_pytorch.py:320-328).
- * v_t_out: [batch, action_horizon, action_dim] fp32  (the caller forms (u_t - v_t)^2).                        */
-int pi05_forward(pi05_engine* e, const pi05_batch* b, const float* x_t, const float* time, float* v_t_out,
-                 void* stream);
-/* dv_t: gradient w.r.t. v_t_out, same shape.  Writes every bound .grad buffer (overwrites, does not accumulate). */
-int pi05_backward(pi05_engine* e, const float* dv_t, void* stream);
+/* actions / noise: [batch, action_horizon, action_dim] fp32, time: [batch] fp32.  noise and time are drawn by the
+ * caller exactly as the reference does (torch.normal / Beta(1.5,1)*0.999+0.001, pi0_pytorch.py:172-184,320-324).
+ * loss_out: [batch, action_horizon, action_dim] fp32 = (u_t - v_t)^2, i.e. F.mse_loss(reduction="none").        */
+int pi05_forward(pi05_engine* e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                 float* loss_out, void* stream);
+/* dloss: gradient w.r.t. loss_out, same shape.  Writes every bound .grad buffer (overwrites, does not accumulate). */
+int pi05_backward(pi05_engine* e, const float* dloss, void* stream);
+/* Enable (1) / disable (0) recording of named intermediates for pi05_get_tap. */
+int pi05_set_taps(pi05_engine* e, int enabled);
 
 /* ---- inference: replaces PI0Pytorch.sample_actions (pi0_pytorch.py:375-419) ----------------------------- */
 /* prefix pass + KV cache (gemma_pytorch.py:102-113) */
@@ -105,18 +108,20 @@ int pi05_get_tap(pi05_engine* e, const char* name, void* dst, int64_t* numel, in
 /* ---- stand-alone operator: the tcgen05 GEMM that every nn.Linear / matmul of the path maps to ----------- */
 typedef struct pi05_gemm_desc {
   int32_t M, N, K, batch;
+  int32_t batch_inner; /* two-level batch z = z1*batch_inner + z0; 0 = one level */
   const void* A; /* bf16 */
   const void* B; /* bf16 */
   int32_t a_major, b_major; /* 0: [rows,K] K contiguous; 1: [K,rows] rows contiguous */
   int64_t lda, ldb, a_batch_stride, b_batch_stride; /* elements */
+  int64_t a_batch_stride1, b_batch_stride1;
   int32_t epilogue; /* see GemmEpilogue in csrc/gemm.h */
   void* D;
-  int64_t ldd, d_batch_stride;
+  int64_t ldd, d_batch_stride, d_batch_stride1;
   void* D2;
-  int64_t ldd2, d2_batch_stride;
+  int64_t ldd2, d2_batch_stride, d2_batch_stride1;
   const void* bias;
   const void* res;
-  int64_t ldres, res_batch_stride;
+  int64_t ldres, res_batch_stride, res_batch_stride1;
   const void* gate;
   int32_t gate_rows;
   int64_t ldgate;

@@ -67,6 +67,7 @@ class GemmDesc(C.Structure):
         ("N", C.c_int32),
         ("K", C.c_int32),
         ("batch", C.c_int32),
+        ("batch_inner", C.c_int32),
         ("A", C.c_void_p),
         ("B", C.c_void_p),
         ("a_major", C.c_int32),
@@ -75,17 +76,22 @@ class GemmDesc(C.Structure):
         ("ldb", C.c_int64),
         ("a_batch_stride", C.c_int64),
         ("b_batch_stride", C.c_int64),
+        ("a_batch_stride1", C.c_int64),
+        ("b_batch_stride1", C.c_int64),
         ("epilogue", C.c_int32),
         ("D", C.c_void_p),
         ("ldd", C.c_int64),
         ("d_batch_stride", C.c_int64),
+        ("d_batch_stride1", C.c_int64),
         ("D2", C.c_void_p),
         ("ldd2", C.c_int64),
         ("d2_batch_stride", C.c_int64),
+        ("d2_batch_stride1", C.c_int64),
         ("bias", C.c_void_p),
         ("res", C.c_void_p),
         ("ldres", C.c_int64),
         ("res_batch_stride", C.c_int64),
+        ("res_batch_stride1", C.c_int64),
         ("gate", C.c_void_p),
         ("gate_rows", C.c_int32),
         ("ldgate", C.c_int64),
@@ -109,6 +115,7 @@ EXPORTS = (
     "pi05_params_updated",
     "pi05_forward",
     "pi05_backward",
+    "pi05_set_taps",
     "pi05_prefill",
     "pi05_denoise",
     "pi05_forward_value",
@@ -145,7 +152,17 @@ def lib() -> C.CDLL:
             l.pi05_params_updated.restype = C.c_int
             l.pi05_params_updated.argtypes = [C.c_void_p, C.c_void_p]
             l.pi05_forward.restype = C.c_int
-            l.pi05_forward.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            l.pi05_forward.argtypes = [
+                C.c_void_p,
+                C.POINTER(Batch),
+                C.c_void_p,
+                C.c_void_p,
+                C.c_void_p,
+                C.c_void_p,
+                C.c_void_p,
+            ]
+            l.pi05_set_taps.restype = C.c_int
+            l.pi05_set_taps.argtypes = [C.c_void_p, C.c_int]
             l.pi05_backward.restype = C.c_int
             l.pi05_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             l.pi05_prefill.restype = C.c_int

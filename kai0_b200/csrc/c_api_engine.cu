@@ -1,0 +1,201 @@
+// C-ABI entry points of the engine (include/pi05.h): lifecycle, parameter binding, forward/backward/decode, taps.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/pi05.h"
+#include "engine.h"
+#include "errors.h"
+
+using pi05::Engine;
+
+namespace pi05 {
+int engine_init_tables(Engine& e, cudaStream_t st);
+int engine_value(Engine& e, float* value_out, cudaStream_t st);
+}  // namespace pi05
+
+static Engine* E(pi05_engine* p) { return reinterpret_cast<Engine*>(p); }
+
+static int validate(const pi05_config* c, char* err, int n) {
+  if (!c) {
+    snprintf(err, n, "null config");
+    return 1;
+  }
+  const int w[] = {c->paligemma.width, c->expert.width, c->vit_width};
+  for (int x : w)
+    if (x <= 0 || x % 8 != 0) {
+      snprintf(err, n, "widths must be positive multiples of 8 (got %d)", x);
+      return 1;
+    }
+  if (c->paligemma.head_dim % 16 != 0 || c->paligemma.head_dim <= 0) {
+    snprintf(err, n, "head_dim must be a multiple of 16");
+    return 1;
+  }
+  if (c->vit_width % c->vit_heads != 0 || (c->vit_width / c->vit_heads) % 8 != 0) {
+    snprintf(err, n, "vit head_dim must be a multiple of 8");
+    return 1;
+  }
+  if (c->image_size % c->vit_patch != 0 || c->max_batch <= 0 || c->num_images <= 0 || c->action_horizon <= 0 ||
+      c->paligemma.mlp_dim % 8 != 0 || c->expert.mlp_dim % 8 != 0 || c->vit_mlp_dim % 8 != 0) {
+    snprintf(err, n, "bad geometry (image/patch, batch, images, horizon or mlp dims)");
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" {
+
+size_t pi05_workspace_bytes(const pi05_config* cfg) {
+  char err[256];
+  if (validate(cfg, err, sizeof(err)) != 0) {
+    pi05::set_error(err);
+    return 0;
+  }
+  Engine tmp;
+  tmp.cfg = *cfg;
+  pi05::engine_plan(tmp, /*dry=*/true);
+  return tmp.arena.off + 4096;
+}
+
+int pi05_create(const pi05_config* cfg, int device, void* workspace, size_t workspace_bytes, pi05_engine** out) {
+  char err[256];
+  if (validate(cfg, err, sizeof(err)) != 0 || !out || !workspace) {
+    pi05::set_error(cfg && out && workspace ? err : "pi05_create: null argument");
+    return 1;
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    pi05::set_error(cudaGetErrorString(ce));
+    return 2;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) {
+    snprintf(err, sizeof(err), "pi05 engine requires an sm_100 (B200) device; device %d is sm_%d0", device, major);
+    pi05::set_error(err);
+    return 2;
+  }
+  Engine* e = new (std::nothrow) Engine();
+  if (!e) {
+    pi05::set_error("out of host memory");
+    return 3;
+  }
+  e->cfg = *cfg;
+  e->device = device;
+  e->arena.base = static_cast<char*>(workspace);
+  e->arena.cap = workspace_bytes;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    pi05::set_error("workspace must be 256B aligned");
+    delete e;
+    return 1;
+  }
+  int rc = pi05::engine_plan(*e, /*dry=*/false);
+  if (rc == 0) rc = pi05::engine_init_tables(*e, nullptr);
+  if (rc != 0) {
+    delete e;
+    return rc;
+  }
+  *out = reinterpret_cast<pi05_engine*>(e);
+  return 0;
+}
+
+void pi05_destroy(pi05_engine* e) { delete E(e); }
+
+int pi05_bind_params(pi05_engine* pe, const pi05_param* params, int n) {
+  Engine* e = E(pe);
+  if (!e || (!params && n > 0)) {
+    pi05::set_error("pi05_bind_params: null argument");
+    return 1;
+  }
+  e->params.clear();
+  for (int i = 0; i < n; ++i) {
+    pi05::PRef r;
+    r.data = params[i].data;
+    r.grad = params[i].grad;
+    r.dtype = params[i].dtype;
+    r.numel = params[i].numel;
+    e->params[params[i].name] = r;
+  }
+  return pi05::engine_resolve_params(*e);
+}
+
+int pi05_params_updated(pi05_engine* pe, void* stream) {
+  (void)stream;
+  return E(pe) ? 0 : 1;
+}
+
+int pi05_set_taps(pi05_engine* pe, int enabled) {
+  if (!E(pe)) return 1;
+  E(pe)->taps_enabled = enabled != 0;
+  return 0;
+}
+
+int pi05_forward(pi05_engine* pe, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                 float* loss_out, void* stream) {
+  if (!E(pe) || !b || !actions || !noise || !time || !loss_out) {
+    pi05::set_error("pi05_forward: null argument");
+    return 1;
+  }
+  return pi05::engine_forward(*E(pe), b, actions, noise, time, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_backward(pi05_engine* pe, const float* dloss, void* stream) {
+  if (!E(pe) || !dloss) {
+    pi05::set_error("pi05_backward: null argument");
+    return 1;
+  }
+  return pi05::engine_backward(*E(pe), dloss, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_prefill(pi05_engine* pe, const pi05_batch* b, void* stream) {
+  if (!E(pe) || !b) {
+    pi05::set_error("pi05_prefill: null argument");
+    return 1;
+  }
+  return pi05::engine_prefill(*E(pe), b, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_denoise(pi05_engine* pe, const float* noise, int num_steps, float* actions_out, void* stream) {
+  if (!E(pe) || !noise || !actions_out || num_steps <= 0) {
+    pi05::set_error("pi05_denoise: bad argument");
+    return 1;
+  }
+  return pi05::engine_denoise(*E(pe), noise, num_steps, actions_out, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_forward_value(pi05_engine* pe, float* value_out, void* stream) {
+  if (!E(pe) || !value_out) {
+    pi05::set_error("pi05_forward_value: null argument");
+    return 1;
+  }
+  return pi05::engine_value(*E(pe), value_out, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_get_tap(pi05_engine* pe, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream) {
+  Engine* e = E(pe);
+  if (!e || !name) {
+    pi05::set_error("pi05_get_tap: null argument");
+    return 1;
+  }
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) {
+    char err[256];
+    snprintf(err, sizeof(err), "pi05_get_tap: no tap named '%s' (taps enabled: %d)", name, e->taps_enabled ? 1 : 0);
+    pi05::set_error(err);
+    return 2;
+  }
+  if (numel) *numel = it->second.numel;
+  if (dtype) *dtype = it->second.dtype;
+  if (dst) {
+    const size_t bytes = static_cast<size_t>(it->second.numel) * (it->second.dtype == PI05_BF16 ? 2 : 4);
+    cudaError_t ce =
+        cudaMemcpyAsync(dst, it->second.ptr, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+    if (ce != cudaSuccess) {
+      pi05::set_error(cudaGetErrorString(ce));
+      return 3;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

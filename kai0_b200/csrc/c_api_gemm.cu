@@ -26,6 +26,10 @@ int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream) {
   }
   pi05::GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.batch = d->batch > 0 ? d->batch : 1;
+  a.batch_inner = d->batch_inner;
+  a.a_batch_stride1 = d->a_batch_stride1; a.b_batch_stride1 = d->b_batch_stride1;
+  a.d_batch_stride1 = d->d_batch_stride1; a.d2_batch_stride1 = d->d2_batch_stride1;
+  a.res_batch_stride1 = d->res_batch_stride1;
   a.A = d->A; a.B = d->B; a.a_major = d->a_major; a.b_major = d->b_major;
   a.lda = d->lda; a.ldb = d->ldb; a.a_batch_stride = d->a_batch_stride; a.b_batch_stride = d->b_batch_stride;
   a.epilogue = d->epilogue; a.D = d->D; a.ldd = d->ldd; a.d_batch_stride = d->d_batch_stride;

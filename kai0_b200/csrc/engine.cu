@@ -1,0 +1,715 @@
+// pi0.5 engine: workspace plan, parameter binding, and the training-time forward pass.
+//
+// Follows, stage by stage (paths relative to /root/reference/src/openpi/models_pytorch/):
+//   pi0_pytorch.py:316-373 (forward), :186-235 (embed_prefix), :237-314 (embed_suffix, pi05 branch),
+//   gemma_pytorch.py:158-238 (joint layer), :262-275 (final norms),
+//   transformers_replace/models/siglip/modeling_siglip.py:271-282,435-481,763-796 (vision tower),
+//   transformers_replace/models/paligemma/modeling_paligemma.py:91-99,232-247 (projector).
+// Every bf16 GEMM runs on the tcgen05 kernel of gemm_sm100.cu; everything else is in *_kernels.cu.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "engine.h"
+#include "errors.h"
+#include "gemm.h"
+
+namespace pi05 {
+
+#define CHECK_RC(x)        \
+  do {                     \
+    int _rc = (x);         \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int engine_gemm(Engine& e, const GemmArgs& a) {
+  char err[512] = "";
+  int rc = gemm_bf16(a, e.stream, err, sizeof(err));
+  if (rc != 0) {
+    snprintf(e.err, sizeof(e.err), "%s", err);
+    set_error(e.err);
+  }
+  return rc;
+}
+
+GemmArgs mk_gemm(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, void* D, int64_t ldd,
+                 int epi) {
+  GemmArgs g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.A = A;
+  g.lda = lda;
+  g.B = Bm;
+  g.ldb = ldb;
+  g.D = D;
+  g.ldd = ldd;
+  g.epilogue = epi;
+  return g;
+}
+
+void add_tap(Engine& e, const char* name, const void* p, int64_t n, int dtype) {
+  if (e.taps_enabled) e.taps[name] = Tap{p, n, dtype};
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// workspace plan (dry = count bytes only)
+// ------------------------------------------------------------------------------------------------------------
+int engine_plan(Engine& e, bool dry) {
+  const pi05_config& c = e.cfg;
+  e.T = (c.image_size / c.vit_patch) * (c.image_size / c.vit_patch);
+  e.NI = c.num_images;
+  e.L = c.max_token_len;
+  e.P = e.NI * e.T + e.L;
+  e.A = c.action_horizon;
+  e.S = e.P + e.A;
+  e.Ppad = round_up(e.P, 8);
+  e.Spad = round_up(e.S, 8);
+  e.D = c.paligemma.width;
+  e.E = c.expert.width;
+  e.W = c.vit_width;
+  e.H = c.paligemma.num_heads;
+  e.hd = c.paligemma.head_dim;
+  e.VH = c.vit_heads;
+  e.vhd = c.vit_width / c.vit_heads;
+  e.Bmax = c.max_batch;
+  e.train = c.train != 0;
+
+  Arena& ar = e.arena;
+  ar.dry = dry;
+  ar.off = 0;
+  ar.overflow = false;
+  const int64_t B = e.Bmax, T = e.T, P = e.P, A = e.A, S = e.S, D = e.D, E = e.E, W = e.W, H = e.H, hd = e.hd;
+  const int64_t nimg = e.NI * B, Mv = nimg * T, M1 = B * P, M2 = B * A;
+  const int64_t QW = (H + 2) * hd;
+  const int depth = c.paligemma.depth;
+  const int vdepth = c.vit_depth;
+  const int64_t vmlp = c.vit_mlp_dim, mlp1 = c.paligemma.mlp_dim, mlp2 = c.expert.mlp_dim;
+  const bool tr = e.train;
+
+  e.rope_cos = ar.get<bf16>((S + 1) * (hd / 2));
+  e.rope_sin = ar.get<bf16>((S + 1) * (hd / 2));
+  e.time_scaling = ar.get<double>(E / 2);
+  e.pad = ar.get<uint8_t>(B * P);
+  e.pos = ar.get<int>(B * P);
+  e.nvalid = ar.get<int>(B);
+
+  // ---- vision tower
+  e.vit_x0 = ar.get<bf16>(Mv * W);
+  e.va.resize(vdepth);
+  VitLayerA shared{};
+  for (int l = 0; l < vdepth; ++l) {
+    VitLayerA& a = e.va[l];
+    if (tr || l == 0) {
+      a.h1 = ar.get<bf16>(Mv * W);
+      a.qkv = ar.get<bf16>(Mv * 3 * W);
+      a.P = ar.get<bf16>(nimg * e.VH * T * T);
+      a.attn = ar.get<bf16>(Mv * W);
+      a.h2 = ar.get<bf16>(Mv * W);
+      a.pre = ar.get<bf16>(Mv * vmlp);
+      a.act = ar.get<bf16>(Mv * vmlp);
+      a.mean1 = ar.get<float>(Mv);
+      a.rstd1 = ar.get<float>(Mv);
+      a.mean2 = ar.get<float>(Mv);
+      a.rstd2 = ar.get<float>(Mv);
+      if (l == 0) shared = a;
+    } else {
+      a = shared;
+    }
+    a.x_in = (l == 0) ? e.vit_x0 : e.va[l - 1].x_out;
+    a.x_mid = ar.get<bf16>(Mv * W);
+    a.x_out = ar.get<bf16>(Mv * W);
+  }
+  e.vit_post = ar.get<bf16>(Mv * W);
+  e.vit_post_mean = ar.get<float>(Mv);
+  e.vit_post_rstd = ar.get<float>(Mv);
+
+  // ---- the two Gemma streams
+  e.a1.resize(depth);
+  e.a2.resize(depth);
+  e.Kl.resize(depth);
+  e.Vl.resize(depth);
+  bf16* x1_0 = ar.get<bf16>(M1 * D);  // prefix_embs
+  bf16* x2_0 = ar.get<bf16>(M2 * E);  // suffix_embs
+  GemmaLayerA sh1{}, sh2{};
+  for (int l = 0; l < depth; ++l) {
+    GemmaLayerA &p1 = e.a1[l], &p2 = e.a2[l];
+    if (tr || l == 0) {
+      p1.n1 = ar.get<bf16>(M1 * D);
+      p1.qkv = ar.get<bf16>(M1 * QW);
+      p1.Q = ar.get<bf16>(M1 * H * hd);
+      p1.P = ar.get<bf16>(B * P * H * e.Ppad);
+      p1.O = ar.get<bf16>(M1 * H * hd);
+      p1.n2 = ar.get<bf16>(M1 * D);
+      p1.GU = ar.get<bf16>(M1 * 2 * mlp1);
+      p1.Hh = ar.get<bf16>(M1 * mlp1);
+      p1.rstd1 = ar.get<float>(M1);
+      p1.rstd2 = ar.get<float>(M1);
+      p1.o_lin = nullptr;
+      p1.d_lin = nullptr;
+      p1.gate1 = nullptr;
+      p1.gate2 = nullptr;
+      p2.n1 = ar.get<bf16>(M2 * E);
+      p2.qkv = ar.get<bf16>(M2 * QW);
+      p2.Q = ar.get<bf16>(M2 * H * hd);
+      p2.P = ar.get<bf16>(B * A * H * e.Spad);
+      p2.O = ar.get<bf16>(M2 * H * hd);
+      p2.o_lin = ar.get<bf16>(M2 * E);
+      p2.n2 = ar.get<bf16>(M2 * E);
+      p2.GU = ar.get<bf16>(M2 * 2 * mlp2);
+      p2.Hh = ar.get<bf16>(M2 * mlp2);
+      p2.d_lin = ar.get<bf16>(M2 * E);
+      p2.gate1 = ar.get<bf16>(B * E);
+      p2.gate2 = ar.get<bf16>(B * E);
+      p2.rstd1 = ar.get<float>(M2);
+      p2.rstd2 = ar.get<float>(M2);
+      if (l == 0) {
+        sh1 = p1;
+        sh2 = p2;
+      }
+    } else {
+      p1 = sh1;
+      p2 = sh2;
+    }
+    p1.x_in = (l == 0) ? x1_0 : e.a1[l - 1].x_out;
+    p2.x_in = (l == 0) ? x2_0 : e.a2[l - 1].x_out;
+    p1.x_mid = ar.get<bf16>(M1 * D);
+    p1.x_out = ar.get<bf16>(M1 * D);
+    p2.x_mid = ar.get<bf16>(M2 * E);
+    p2.x_out = ar.get<bf16>(M2 * E);
+    e.Kl[l] = ar.get<bf16>(B * S * hd);
+    e.Vl[l] = ar.get<bf16>(B * S * hd);
+  }
+  e.prefix_out = ar.get<bf16>(M1 * D);
+  e.suffix_out = ar.get<bf16>(M2 * E);
+  e.rstd_f1 = ar.get<float>(M1);
+  e.rstd_f2 = ar.get<float>(M2);
+
+  // ---- suffix front-end / head (fp32)
+  const int nmods = 2 * depth + 1;
+  e.x_t = ar.get<float>(M2 * c.action_dim);
+  e.u_t = ar.get<float>(M2 * c.action_dim);
+  e.temb = ar.get<float>(B * E);
+  e.aemb32 = ar.get<float>(M2 * E);
+  e.t1 = ar.get<float>(B * E);
+  e.t1s = ar.get<float>(B * E);
+  e.t2 = ar.get<float>(B * E);
+  e.cond = ar.get<float>(B * E);
+  e.mods = ar.get<float>(nmods * B * 3 * E);
+  e.so32 = ar.get<float>(M2 * E);
+  e.v_t = ar.get<float>(M2 * c.action_dim);
+  e.timevec = ar.get<float>(B);
+
+  // ---- backward scratch
+  if (tr) {
+    auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
+    const int64_t r1 = mx(M1 * D, Mv * W);
+    e.g_x1 = ar.get<bf16>(r1);
+    e.g_x1b = ar.get<bf16>(r1);
+    e.g_x2 = ar.get<bf16>(M2 * E);
+    e.g_x2b = ar.get<bf16>(M2 * E);
+    e.g_big = ar.get<bf16>(mx(mx(M1 * 2 * mlp1, Mv * vmlp), M2 * 2 * mlp2));
+    e.g_big2 = ar.get<bf16>(mx(mx(M1 * mlp1, Mv * vmlp), M2 * mlp2));
+    const int64_t rt = mx(mx(M1 * QW, Mv * 3 * W), mx(M1 * D, M1 * H * hd));
+    e.g_t1 = ar.get<bf16>(rt);
+    e.g_t2 = ar.get<bf16>(rt);
+    e.g_t3 = ar.get<bf16>(rt);
+    e.g_P = ar.get<bf16>(mx(mx(B * P * H * e.Ppad, nimg * e.VH * T * T), B * A * H * e.Spad));
+    e.g2_do = ar.get<bf16>(M2 * E);
+    e.g2_big = ar.get<bf16>(M2 * 2 * mlp2);
+    e.g2_big2 = ar.get<bf16>(M2 * mlp2);
+    e.g2_t1 = ar.get<bf16>(M2 * mx(QW, E));
+    e.g2_t2 = ar.get<bf16>(M2 * mx(H * hd, E));
+    e.g2_t3 = ar.get<bf16>(M2 * H * hd);
+    e.g_dK = ar.get<float>(B * S * hd);
+    e.g_dV = ar.get<float>(B * S * hd);
+    e.g_dmods = ar.get<float>(nmods * B * 3 * E);
+    e.g_f32a = ar.get<float>(mx(M2 * E, B * 3 * E));
+    e.g_f32b = ar.get<float>(mx(M2 * E, B * 3 * E));
+    e.g_f32c = ar.get<float>(mx(M2 * E, B * 3 * E));
+    e.g_acc_elems = static_cast<size_t>(mx(mx(4 * W + 2 * vmlp, 4 * D), mx(T * W + W, 3 * W * 14 * 14 * 3)) + 1024);
+    e.g_acc = ar.get<float>(e.g_acc_elems);
+    e.g_embed_scratch = ar.get<float>(B * e.L * D);
+    e.g_first = ar.get<int>(B * e.L);
+  }
+  ar.alloc(256);
+  if (!dry && ar.overflow) {
+    snprintf(e.err, sizeof(e.err), "workspace too small: need %zu bytes, have %zu", ar.off, ar.cap);
+    set_error(e.err);
+    return 5;
+  }
+  return 0;
+}
+
+// Host-computed constant tables, uploaded once at create time.
+int engine_init_tables(Engine& e, cudaStream_t st) {
+  const int half = e.hd / 2;
+  const int rows = e.S + 1;
+  std::vector<__nv_bfloat16> hc(static_cast<size_t>(rows) * half), hs(static_cast<size_t>(rows) * half);
+  for (int i = 0; i < half; ++i) {
+    // modeling_gemma.py:129-160 with rope_type "default": inv_freq = 1 / theta^(2i/hd), all in fp32
+    const float ex = static_cast<float>(2 * i) / static_cast<float>(e.hd);
+    const float inv = 1.0f / powf(10000.0f, ex);
+    for (int r = 0; r < rows; ++r) {
+      const float ang = inv * static_cast<float>(r - 1);
+      hc[static_cast<size_t>(r) * half + i] = __float2bfloat16_rn(cosf(ang));
+      hs[static_cast<size_t>(r) * half + i] = __float2bfloat16_rn(sinf(ang));
+    }
+  }
+  cudaMemcpyAsync(e.rope_cos, hc.data(), hc.size() * 2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(e.rope_sin, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice, st);
+  // pi0_pytorch.py:25-42: fraction = linspace(0,1,E/2) (fp64); period = 4e-3 * (4/4e-3)^fraction; 1/period*2*pi
+  const int th = e.E / 2;
+  std::vector<double> sc(th);
+  const double step = th > 1 ? 1.0 / static_cast<double>(th - 1) : 0.0;
+  for (int i = 0; i < th; ++i) {
+    const double frac = (i < th / 2) ? i * step : 1.0 - (th - 1 - i) * step;  // torch.linspace's symmetric form
+    const double period = 4e-3 * pow(4.0 / 4e-3, frac);
+    sc[i] = 1.0 / period * 2 * M_PI;
+  }
+  cudaMemcpyAsync(e.time_scaling, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+  cudaError_t ce = cudaStreamSynchronize(st);  // host vectors go out of scope
+  if (ce != cudaSuccess) {
+    snprintf(e.err, sizeof(e.err), "table upload: %s", cudaGetErrorString(ce));
+    set_error(e.err);
+    return 6;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// parameter resolution (reference state_dict names; fused-weight contiguity is required and checked)
+// ------------------------------------------------------------------------------------------------------------
+static bool get_param(Engine& e, const std::string& name, int dtype, int64_t numel, PRef* out, std::string* missing) {
+  auto it = e.params.find(name);
+  if (it == e.params.end()) {
+    if (missing->size() < 600) *missing += name + " ";
+    return false;
+  }
+  if (it->second.dtype != dtype || it->second.numel != numel) {
+    if (missing->size() < 600)
+      *missing += name + "(dtype/numel " + std::to_string(it->second.dtype) + "/" + std::to_string(it->second.numel) +
+                  " want " + std::to_string(dtype) + "/" + std::to_string(numel) + ") ";
+    return false;
+  }
+  *out = it->second;
+  return true;
+}
+
+static bool contiguous_after(const PRef& a, const PRef& b, int elem) {
+  const bool d = static_cast<char*>(a.data) + a.numel * elem == static_cast<char*>(b.data);
+  const bool g = (a.grad == nullptr && b.grad == nullptr) ||
+                 (a.grad && b.grad && static_cast<char*>(a.grad) + a.numel * elem == static_cast<char*>(b.grad));
+  return d && g;
+}
+
+int engine_resolve_params(Engine& e) {
+  const pi05_config& c = e.cfg;
+  std::string miss, contig;
+  const std::string PWE = "paligemma_with_expert.";
+  const std::string VT = PWE + "paligemma.model.vision_tower.vision_model.";
+  const std::string LM = PWE + "paligemma.model.language_model.";
+  const std::string EX = PWE + "gemma_expert.model.";
+  const int64_t W = e.W, D = e.D, E = e.E, pp = c.vit_patch * c.vit_patch * 3;
+  const int F = PI05_F32, BF = PI05_BF16;
+  get_param(e, VT + "embeddings.patch_embedding.weight", F, W * pp, &e.patch_w, &miss);
+  get_param(e, VT + "embeddings.patch_embedding.bias", F, W, &e.patch_b, &miss);
+  get_param(e, VT + "embeddings.position_embedding.weight", F, e.T * W, &e.pos_emb, &miss);
+  e.vit.resize(c.vit_depth);
+  for (int l = 0; l < c.vit_depth; ++l) {
+    const std::string Lp = VT + "encoder.layers." + std::to_string(l) + ".";
+    VitLayerP& p = e.vit[l];
+    get_param(e, Lp + "layer_norm1.weight", BF, W, &p.ln1_w, &miss);
+    get_param(e, Lp + "layer_norm1.bias", BF, W, &p.ln1_b, &miss);
+    get_param(e, Lp + "layer_norm2.weight", BF, W, &p.ln2_w, &miss);
+    get_param(e, Lp + "layer_norm2.bias", BF, W, &p.ln2_b, &miss);
+    get_param(e, Lp + "self_attn.q_proj.weight", BF, W * W, &p.q_w, &miss);
+    get_param(e, Lp + "self_attn.k_proj.weight", BF, W * W, &p.k_w, &miss);
+    get_param(e, Lp + "self_attn.v_proj.weight", BF, W * W, &p.v_w, &miss);
+    get_param(e, Lp + "self_attn.q_proj.bias", BF, W, &p.q_b, &miss);
+    get_param(e, Lp + "self_attn.k_proj.bias", BF, W, &p.k_b, &miss);
+    get_param(e, Lp + "self_attn.v_proj.bias", BF, W, &p.v_b, &miss);
+    get_param(e, Lp + "self_attn.out_proj.weight", BF, W * W, &p.out_w, &miss);
+    get_param(e, Lp + "self_attn.out_proj.bias", BF, W, &p.out_b, &miss);
+    get_param(e, Lp + "mlp.fc1.weight", BF, static_cast<int64_t>(c.vit_mlp_dim) * W, &p.fc1_w, &miss);
+    get_param(e, Lp + "mlp.fc1.bias", BF, c.vit_mlp_dim, &p.fc1_b, &miss);
+    get_param(e, Lp + "mlp.fc2.weight", BF, static_cast<int64_t>(c.vit_mlp_dim) * W, &p.fc2_w, &miss);
+    get_param(e, Lp + "mlp.fc2.bias", BF, W, &p.fc2_b, &miss);
+    if (p.q_w.data && p.k_w.data && p.v_w.data &&
+        !(contiguous_after(p.q_w, p.k_w, 2) && contiguous_after(p.k_w, p.v_w, 2) && contiguous_after(p.q_b, p.k_b, 2) &&
+          contiguous_after(p.k_b, p.v_b, 2)))
+      contig += Lp + "self_attn.{q,k,v}_proj ";
+  }
+  get_param(e, VT + "post_layernorm.weight", BF, W, &e.post_ln_w, &miss);
+  get_param(e, VT + "post_layernorm.bias", BF, W, &e.post_ln_b, &miss);
+  get_param(e, PWE + "paligemma.model.multi_modal_projector.linear.weight", BF, D * W, &e.proj_w, &miss);
+  get_param(e, PWE + "paligemma.model.multi_modal_projector.linear.bias", BF, D, &e.proj_b, &miss);
+  get_param(e, LM + "embed_tokens.weight", BF, static_cast<int64_t>(c.vocab_size) * D, &e.embed, &miss);
+
+  for (int s = 0; s < 2; ++s) {
+    const pi05_gemma_cfg& g = s == 0 ? c.paligemma : c.expert;
+    std::vector<GemmaLayerP>& Lv = s == 0 ? e.pg : e.ex;
+    const std::string pre = s == 0 ? LM : EX;
+    const int64_t w = g.width, hq = static_cast<int64_t>(g.num_heads) * g.head_dim,
+                  hk = static_cast<int64_t>(g.num_kv_heads) * g.head_dim;
+    Lv.resize(g.depth);
+    for (int l = 0; l < g.depth; ++l) {
+      const std::string Lp = pre + "layers." + std::to_string(l) + ".";
+      GemmaLayerP& p = Lv[l];
+      get_param(e, Lp + "self_attn.q_proj.weight", BF, hq * w, &p.q_w, &miss);
+      get_param(e, Lp + "self_attn.k_proj.weight", BF, hk * w, &p.k_w, &miss);
+      get_param(e, Lp + "self_attn.v_proj.weight", BF, hk * w, &p.v_w, &miss);
+      get_param(e, Lp + "self_attn.o_proj.weight", BF, w * hq, &p.o_w, &miss);
+      get_param(e, Lp + "mlp.gate_proj.weight", BF, static_cast<int64_t>(g.mlp_dim) * w, &p.gate_w, &miss);
+      get_param(e, Lp + "mlp.up_proj.weight", BF, static_cast<int64_t>(g.mlp_dim) * w, &p.up_w, &miss);
+      get_param(e, Lp + "mlp.down_proj.weight", BF, static_cast<int64_t>(g.mlp_dim) * w, &p.down_w, &miss);
+      if (s == 0) {
+        get_param(e, Lp + "input_layernorm.weight", F, w, &p.in_w, &miss);
+        get_param(e, Lp + "post_attention_layernorm.weight", F, w, &p.post_w, &miss);
+      } else {
+        get_param(e, Lp + "input_layernorm.dense.weight", F, 3 * w * w, &p.in_dw, &miss);
+        get_param(e, Lp + "input_layernorm.dense.bias", F, 3 * w, &p.in_db, &miss);
+        get_param(e, Lp + "post_attention_layernorm.dense.weight", F, 3 * w * w, &p.post_dw, &miss);
+        get_param(e, Lp + "post_attention_layernorm.dense.bias", F, 3 * w, &p.post_db, &miss);
+      }
+      if (p.q_w.data && p.k_w.data && p.v_w.data &&
+          !(contiguous_after(p.q_w, p.k_w, 2) && contiguous_after(p.k_w, p.v_w, 2)))
+        contig += Lp + "self_attn.{q,k,v}_proj ";
+      if (p.gate_w.data && p.up_w.data && !contiguous_after(p.gate_w, p.up_w, 2)) contig += Lp + "mlp.{gate,up}_proj ";
+    }
+  }
+  get_param(e, LM + "norm.weight", F, D, &e.pg_norm_w, &miss);
+  get_param(e, EX + "norm.dense.weight", F, 3 * E * E, &e.ex_norm_dw, &miss);
+  get_param(e, EX + "norm.dense.bias", F, 3 * E, &e.ex_norm_db, &miss);
+  get_param(e, "action_in_proj.weight", F, E * c.action_dim, &e.ain_w, &miss);
+  get_param(e, "action_in_proj.bias", F, E, &e.ain_b, &miss);
+  get_param(e, "action_out_proj.weight", F, E * c.action_dim, &e.aout_w, &miss);
+  get_param(e, "action_out_proj.bias", F, c.action_dim, &e.aout_b, &miss);
+  get_param(e, "time_mlp_in.weight", F, E * E, &e.tin_w, &miss);
+  get_param(e, "time_mlp_in.bias", F, E, &e.tin_b, &miss);
+  get_param(e, "time_mlp_out.weight", F, E * E, &e.tout_w, &miss);
+  get_param(e, "time_mlp_out.bias", F, E, &e.tout_b, &miss);
+  if (c.value_head) {
+    get_param(e, "value_head.0.weight", F, E * E, &e.vh0_w, &miss);
+    get_param(e, "value_head.0.bias", F, E, &e.vh0_b, &miss);
+    get_param(e, "value_head.2.weight", F, E * E, &e.vh2_w, &miss);
+    get_param(e, "value_head.2.bias", F, E, &e.vh2_b, &miss);
+    get_param(e, "value_head.4.weight", F, E, &e.vh4_w, &miss);
+    get_param(e, "value_head.4.bias", F, 1, &e.vh4_b, &miss);
+  }
+  if (!miss.empty() || !contig.empty()) {
+    snprintf(e.err, sizeof(e.err), "bind_params: missing/mismatched: [%s] not contiguous (fused arenas required): [%s]",
+             miss.c_str(), contig.c_str());
+    set_error(e.err);
+    return 7;
+  }
+  if (c.paligemma.num_kv_heads != 1 || c.expert.num_kv_heads != 1 || c.paligemma.head_dim != c.expert.head_dim ||
+      c.paligemma.num_heads != c.expert.num_heads || c.paligemma.depth != c.expert.depth) {
+    snprintf(e.err, sizeof(e.err), "unsupported attention geometry (reference hard-codes 8 q heads / 1 kv head)");
+    set_error(e.err);
+    return 7;
+  }
+  e.bound = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward pieces
+// ------------------------------------------------------------------------------------------------------------
+// SigLIP tower + projector for all NI*B images at once (row-independent, so identical to the reference's
+// per-camera calls, pi0_pytorch.py:197-202); writes image tokens straight into prefix_embs.
+int vision_forward(Engine& e, const float* images, int B, bf16* prefix_embs) {
+  const pi05_config& c = e.cfg;
+  cudaStream_t st = e.stream;
+  const int nimg = e.NI * B, T = e.T, W = e.W, VH = e.VH, vhd = e.vhd;
+  const int Mv = nimg * T;
+  const float ln_eps = 1e-6f;
+  patch_embed_fwd(images, e.patch_w.d<float>(), e.patch_b.d<float>(), e.pos_emb.d<float>(), e.vit_x0, nimg,
+                  c.image_size, c.vit_patch, W, st);
+  add_tap(e, "vit_embed", e.vit_x0, static_cast<int64_t>(Mv) * W, PI05_BF16);
+  for (int l = 0; l < c.vit_depth; ++l) {
+    const VitLayerP& p = e.vit[l];
+    VitLayerA& a = e.va[l];
+    layernorm_fwd(a.x_in, p.ln1_w.d<bf16>(), p.ln1_b.d<bf16>(), a.h1, a.mean1, a.rstd1, Mv, W, ln_eps, st);
+    {  // fused q|k|v projection (+bias)
+      GemmArgs g = mk_gemm(Mv, 3 * W, W, a.h1, W, p.q_w.data, W, a.qkv, 3 * W, EPI_BIAS);
+      g.bias = p.q_b.data;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    {  // scores[img, head] = bf(bf(Q K^T) * hd^-1/2)   (modeling_siglip.py:333)
+      GemmArgs g = mk_gemm(T, T, vhd, a.qkv, 3 * W, a.qkv + W, 3 * W, a.P, T, EPI_SCALE);
+      g.batch = nimg * VH;
+      g.batch_inner = VH;
+      g.a_batch_stride = vhd;
+      g.a_batch_stride1 = static_cast<int64_t>(T) * 3 * W;
+      g.b_batch_stride = vhd;
+      g.b_batch_stride1 = static_cast<int64_t>(T) * 3 * W;
+      g.d_batch_stride = static_cast<int64_t>(T) * T;
+      g.d_batch_stride1 = static_cast<int64_t>(VH) * T * T;
+      g.scale = 1.0f / sqrtf(static_cast<float>(vhd));
+      g.block_n = (T > 128) ? 256 : 128;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    softmax_fwd(a.P, T, T, nimg * VH, T, 0, nullptr, nullptr, 1, st);
+    {  // attn[img, t, head, :] = P V
+      GemmArgs g = mk_gemm(T, vhd, T, a.P, T, a.qkv + 2 * W, 3 * W, a.attn, W, EPI_STORE);
+      g.b_major = 1;
+      g.batch = nimg * VH;
+      g.batch_inner = VH;
+      g.a_batch_stride = static_cast<int64_t>(T) * T;
+      g.a_batch_stride1 = static_cast<int64_t>(VH) * T * T;
+      g.b_batch_stride = vhd;
+      g.b_batch_stride1 = static_cast<int64_t>(T) * 3 * W;
+      g.d_batch_stride = vhd;
+      g.d_batch_stride1 = static_cast<int64_t>(T) * W;
+      g.block_n = 128;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    {  // out_proj + bias + residual
+      GemmArgs g = mk_gemm(Mv, W, W, a.attn, W, p.out_w.data, W, a.x_mid, W, EPI_RES);
+      g.bias = p.out_b.data;
+      g.res = a.x_in;
+      g.ldres = W;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    layernorm_fwd(a.x_mid, p.ln2_w.d<bf16>(), p.ln2_b.d<bf16>(), a.h2, a.mean2, a.rstd2, Mv, W, ln_eps, st);
+    {  // fc1 + bias + gelu_tanh
+      GemmArgs g = mk_gemm(Mv, c.vit_mlp_dim, W, a.h2, W, p.fc1_w.data, W, a.pre, c.vit_mlp_dim, EPI_BIAS_GELU);
+      g.bias = p.fc1_b.data;
+      g.D2 = a.act;
+      g.ldd2 = c.vit_mlp_dim;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    {  // fc2 + bias + residual
+      GemmArgs g = mk_gemm(Mv, W, c.vit_mlp_dim, a.act, c.vit_mlp_dim, p.fc2_w.data, c.vit_mlp_dim, a.x_out, W, EPI_RES);
+      g.bias = p.fc2_b.data;
+      g.res = a.x_mid;
+      g.ldres = W;
+      CHECK_RC(engine_gemm(e, g));
+    }
+    if (e.taps_enabled) {
+      char nm[64];
+      snprintf(nm, sizeof(nm), "vit_layer%d", l);
+      add_tap(e, nm, a.x_out, static_cast<int64_t>(Mv) * W, PI05_BF16);
+    }
+  }
+  const bf16* xl = c.vit_depth > 0 ? e.va[c.vit_depth - 1].x_out : e.vit_x0;
+  layernorm_fwd(xl, e.post_ln_w.d<bf16>(), e.post_ln_b.d<bf16>(), e.vit_post, e.vit_post_mean, e.vit_post_rstd, Mv, W,
+                ln_eps, st);
+  {  // projector (+bias), scattered into prefix_embs[b, n*T + t, :]  (z0 = b, z1 = image index n)
+    GemmArgs g = mk_gemm(T, e.D, W, e.vit_post, W, e.proj_w.data, W, prefix_embs, e.D, EPI_BIAS);
+    g.bias = e.proj_b.data;
+    g.batch = nimg;
+    g.batch_inner = B;
+    g.a_batch_stride = static_cast<int64_t>(T) * W;
+    g.a_batch_stride1 = static_cast<int64_t>(B) * T * W;
+    g.d_batch_stride = static_cast<int64_t>(e.P) * e.D;
+    g.d_batch_stride1 = static_cast<int64_t>(T) * e.D;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  return 0;
+}
+
+// embed_prefix (pi0_pytorch.py:186-235) + masks / positions (:342-343)
+int prefix_forward(Engine& e, const pi05_batch* b) {
+  const int B = b->batch;
+  prefix_meta(b->image_masks, b->token_mask, B, e.NI, e.T, e.L, e.pad, e.pos, e.nvalid, e.stream);
+  bf16* prefix_embs = e.a1[0].x_in;
+  CHECK_RC(vision_forward(e, b->images, B, prefix_embs));
+  embed_tokens_fwd(b->tokens, e.embed.d<bf16>(), prefix_embs, B, e.L, e.D, static_cast<int64_t>(e.P) * e.D, e.NI * e.T,
+                   static_cast<float>(sqrt(static_cast<double>(e.D))), e.stream);
+  add_tap(e, "prefix_embs", prefix_embs, static_cast<int64_t>(B) * e.P * e.D, PI05_BF16);
+  return 0;
+}
+
+// embed_suffix, pi05 branch (pi0_pytorch.py:237-314) + all adaRMS modulations (modeling_gemma.py:88)
+int suffix_frontend(Engine& e, const float* x_t, const float* time, int B) {
+  cudaStream_t st = e.stream;
+  const int E = e.E, A = e.A, M2 = B * A, depth = e.cfg.paligemma.depth;
+  time_embedding(time, e.time_scaling, e.temb, B, E / 2, st);
+  linear_f32(x_t, e.ain_w.d<float>(), e.ain_b.d<float>(), e.aemb32, M2, E, e.cfg.action_dim, st);
+  cast_f32_to_bf16(e.aemb32, e.a2[0].x_in, static_cast<int64_t>(M2) * E, st);
+  linear_f32(e.temb, e.tin_w.d<float>(), e.tin_b.d<float>(), e.t1, B, E, E, st);
+  silu_fwd(e.t1, e.t1s, static_cast<int64_t>(B) * E, st);
+  linear_f32(e.t1s, e.tout_w.d<float>(), e.tout_b.d<float>(), e.t2, B, E, E, st);
+  silu_fwd(e.t2, e.cond, static_cast<int64_t>(B) * E, st);
+  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
+  for (int l = 0; l < depth; ++l) {
+    linear_f32(e.cond, e.ex[l].in_dw.d<float>(), e.ex[l].in_db.d<float>(), e.mods + (2 * l) * ms, B, 3 * E, E, st);
+    linear_f32(e.cond, e.ex[l].post_dw.d<float>(), e.ex[l].post_db.d<float>(), e.mods + (2 * l + 1) * ms, B, 3 * E, E,
+               st);
+  }
+  linear_f32(e.cond, e.ex_norm_dw.d<float>(), e.ex_norm_db.d<float>(), e.mods + (2 * depth) * ms, B, 3 * E, E, st);
+  add_tap(e, "suffix_embs", e.a2[0].x_in, static_cast<int64_t>(M2) * E, PI05_BF16);
+  add_tap(e, "adarms_cond", e.cond, static_cast<int64_t>(B) * E, PI05_F32);
+  return 0;
+}
+
+// One joint layer (gemma_pytorch.py:158-238).
+int joint_layer_forward(Engine& e, int l, int B) {
+  cudaStream_t st = e.stream;
+  const pi05_config& c = e.cfg;
+  const int P = e.P, A = e.A, S = e.S, D = e.D, E = e.E, H = e.H, hd = e.hd;
+  const int M1 = B * P, M2 = B * A, QW = (H + 2) * hd;
+  const float eps = 1e-6f;
+  GemmaLayerA &p1 = e.a1[l], &p2 = e.a2[l];
+  const GemmaLayerP &w1 = e.pg[l], &w2 = e.ex[l];
+  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
+  const float* mod_in = e.mods + (2 * l) * ms;
+  const float* mod_post = e.mods + (2 * l + 1) * ms;
+  bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
+
+  // input norms
+  rmsnorm_fwd(p1.x_in, w1.in_w.d<float>(), nullptr, 0, p1.n1, p1.rstd1, nullptr, M1, D, eps, st);
+  rmsnorm_fwd(p2.x_in, nullptr, mod_in, A, p2.n1, p2.rstd1, p2.gate1, M2, E, eps, st);
+  // fused q|k|v projections
+  CHECK_RC(engine_gemm(e, mk_gemm(M1, QW, D, p1.n1, D, w1.q_w.data, D, p1.qkv, QW, EPI_STORE)));
+  CHECK_RC(engine_gemm(e, mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE)));
+  // RoPE + concat along the sequence (gemma_pytorch.py:181-195)
+  rope_pack_fwd(p1.qkv, P, H, hd, e.pos, e.nvalid, 0, e.rope_cos, e.rope_sin, p1.Q, Kc, Vc, 0, S, B, st);
+  rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
+  const float scaling = 1.0f / sqrtf(static_cast<float>(hd));
+  // scores: prefix queries see prefix keys; suffix queries see everything (pi0_pytorch.py:52-81)
+  {
+    GemmArgs g = mk_gemm(P * H, P, hd, p1.Q, hd, Kc, hd, p1.P, e.Ppad, EPI_SCALE);
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(P) * H * hd;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(P) * H * e.Ppad;
+    g.scale = scaling;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g = mk_gemm(A * H, S, hd, p2.Q, hd, Kc, hd, p2.P, e.Spad, EPI_SCALE);
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(A) * H * hd;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(A) * H * e.Spad;
+    g.scale = scaling;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  softmax_fwd(p1.P, e.Ppad, P * H, B, P, P, e.pad, e.pad, H, st);
+  softmax_fwd(p2.P, e.Spad, A * H, B, S, P, e.pad, nullptr, H, st);
+  {  // O = P V  (V stored [keys, hd] -> N-major B operand)
+    GemmArgs g = mk_gemm(P * H, hd, P, p1.P, e.Ppad, Vc, hd, p1.O, hd, EPI_STORE);
+    g.b_major = 1;
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(P) * H * e.Ppad;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(P) * H * hd;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g = mk_gemm(A * H, hd, S, p2.P, e.Spad, Vc, hd, p2.O, hd, EPI_STORE);
+    g.b_major = 1;
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(A) * H * e.Spad;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(A) * H * hd;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {  // o_proj + (gated) residual
+    GemmArgs g = mk_gemm(M1, D, H * hd, p1.O, H * hd, w1.o_w.data, H * hd, p1.x_mid, D, EPI_RES);
+    g.res = p1.x_in;
+    g.ldres = D;
+    CHECK_RC(engine_gemm(e, g));
+    GemmArgs g2 = mk_gemm(M2, E, H * hd, p2.O, H * hd, w2.o_w.data, H * hd, p2.x_mid, E, EPI_RES);
+    g2.res = p2.x_in;
+    g2.ldres = E;
+    g2.gate = p2.gate1;
+    g2.gate_rows = A;
+    g2.ldgate = E;
+    g2.D2 = p2.o_lin;
+    g2.ldd2 = E;
+    CHECK_RC(engine_gemm(e, g2));
+  }
+  // post-attention norms
+  rmsnorm_fwd(p1.x_mid, w1.post_w.d<float>(), nullptr, 0, p1.n2, p1.rstd2, nullptr, M1, D, eps, st);
+  rmsnorm_fwd(p2.x_mid, nullptr, mod_post, A, p2.n2, p2.rstd2, p2.gate2, M2, E, eps, st);
+  {  // GeGLU up-projection (fused gate|up weight) then down-projection + (gated) residual
+    GemmArgs g = mk_gemm(M1, c.paligemma.mlp_dim, D, p1.n2, D, w1.gate_w.data, D, p1.GU, 2 * c.paligemma.mlp_dim,
+                         EPI_GEGLU);
+    g.D2 = p1.Hh;
+    g.ldd2 = c.paligemma.mlp_dim;
+    CHECK_RC(engine_gemm(e, g));
+    GemmArgs g2 = mk_gemm(M2, c.expert.mlp_dim, E, p2.n2, E, w2.gate_w.data, E, p2.GU, 2 * c.expert.mlp_dim, EPI_GEGLU);
+    g2.D2 = p2.Hh;
+    g2.ldd2 = c.expert.mlp_dim;
+    CHECK_RC(engine_gemm(e, g2));
+  }
+  {
+    GemmArgs g = mk_gemm(M1, D, c.paligemma.mlp_dim, p1.Hh, c.paligemma.mlp_dim, w1.down_w.data, c.paligemma.mlp_dim,
+                         p1.x_out, D, EPI_RES);
+    g.res = p1.x_mid;
+    g.ldres = D;
+    CHECK_RC(engine_gemm(e, g));
+    GemmArgs g2 =
+        mk_gemm(M2, E, c.expert.mlp_dim, p2.Hh, c.expert.mlp_dim, w2.down_w.data, c.expert.mlp_dim, p2.x_out, E, EPI_RES);
+    g2.res = p2.x_mid;
+    g2.ldres = E;
+    g2.gate = p2.gate2;
+    g2.gate_rows = A;
+    g2.ldgate = E;
+    g2.D2 = p2.d_lin;
+    g2.ldd2 = E;
+    CHECK_RC(engine_gemm(e, g2));
+  }
+  if (e.taps_enabled) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "layer%d_prefix", l);
+    add_tap(e, nm, p1.x_out, static_cast<int64_t>(M1) * D, PI05_BF16);
+    snprintf(nm, sizeof(nm), "layer%d_suffix", l);
+    add_tap(e, nm, p2.x_out, static_cast<int64_t>(M2) * E, PI05_BF16);
+  }
+  return 0;
+}
+
+int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                   float* loss_out, cudaStream_t st) {
+  if (!e.bound) {
+    snprintf(e.err, sizeof(e.err), "pi05_forward: parameters not bound");
+    set_error(e.err);
+    return 8;
+  }
+  if (b->batch <= 0 || b->batch > e.Bmax) {
+    snprintf(e.err, sizeof(e.err), "pi05_forward: batch %d outside [1, %d]", b->batch, e.Bmax);
+    set_error(e.err);
+    return 8;
+  }
+  e.stream = st;
+  e.taps.clear();
+  const int B = b->batch;
+  e.B = B;
+  e.batch_copy = *b;
+  const pi05_config& c = e.cfg;
+  const int depth = c.paligemma.depth;
+  const int M2 = B * e.A;
+  flow_inputs(actions, noise, time, e.x_t, e.u_t, B, e.A * c.action_dim, st);
+  CHECK_RC(prefix_forward(e, b));
+  CHECK_RC(suffix_frontend(e, e.x_t, time, B));
+  for (int l = 0; l < depth; ++l) CHECK_RC(joint_layer_forward(e, l, B));
+  const int64_t ms = static_cast<int64_t>(B) * 3 * e.E;
+  const bf16* x1f = depth > 0 ? e.a1[depth - 1].x_out : e.a1[0].x_in;
+  const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;
+  if (e.taps_enabled) {
+    rmsnorm_fwd(x1f, e.pg_norm_w.d<float>(), nullptr, 0, e.prefix_out, e.rstd_f1, nullptr, B * e.P, e.D, 1e-6f, st);
+    add_tap(e, "prefix_out", e.prefix_out, static_cast<int64_t>(B) * e.P * e.D, PI05_BF16);
+  }
+  rmsnorm_fwd(x2f, nullptr, e.mods + (2 * depth) * ms, e.A, e.suffix_out, e.rstd_f2, nullptr, M2, e.E, 1e-6f, st);
+  add_tap(e, "suffix_out", e.suffix_out, static_cast<int64_t>(M2) * e.E, PI05_BF16);
+  cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * e.E, st);
+  linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, c.action_dim, e.E, st);
+  add_tap(e, "v_t", e.v_t, static_cast<int64_t>(M2) * c.action_dim, PI05_F32);
+  flow_loss(e.u_t, e.v_t, loss_out, static_cast<int64_t>(M2) * c.action_dim, st);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(e.err, sizeof(e.err), "pi05_forward: %s", cudaGetErrorString(ce));
+    set_error(e.err);
+    return 9;
+  }
+  return 0;
+}
+
+}  // namespace pi05

@@ -1,0 +1,138 @@
+// Engine state for the pi0.5 forward / backward / decode path (see engine.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pi05.h"
+#include "kernels.h"
+
+namespace pi05 {
+
+struct PRef {
+  void* data = nullptr;
+  void* grad = nullptr;
+  int dtype = 0;
+  int64_t numel = 0;
+  template <class T>
+  T* d() const { return static_cast<T*>(data); }
+  template <class T>
+  T* g() const { return static_cast<T*>(grad); }
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  size_t cap = 0;
+  bool dry = true;
+  bool overflow = false;
+  void* alloc(size_t bytes) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = dry ? nullptr : static_cast<void*>(base + off);
+    off += bytes;
+    if (!dry && off > cap) overflow = true;
+    return p;
+  }
+  template <class T>
+  T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+};
+
+struct VitLayerP {
+  PRef ln1_w, ln1_b, q_w, k_w, v_w, q_b, k_b, v_b, out_w, out_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+};
+struct VitLayerA {
+  bf16 *x_in, *h1, *qkv, *P, *attn, *x_mid, *h2, *pre, *act, *x_out;
+  float *mean1, *rstd1, *mean2, *rstd2;
+};
+
+struct GemmaLayerP {
+  PRef q_w, k_w, v_w, o_w, gate_w, up_w, down_w;
+  PRef in_w, post_w;                          // plain RMSNorm weights (fp32)
+  PRef in_dw, in_db, post_dw, post_db;        // adaptive dense (fp32)
+};
+struct GemmaLayerA {  // per stream
+  bf16 *x_in, *n1, *qkv, *Q, *P, *O, *o_lin, *x_mid, *n2, *GU, *Hh, *d_lin, *x_out;
+  bf16 *gate1, *gate2;
+  float *rstd1, *rstd2;
+};
+
+struct Tap {
+  const void* ptr;
+  int64_t numel;
+  int dtype;
+};
+
+struct Engine {
+  pi05_config cfg{};
+  int device = 0;
+  // derived sizes
+  int T = 0, NI = 0, L = 0, P = 0, A = 0, S = 0, Spad = 0, Ppad = 0;
+  int D = 0, E = 0, W = 0, H = 0, hd = 0, VH = 0, vhd = 0, Bmax = 0;
+  bool train = false;
+
+  std::map<std::string, PRef> params;
+  bool bound = false;
+  // resolved parameters
+  PRef patch_w, patch_b, pos_emb, post_ln_w, post_ln_b, proj_w, proj_b, embed;
+  std::vector<VitLayerP> vit;
+  std::vector<GemmaLayerP> pg, ex;  // paligemma LM, expert
+  PRef pg_norm_w, ex_norm_dw, ex_norm_db;
+  PRef ain_w, ain_b, aout_w, aout_b, tin_w, tin_b, tout_w, tout_b;
+  PRef vh0_w, vh0_b, vh2_w, vh2_b, vh4_w, vh4_b;
+
+  // workspace
+  Arena arena;
+  // constant tables
+  bf16 *rope_cos = nullptr, *rope_sin = nullptr;  // [S+1, hd/2]
+  double* time_scaling = nullptr;                  // [E/2]
+  // per-call state
+  int B = 0;                 // batch of the last forward / prefill
+  const pi05_batch* last_batch = nullptr;
+  pi05_batch batch_copy{};
+  uint8_t* pad = nullptr;    // [B, P]
+  int *pos = nullptr, *nvalid = nullptr;
+  // vision
+  bf16* vit_x0 = nullptr;
+  std::vector<VitLayerA> va;
+  bf16* vit_post = nullptr;
+  float *vit_post_mean = nullptr, *vit_post_rstd = nullptr;
+  // streams
+  std::vector<GemmaLayerA> a1, a2;
+  bf16 *Kc = nullptr, *Vc = nullptr;  // per layer [depth][B, S, hd] (train) or KV cache (decode)
+  std::vector<bf16*> Kl, Vl;
+  bf16 *prefix_out = nullptr, *suffix_out = nullptr;
+  float* rstd_f1 = nullptr;
+  float* rstd_f2 = nullptr;
+  // suffix front-end (fp32)
+  float *x_t = nullptr, *u_t = nullptr, *temb = nullptr, *aemb32 = nullptr, *t1 = nullptr, *t1s = nullptr, *t2 = nullptr,
+        *cond = nullptr, *mods = nullptr, *so32 = nullptr, *v_t = nullptr, *timevec = nullptr;
+  // backward scratch
+  bf16 *g_x1 = nullptr, *g_x1b = nullptr, *g_x2 = nullptr, *g_x2b = nullptr, *g_big = nullptr, *g_big2 = nullptr,
+       *g_t1 = nullptr, *g_t2 = nullptr, *g_t3 = nullptr, *g_P = nullptr, *g2_do = nullptr, *g2_big = nullptr,
+       *g2_big2 = nullptr, *g2_t1 = nullptr, *g2_t2 = nullptr, *g2_t3 = nullptr;
+  float *g_dK = nullptr, *g_dV = nullptr, *g_dmods = nullptr, *g_f32a = nullptr, *g_f32b = nullptr, *g_f32c = nullptr,
+        *g_acc = nullptr, *g_embed_scratch = nullptr;
+  int* g_first = nullptr;
+  size_t g_acc_elems = 0;
+
+  bool taps_enabled = false;
+  std::map<std::string, Tap> taps;
+  cudaStream_t stream = nullptr;
+  char err[1024] = "";
+};
+
+// engine.cu
+int engine_plan(Engine& e, bool dry);
+int engine_resolve_params(Engine& e);
+int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                   float* loss_out, cudaStream_t st);
+// engine_bwd.cu
+int engine_backward(Engine& e, const float* dloss, cudaStream_t st);
+// engine_decode.cu
+int engine_prefill(Engine& e, const pi05_batch* b, cudaStream_t st);
+int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_out, cudaStream_t st);
+
+}  // namespace pi05

@@ -1,0 +1,210 @@
+// Inference path: prefix pass that fills the per-layer KV cache, then the Euler denoise loop over the action
+// expert only.  Follows pi0_pytorch.py:375-419 (sample_actions), :421-461 (denoise_step),
+// gemma_pytorch.py:102-125 (single-stream branches) -> modeling_gemma.py:344-384,446-555.
+#include <cmath>
+#include <cstdio>
+
+#include "engine.h"
+#include "errors.h"
+#include "gemm.h"
+
+namespace pi05 {
+
+#define CHECK_RC(x)           \
+  do {                        \
+    int _rc = (x);            \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+int engine_gemm(Engine& e, const GemmArgs& a);
+GemmArgs mk_gemm(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, void* D, int64_t ldd,
+                 int epi);
+int prefix_forward(Engine& e, const pi05_batch* b);
+int suffix_frontend(Engine& e, const float* x_t, const float* time, int B);
+void add_tap(Engine& e, const char* name, const void* p, int64_t n, int dtype);
+
+// PaliGemma-only layer; K/V (post-RoPE K) go to the cache rows [0, P) (modeling_gemma.py:303-307).
+static int prefix_layer(Engine& e, int l, int B, bool kv_only) {
+  cudaStream_t st = e.stream;
+  const pi05_config& c = e.cfg;
+  const int P = e.P, S = e.S, D = e.D, H = e.H, hd = e.hd;
+  const int M1 = B * P, QW = (H + 2) * hd;
+  GemmaLayerA& p1 = e.a1[l];
+  const GemmaLayerP& w1 = e.pg[l];
+  bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
+  rmsnorm_fwd(p1.x_in, w1.in_w.d<float>(), nullptr, 0, p1.n1, p1.rstd1, nullptr, M1, D, 1e-6f, st);
+  CHECK_RC(engine_gemm(e, mk_gemm(M1, QW, D, p1.n1, D, w1.q_w.data, D, p1.qkv, QW, EPI_STORE)));
+  rope_pack_fwd(p1.qkv, P, H, hd, e.pos, e.nvalid, 0, e.rope_cos, e.rope_sin, p1.Q, Kc, Vc, 0, S, B, st);
+  if (kv_only) return 0;  // the last layer's output is never read by the decode loop
+  {
+    GemmArgs g = mk_gemm(P * H, P, hd, p1.Q, hd, Kc, hd, p1.P, e.Ppad, EPI_SCALE);
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(P) * H * hd;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(P) * H * e.Ppad;
+    g.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    CHECK_RC(engine_gemm(e, g));
+  }
+  softmax_fwd(p1.P, e.Ppad, P * H, B, P, P, e.pad, e.pad, H, st);
+  {
+    GemmArgs g = mk_gemm(P * H, hd, P, p1.P, e.Ppad, Vc, hd, p1.O, hd, EPI_STORE);
+    g.b_major = 1;
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(P) * H * e.Ppad;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(P) * H * hd;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g = mk_gemm(M1, D, H * hd, p1.O, H * hd, w1.o_w.data, H * hd, p1.x_mid, D, EPI_RES);
+    g.res = p1.x_in;
+    g.ldres = D;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  rmsnorm_fwd(p1.x_mid, w1.post_w.d<float>(), nullptr, 0, p1.n2, p1.rstd2, nullptr, M1, D, 1e-6f, st);
+  {
+    GemmArgs g = mk_gemm(M1, c.paligemma.mlp_dim, D, p1.n2, D, w1.gate_w.data, D, p1.GU, 2 * c.paligemma.mlp_dim,
+                         EPI_GEGLU);
+    g.D2 = p1.Hh;
+    g.ldd2 = c.paligemma.mlp_dim;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g = mk_gemm(M1, D, c.paligemma.mlp_dim, p1.Hh, c.paligemma.mlp_dim, w1.down_w.data, c.paligemma.mlp_dim,
+                         p1.x_out, D, EPI_RES);
+    g.res = p1.x_mid;
+    g.ldres = D;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  return 0;
+}
+
+// Expert-only layer reading the cache: K,V = cat(cache, new) (modeling_gemma.py:308-310).
+static int suffix_layer(Engine& e, int l, int B) {
+  cudaStream_t st = e.stream;
+  const pi05_config& c = e.cfg;
+  const int P = e.P, A = e.A, S = e.S, E = e.E, H = e.H, hd = e.hd;
+  const int M2 = B * A, QW = (H + 2) * hd;
+  GemmaLayerA& p2 = e.a2[l];
+  const GemmaLayerP& w2 = e.ex[l];
+  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
+  bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
+  rmsnorm_fwd(p2.x_in, nullptr, e.mods + (2 * l) * ms, A, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
+  CHECK_RC(engine_gemm(e, mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE)));
+  rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
+  {
+    GemmArgs g = mk_gemm(A * H, S, hd, p2.Q, hd, Kc, hd, p2.P, e.Spad, EPI_SCALE);
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(A) * H * hd;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(A) * H * e.Spad;
+    g.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    CHECK_RC(engine_gemm(e, g));
+  }
+  softmax_fwd(p2.P, e.Spad, A * H, B, S, P, e.pad, nullptr, H, st);
+  {
+    GemmArgs g = mk_gemm(A * H, hd, S, p2.P, e.Spad, Vc, hd, p2.O, hd, EPI_STORE);
+    g.b_major = 1;
+    g.batch = B;
+    g.a_batch_stride = static_cast<int64_t>(A) * H * e.Spad;
+    g.b_batch_stride = static_cast<int64_t>(S) * hd;
+    g.d_batch_stride = static_cast<int64_t>(A) * H * hd;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g = mk_gemm(M2, E, H * hd, p2.O, H * hd, w2.o_w.data, H * hd, p2.x_mid, E, EPI_RES);
+    g.res = p2.x_in;
+    g.ldres = E;
+    g.gate = p2.gate1;
+    g.gate_rows = A;
+    g.ldgate = E;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  rmsnorm_fwd(p2.x_mid, nullptr, e.mods + (2 * l + 1) * ms, A, p2.n2, p2.rstd2, p2.gate2, M2, E, 1e-6f, st);
+  {
+    GemmArgs g = mk_gemm(M2, c.expert.mlp_dim, E, p2.n2, E, w2.gate_w.data, E, p2.GU, 2 * c.expert.mlp_dim, EPI_GEGLU);
+    g.D2 = p2.Hh;
+    g.ldd2 = c.expert.mlp_dim;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  {
+    GemmArgs g =
+        mk_gemm(M2, E, c.expert.mlp_dim, p2.Hh, c.expert.mlp_dim, w2.down_w.data, c.expert.mlp_dim, p2.x_out, E, EPI_RES);
+    g.res = p2.x_mid;
+    g.ldres = E;
+    g.gate = p2.gate2;
+    g.gate_rows = A;
+    g.ldgate = E;
+    CHECK_RC(engine_gemm(e, g));
+  }
+  return 0;
+}
+
+int engine_prefill(Engine& e, const pi05_batch* b, cudaStream_t st) {
+  if (!e.bound || b->batch <= 0 || b->batch > e.Bmax) {
+    snprintf(e.err, sizeof(e.err), "pi05_prefill: parameters not bound or batch %d outside [1, %d]", b->batch, e.Bmax);
+    set_error(e.err);
+    return 8;
+  }
+  e.stream = st;
+  e.taps.clear();
+  e.B = b->batch;
+  CHECK_RC(prefix_forward(e, b));
+  const int depth = e.cfg.paligemma.depth;
+  for (int l = 0; l < depth; ++l) CHECK_RC(prefix_layer(e, l, e.B, /*kv_only=*/l == depth - 1));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(e.err, sizeof(e.err), "pi05_prefill: %s", cudaGetErrorString(ce));
+    set_error(e.err);
+    return 9;
+  }
+  return 0;
+}
+
+int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_out, cudaStream_t st) {
+  if (!e.bound || e.B <= 0) {
+    snprintf(e.err, sizeof(e.err), "pi05_denoise: call pi05_prefill first");
+    set_error(e.err);
+    return 8;
+  }
+  e.stream = st;
+  const int B = e.B, A = e.A, E = e.E, ad = e.cfg.action_dim, depth = e.cfg.paligemma.depth;
+  const int M2 = B * A;
+  const int64_t n = static_cast<int64_t>(M2) * ad;
+  cudaMemcpyAsync(actions_out, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  // pi0_pytorch.py:401-418: dt and time are fp32 tensors; time is a running fp32 sum; loop while time >= -dt/2
+  const float dt = static_cast<float>(-1.0 / static_cast<double>(num_steps));
+  float time = 1.0f;
+  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
+  int step = 0;
+  while (time >= -dt / 2) {
+    fill_f32(e.timevec, time, B, st);  // time.expand(bsize), pi0_pytorch.py:407
+    CHECK_RC(suffix_frontend(e, actions_out, e.timevec, B));
+    for (int l = 0; l < depth; ++l) CHECK_RC(suffix_layer(e, l, B));
+    const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;
+    rmsnorm_fwd(x2f, nullptr, e.mods + (2 * depth) * ms, A, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
+    cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * E, st);
+    linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, ad, E, st);
+    if (e.taps_enabled && step == 0) add_tap(e, "v_t_step0", e.v_t, n, PI05_F32);
+    euler_step(actions_out, e.v_t, dt, n, st);
+    time = time + dt;
+    ++step;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(e.err, sizeof(e.err), "pi05_denoise: %s", cudaGetErrorString(ce));
+    set_error(e.err);
+    return 9;
+  }
+  return 0;
+}
+
+int engine_value(Engine& e, float* value_out, cudaStream_t st) {
+  (void)value_out;
+  (void)st;
+  snprintf(e.err, sizeof(e.err), "pi05_forward_value: value head not built in this round");
+  set_error(e.err);
+  return 10;
+}
+
+}  // namespace pi05

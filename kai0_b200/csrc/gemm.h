@@ -22,21 +22,25 @@ enum GemmEpilogue : int {
 struct GemmArgs {
   // Problem: for every batch index z: D[z][M,N] = A[z][M,K] * B[z][N,K]^T
   int M = 0, N = 0, K = 0, batch = 1;
+  // Two-level batch: z = z1 * batch_inner + z0 (batch_inner = 0 means "= batch", i.e. one level).  Every operand
+  // has a stride per level (elements); a 0 stride means the operand does not move along that level.
+  int batch_inner = 0;
   // Operands (bf16).  major 0: row-major [rows, K] (K contiguous).  major 1: row-major [K, rows] (rows contiguous).
   const void* A = nullptr;
   const void* B = nullptr;
   int a_major = 0, b_major = 0;
   int64_t lda = 0, ldb = 0;                      // elements between consecutive rows of the stored matrix
-  int64_t a_batch_stride = 0, b_batch_stride = 0;  // elements; 0 = operand shared by all batches
+  int64_t a_batch_stride = 0, b_batch_stride = 0;  // level-0 stride (elements); 0 = shared by all batches
+  int64_t a_batch_stride1 = 0, b_batch_stride1 = 0;  // level-1 stride
   // Output
   int epilogue = EPI_STORE;
   void* D = nullptr;
-  int64_t ldd = 0, d_batch_stride = 0;
-  void* D2 = nullptr;
-  int64_t ldd2 = 0, d2_batch_stride = 0;
+  int64_t ldd = 0, d_batch_stride = 0, d_batch_stride1 = 0;
+  void* D2 = nullptr;  // EPI_BIAS_GELU / EPI_GEGLU second output; EPI_RES: optional copy of the pre-gate value t
+  int64_t ldd2 = 0, d2_batch_stride = 0, d2_batch_stride1 = 0;
   const void* bias = nullptr;  // bf16 [N]
   const void* res = nullptr;   // bf16 [M, ldres]
-  int64_t ldres = 0, res_batch_stride = 0;
+  int64_t ldres = 0, res_batch_stride = 0, res_batch_stride1 = 0;
   const void* gate = nullptr;  // bf16 [ceil(M / gate_rows), ldgate]
   int gate_rows = 1;
   int64_t ldgate = 0;

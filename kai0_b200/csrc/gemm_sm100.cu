@@ -40,17 +40,17 @@ struct Cfg {
 };
 
 struct KParams {
-  int M, N, K, batch;
-  int a_mn, b_mn, a_batched, b_batched;
+  int M, N, K, batch, nz0;
+  int a_mn, b_mn, a_b0, a_b1, b_b0, b_b1;
   int num_m, num_n, num_kb;
   uint32_t idesc;
   void* D;
-  long long ldd, dbs;
+  long long ldd, dbs, dbs1;
   void* D2;
-  long long ldd2, d2bs;
+  long long ldd2, d2bs, d2bs1;
   const __nv_bfloat16* bias;
   const __nv_bfloat16* res;
-  long long ldres, resbs;
+  long long ldres, resbs, resbs1;
   const __nv_bfloat16* gate;
   int gate_rows;
   long long ldgate;
@@ -60,13 +60,15 @@ struct KParams {
 };
 
 struct TileCoord {
-  int z, m_blk, n_blk;
+  int z, z0, z1, m_blk, n_blk;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(int tile, const KParams& p) {
   const int per_batch = p.num_m * p.num_n;
   TileCoord c;
   c.z = tile / per_batch;
+  c.z1 = c.z / p.nz0;
+  c.z0 = c.z - c.z1 * p.nz0;
   const int t = tile - c.z * per_batch;
   const int group_span = GROUP_M * p.num_n;
   const int group = t / group_span;
@@ -177,8 +179,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const TileCoord tc = decode_tile(tile, p);
         const int m0 = tc.m_blk * BM;
         const int n0 = tc.n_blk * BN_OUT;
-        const int za = p.a_batched ? tc.z : 0;
-        const int zb = p.b_batched ? tc.z : 0;
+        const int za0 = p.a_b0 ? tc.z0 : 0, za1 = p.a_b1 ? tc.z1 : 0;
+        const int zb0 = p.b_b0 ? tc.z0 : 0, zb1 = p.b_b1 ? tc.z1 : 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
           const uint32_t full = full_bar0 + 8 * stage;
@@ -187,19 +189,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t sb = smem_b0 + stage * C::B_STAGE_BYTES;
           const int k0 = kb * BK;
           if (!p.a_mn) {
-            tma_load_3d(sa, &tma_a, full, k0, m0, za);
+            tma_load_4d(sa, &tma_a, full, k0, m0, za0, za1);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * (BK * 128), &tma_a, full, m0 + 64 * i, k0, za);
+            for (int i = 0; i < BM / 64; ++i) tma_load_4d(sa + i * (BK * 128), &tma_a, full, m0 + 64 * i, k0, za0, za1);
           }
           if (EPI == EPI_GEGLU) {
-            tma_load_3d(sb, &tma_b, full, k0, n0, zb);
-            tma_load_3d(sb + (BN / 2) * 128, &tma_b, full, k0, p.N + n0, zb);
+            tma_load_4d(sb, &tma_b, full, k0, n0, zb0, zb1);
+            tma_load_4d(sb + (BN / 2) * 128, &tma_b, full, k0, p.N + n0, zb0, zb1);
           } else if (!p.b_mn) {
-            tma_load_3d(sb, &tma_b, full, k0, n0, zb);
+            tma_load_4d(sb, &tma_b, full, k0, n0, zb0, zb1);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (BK * 128), &tma_b, full, n0 + 64 * i, k0, zb);
+            for (int i = 0; i < BN / 64; ++i) tma_load_4d(sb + i * (BK * 128), &tma_b, full, n0 + 64 * i, k0, zb0, zb1);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -290,16 +292,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               u[i] = uu;
               h[i] = a * uu;
             }
-            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd;
+            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.D) + tc.z0 * p.dbs + tc.z1 * p.dbs1 + static_cast<long long>(row) * p.ldd;
             store_bf16x32(d + col, nvalid, v);
             store_bf16x32(d + p.N + col, nvalid, u);
             __nv_bfloat16* d2 =
-                static_cast<__nv_bfloat16*>(p.D2) + tc.z * p.d2bs + static_cast<long long>(row) * p.ldd2;
+                static_cast<__nv_bfloat16*>(p.D2) + tc.z0 * p.d2bs + tc.z1 * p.d2bs1 + static_cast<long long>(row) * p.ldd2;
             store_bf16x32(d2 + col, nvalid, h);
           }
         } else if constexpr (EPI == EPI_F32) {
           if (row_ok) {
-            float* d = static_cast<float*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd + col;
+            float* d = static_cast<float*>(p.D) + tc.z0 * p.dbs + tc.z1 * p.dbs1 + static_cast<long long>(row) * p.ldd + col;
             if (p.accumulate) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -335,6 +337,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               }
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+              if (p.D2 != nullptr) {  // keep the pre-gate linear output for the backward of the gate
+                __nv_bfloat16* d2 = static_cast<__nv_bfloat16*>(p.D2) + tc.z0 * p.d2bs + tc.z1 * p.d2bs1 +
+                                    static_cast<long long>(row) * p.ldd2 + col;
+                store_bf16x32(d2, nvalid, v);
+              }
               if (p.gate != nullptr) {
                 float gt[32];
                 load_bf16x32(p.gate + static_cast<long long>(row / p.gate_rows) * p.ldgate + col, nvalid, gt);
@@ -342,18 +349,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] * gt[i]);
               }
               float rs[32];
-              load_bf16x32(p.res + tc.z * p.resbs + static_cast<long long>(row) * p.ldres + col, nvalid, rs);
+              load_bf16x32(p.res + tc.z0 * p.resbs + tc.z1 * p.resbs1 + static_cast<long long>(row) * p.ldres + col, nvalid, rs);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += rs[i];
             }
             __nv_bfloat16* d =
-                static_cast<__nv_bfloat16*>(p.D) + tc.z * p.dbs + static_cast<long long>(row) * p.ldd + col;
+                static_cast<__nv_bfloat16*>(p.D) + tc.z0 * p.dbs + tc.z1 * p.dbs1 + static_cast<long long>(row) * p.ldd + col;
             store_bf16x32(d, nvalid, v);
             if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_f(bf16_round(v[i]));
               __nv_bfloat16* d2 =
-                  static_cast<__nv_bfloat16*>(p.D2) + tc.z * p.d2bs + static_cast<long long>(row) * p.ldd2 + col;
+                  static_cast<__nv_bfloat16*>(p.D2) + tc.z0 * p.d2bs + tc.z1 * p.d2bs1 + static_cast<long long>(row) * p.ldd2 + col;
               store_bf16x32(d2, nvalid, v);
             }
           }
@@ -390,7 +397,8 @@ EncodeFn get_encode_fn() {
   return fn;
 }
 
-using TmapKey = std::tuple<const void*, int, long long, long long, long long, long long, long long, int>;
+using TmapKey = std::tuple<const void*, int, long long, long long, long long, long long, long long, long long,
+                           long long, int>;
 std::map<TmapKey, CUtensorMap>& tmap_cache() {
   static std::map<TmapKey, CUtensorMap> c;
   return c;
@@ -400,13 +408,14 @@ std::mutex& tmap_mutex() {
   return m;
 }
 
-// major 0: stored [rows, K] (K contiguous)  -> dims {K, rows, batch}, box {64, box_rows, 1}
-// major 1: stored [K, rows] (rows contiguous) -> dims {rows, K, batch}, box {64, 64, 1}
-bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, long long K, long long ld, long long batch,
-               long long batch_stride, int box_rows, char* err, int err_len) {
-  const bool batched = batch > 1 && batch_stride != 0;
-  const long long nb = batched ? batch : 1;
-  TmapKey key{ptr, major, rows, K, ld, nb, batch_stride, box_rows};
+// major 0: stored [rows, K] (K contiguous)  -> dims {K, rows, nz0, nz1}, box {64, box_rows, 1, 1}
+// major 1: stored [K, rows] (rows contiguous) -> dims {rows, K, nz0, nz1}, box {64, 64, 1, 1}
+// A batch level whose stride is 0 is collapsed to extent 1 (the kernel then passes coordinate 0).
+bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, long long K, long long ld, long long nz0,
+               long long bs0, long long nz1, long long bs1, int box_rows, char* err, int err_len) {
+  if (bs0 == 0) nz0 = 1;
+  if (bs1 == 0) nz1 = 1;
+  TmapKey key{ptr, major, rows, K, ld, nz0, bs0, nz1, bs1, box_rows};
   {
     std::lock_guard<std::mutex> g(tmap_mutex());
     auto it = tmap_cache().find(key);
@@ -420,10 +429,10 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, lon
     if (err) snprintf(err, err_len, "cuTensorMapEncodeTiled entry point unavailable");
     return false;
   }
-  cuuint64_t dims[3];
-  cuuint64_t strides[2];
-  cuuint32_t box[3];
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   if (major == 0) {
     dims[0] = K;
     dims[1] = rows;
@@ -435,22 +444,26 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, lon
     box[0] = 64;
     box[1] = BK;
   }
-  dims[2] = nb;
+  dims[2] = nz0;
+  dims[3] = nz1;
   box[2] = 1;
+  box[3] = 1;
   strides[0] = static_cast<cuuint64_t>(ld) * 2;
-  strides[1] = batched ? static_cast<cuuint64_t>(batch_stride) * 2 : strides[0] * dims[1];
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+  strides[1] = nz0 > 1 ? static_cast<cuuint64_t>(bs0) * 2 : strides[0] * dims[1];
+  strides[2] = nz1 > 1 ? static_cast<cuuint64_t>(bs1) * 2 : strides[1] * dims[2];
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
     if (err)
-      snprintf(err, err_len, "gemm operand not 16B aligned (ptr %p ld %lld batch_stride %lld)", ptr, ld, batch_stride);
+      snprintf(err, err_len, "gemm operand not 16B aligned (ptr %p ld %lld batch strides %lld %lld)", ptr, ld, bs0, bs1);
     return false;
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err)
-      snprintf(err, err_len, "cuTensorMapEncodeTiled failed (%d): major %d rows %lld K %lld ld %lld batch %lld bs %lld",
-               static_cast<int>(r), major, rows, K, ld, nb, batch_stride);
+      snprintf(err, err_len,
+               "cuTensorMapEncodeTiled failed (%d): major %d rows %lld K %lld ld %lld nz0 %lld bs0 %lld nz1 %lld bs1 %lld",
+               static_cast<int>(r), major, rows, K, ld, nz0, bs0, nz1, bs1);
     return false;
   }
   std::lock_guard<std::mutex> g(tmap_mutex());
@@ -531,9 +544,18 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   const long long b_rows = (a.epilogue == EPI_GEGLU) ? 2LL * a.N : a.N;
   const int b_box_rows = (a.epilogue == EPI_GEGLU) ? bn / 2 : bn;
 
+  const int nz0 = (a.batch_inner > 0) ? a.batch_inner : a.batch;
+  if (a.batch % nz0 != 0) {
+    if (err) snprintf(err, err_len, "gemm: batch %d not a multiple of batch_inner %d", a.batch, nz0);
+    return 1;
+  }
+  const int nz1 = a.batch / nz0;
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, a.A, a.a_major, a.M, a.K, a.lda, a.batch, a.a_batch_stride, BM, err, err_len)) return 4;
-  if (!make_tmap(&tb, a.B, a.b_major, b_rows, a.K, a.ldb, a.batch, a.b_batch_stride, b_box_rows, err, err_len))
+  if (!make_tmap(&ta, a.A, a.a_major, a.M, a.K, a.lda, nz0, a.a_batch_stride, nz1, a.a_batch_stride1, BM, err,
+                 err_len))
+    return 4;
+  if (!make_tmap(&tb, a.B, a.b_major, b_rows, a.K, a.ldb, nz0, a.b_batch_stride, nz1, a.b_batch_stride1, b_box_rows,
+                 err, err_len))
     return 4;
 
   KParams kp;
@@ -544,8 +566,11 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   kp.batch = a.batch;
   kp.a_mn = a.a_major;
   kp.b_mn = a.b_major;
-  kp.a_batched = (a.batch > 1 && a.a_batch_stride != 0) ? 1 : 0;
-  kp.b_batched = (a.batch > 1 && a.b_batch_stride != 0) ? 1 : 0;
+  kp.nz0 = nz0;
+  kp.a_b0 = (nz0 > 1 && a.a_batch_stride != 0) ? 1 : 0;
+  kp.a_b1 = (nz1 > 1 && a.a_batch_stride1 != 0) ? 1 : 0;
+  kp.b_b0 = (nz0 > 1 && a.b_batch_stride != 0) ? 1 : 0;
+  kp.b_b1 = (nz1 > 1 && a.b_batch_stride1 != 0) ? 1 : 0;
   kp.num_m = (a.M + BM - 1) / BM;
   kp.num_n = (a.N + bn_out - 1) / bn_out;
   kp.num_kb = (a.K + BK - 1) / BK;
@@ -553,13 +578,16 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   kp.D = a.D;
   kp.ldd = a.ldd;
   kp.dbs = a.d_batch_stride;
+  kp.dbs1 = a.d_batch_stride1;
   kp.D2 = a.D2;
   kp.ldd2 = a.ldd2;
   kp.d2bs = a.d2_batch_stride;
+  kp.d2bs1 = a.d2_batch_stride1;
   kp.bias = static_cast<const __nv_bfloat16*>(a.bias);
   kp.res = static_cast<const __nv_bfloat16*>(a.res);
   kp.ldres = a.ldres;
   kp.resbs = a.res_batch_stride;
+  kp.resbs1 = a.res_batch_stride1;
   kp.gate = static_cast<const __nv_bfloat16*>(a.gate);
   kp.gate_rows = a.gate_rows > 0 ? a.gate_rows : 1;
   kp.ldgate = a.ldgate;

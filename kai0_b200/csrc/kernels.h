@@ -71,6 +71,7 @@ void cast_bf16_to_f32(const bf16* in, float* out, int64_t n, cudaStream_t st);
 void add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t st);  // out = bf(a + b)
 void add_f32(float* a, const float* b, int64_t n, cudaStream_t st);                  // a += b
 void fill_zero(void* p, size_t bytes, cudaStream_t st);
+void fill_f32(float* p, float v, int64_t n, cudaStream_t st);
 // sincos time embedding in fp64 (pi0_pytorch.py:25-42,264-267): out[b, :] fp32 [2*half]
 void time_embedding(const float* time, const double* scaling /*[half]*/, float* out, int batch, int half, cudaStream_t st);
 void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st);
@@ -84,6 +85,9 @@ void euler_step(float* x, const float* v, float dt, int64_t n, cudaStream_t st);
 // copy rows [b, row_off:row_off+T, :] of a [batch, S, width] bf16 tensor to a contiguous fp32 [batch*T, width]
 void gather_rows_f32(const bf16* in, int64_t in_bstride, int row_off, int T, int width, float* out, int batch,
                      cudaStream_t st);
+// out[(b*T + t), :] = in[b, row_off + t, :]  (bf16 row gather out of a [batch, S, width] tensor)
+void copy_rows_bf16(const bf16* in, int64_t in_bstride, int row_off, int T, int width, bf16* out, int batch,
+                    cudaStream_t st);
 void scatter_rows_bf16(const float* in, bf16* out, int64_t out_bstride, int row_off, int T, int width, int batch,
                        cudaStream_t st);
 

@@ -1,0 +1,184 @@
+// fp32 SIMT GEMMs for the small fp32 linears of the path (action_in/out_proj, time MLP, adaRMS dense:
+// pi0_pytorch.py:270-273,289-293,368-371; modeling_gemma.py:88) and the fp32 patch-embedding convolution
+// expressed as a GEMM over an implicit im2col (modeling_siglip.py:220-226,271-282).
+//
+// C[i,j] (+)= sum_k A(i,k) * B(j,k) with operand access through small loader functors; 64x64x16 tiles,
+// 256 threads, 4x4 register micro-tiles.  These are <1% of the step's FLOPs and must stay fp32-exact.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pi05 {
+
+namespace {
+
+struct LinearF32 {  // element (r,k) at p[r*sr + k*sk]
+  const float* p;
+  int64_t sr, sk;
+  __device__ __forceinline__ float operator()(int r, int k) const { return p[r * sr + k * sk]; }
+};
+struct LinearBF16 {
+  const bf16* p;
+  int64_t sr, sk;
+  __device__ __forceinline__ float operator()(int r, int k) const { return __bfloat162float(p[r * sr + k * sk]); }
+};
+struct Im2col {  // row = img*P*P + prow*P + pcol ; k = ch*p*p + py*p + px
+  const float* img;
+  int S, p, P;  // image size, patch, patches per side
+  __device__ __forceinline__ float operator()(int r, int k) const {
+    const int pp = p * p;
+    const int im = r / (P * P), pr = (r / P) % P, pc = r % P;
+    const int ch = k / pp, py = (k % pp) / p, px = k % p;
+    return img[(static_cast<int64_t>(im) * 3 + ch) * S * S + static_cast<int64_t>(pr * p + py) * S + pc * p + px];
+  }
+};
+struct Im2colT {  // transposed roles: "row" = k-feature index, "k" = patch-row index  (for wgrad: B(j=feature, kk=row))
+  Im2col base;
+  __device__ __forceinline__ float operator()(int feat, int row) const { return base(row, feat); }
+};
+
+struct EpiF32 {  // C fp32 [M,N] row-major (+bias[j]) ; accumulate / atomic variants
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int mode;  // 0 store, 1 accumulate (+=), 2 atomicAdd
+  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+    if (bias) v = __fadd_rn(v, bias[j]);
+    float* c = C + i * ldc + j;
+    if (mode == 0) *c = v;
+    else if (mode == 1) *c += v;
+    else atomicAdd(c, v);
+  }
+};
+struct EpiPatch {  // out bf16 [rows, width] = bf( (acc + bias[c]) + pos[patch, c] )
+  bf16* out;
+  int width, patches;
+  const float* bias;
+  const float* pos;
+  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+    v = __fadd_rn(v, bias[j]);
+    v = __fadd_rn(v, pos[static_cast<int64_t>(i % patches) * width + j]);
+    out[static_cast<int64_t>(i) * width + j] = __float2bfloat16_rn(v);
+  }
+};
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <class LA, class LB, class EPI>
+__global__ void __launch_bounds__(256) sgemm_k(LA la, LB lb, EPI epi, int M, int N, int K, int k_per_split) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = threadIdx.x + r * 256;  // 0..1023
+      const int kk = e & 15, ii = e >> 4;
+      const int gi = i0 + ii, gj = j0 + ii, gk = k0 + kk;
+      As[kk][ii] = (gi < M && gk < kend) ? la(gi, gk) : 0.f;
+      Bs[kk][ii] = (gj < N && gk < kend) ? lb(gj, gk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        a[x] = As[kk][ty * 4 + x];
+        b[x] = Bs[kk][tx * 4 + x];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
+      if (i < M && j < N) epi(i, j, acc[x][y]);
+    }
+}
+
+template <class LA, class LB, class EPI>
+void run(LA la, LB lb, EPI epi, int M, int N, int K, int splits, cudaStream_t st) {
+  if (splits < 1) splits = 1;
+  int kps = (K + splits - 1) / splits;
+  kps = ((kps + TK - 1) / TK) * TK;
+  splits = (K + kps - 1) / kps;
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
+  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps);
+}
+
+__global__ void colsum_f32_k(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < M; ++i) s += x[static_cast<int64_t>(i) * N + j];
+  out[j] = s;
+}
+
+// dpos[patch, c] = sum_img dout[img, patch, c]; dbias[c] = sum_{img,patch} dout
+__global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ dpos, int n_img, int patches, int width) {
+  const int64_t total = static_cast<int64_t>(patches) * width;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int im = 0; im < n_img; ++im) s += __bfloat162float(dout[im * total + idx]);
+    dpos[idx] = s;
+  }
+}
+
+}  // namespace
+
+void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st) {
+  run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, 0}, M, N, K, 1, st);
+}
+
+void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, int accumulate, cudaStream_t st) {
+  // dX[i, k] = sum_n dY[i, n] W[n, k]  -> A(i, n) = dY, B(k, n) = W[n*K + k]
+  run(LinearF32{dY, N, 1}, LinearF32{W, 1, K}, EpiF32{dX, K, nullptr, accumulate ? 1 : 0}, M, K, N, 1, st);
+}
+
+void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
+  // dW[n, k] = sum_i dY[i, n] X[i, k] -> A(n, i) = dY[i*N + n], B(k, i) = X[i*K + k]
+  run(LinearF32{dY, 1, N}, LinearF32{X, 1, K}, EpiF32{dW, K, nullptr, 0}, N, K, M, 1, st);
+  if (db) colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY, M, N, db);
+}
+
+void patch_embed_fwd(const float* images, const float* W, const float* bias, const float* pos, bf16* out, int n_img,
+                     int image_size, int patch, int width, cudaStream_t st) {
+  const int P = image_size / patch;
+  const int K = 3 * patch * patch;
+  run(Im2col{images, image_size, patch, P}, LinearF32{W, K, 1}, EpiPatch{out, width, P * P, bias, pos}, n_img * P * P,
+      width, K, 1, st);
+}
+
+void patch_embed_bwd(const float* images, const bf16* dout, float* dW, float* dbias, float* dpos, float* scratch,
+                     int n_img, int image_size, int patch, int width, cudaStream_t st) {
+  (void)scratch;
+  const int P = image_size / patch;
+  const int K = 3 * patch * patch;
+  const int rows = n_img * P * P;
+  // dW[c, f] = sum_row dout[row, c] * im2col(row, f)
+  cudaMemsetAsync(dW, 0, static_cast<size_t>(width) * K * sizeof(float), st);
+  const int splits = rows >= 4096 ? 16 : 1;
+  run(LinearBF16{dout, 1, width}, Im2colT{Im2col{images, image_size, patch, P}}, EpiF32{dW, K, nullptr, 2}, width, K,
+      rows, splits, st);
+  const int64_t total = static_cast<int64_t>(P) * P * width;
+  patch_dpos_k<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(dout, dpos, n_img, P * P, width);
+  // dbias = column sum of dpos
+  colsum_f32_k<<<(width + 127) / 128, 128, 0, st>>>(dpos, P * P, width, dbias);
+}
+
+}  // namespace pi05

@@ -1,0 +1,597 @@
+"""Drop-in mirror of the reference's `openpi.models_pytorch.pi0_pytorch` surface on top of libpi05.so.
+
+Reference class: `PI0Pytorch` (src/openpi/models_pytorch/pi0_pytorch.py:84-461).  Same constructor argument, same
+`forward(observation, actions, noise=None, time=None)` / `sample_actions(device, observation, noise=None,
+num_steps=10)` signatures and return shapes, same state_dict keys / shapes / dtypes (gemma_pytorch.py:63-83), real
+`.grad`s, `gradient_checkpointing_enable()` (a no-op: the engine keeps activations resident, nothing is recomputed)
+and `paligemma_with_expert.to_bfloat16_for_selected_params()`.  All arithmetic happens in the CUDA engine; this file
+only owns memory (flat per-dtype parameter/gradient arenas the `nn.Parameter`s are views of), RNG draws
+(noise / time, exactly where the reference draws them) and the autograd plumbing.
+
+There is no CPU path: calling `forward` / `sample_actions` without the built library on an sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import logging
+import math
+from collections import OrderedDict
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+logger = logging.getLogger("kai0_b200")
+
+IMAGE_KEYS = ("base_0_rgb", "left_wrist_0_rgb", "right_wrist_0_rgb")  # preprocessing_pytorch.py:11-15
+IMAGE_RESOLUTION = (224, 224)
+PALIGEMMA_VOCAB_SIZE = 257_152  # models/gemma.py:40
+
+
+@dataclasses.dataclass(frozen=True)
+class GemmaVariant:
+    """models/gemma.py:43-51 (without LoRA: full fine-tune is the path in scope)."""
+
+    width: int
+    depth: int
+    mlp_dim: int
+    num_heads: int
+    num_kv_heads: int
+    head_dim: int
+
+
+def get_gemma_config(variant) -> GemmaVariant:
+    """models/gemma.py:58-110.  Accepts a variant name or an object with the six fields (duck-typed)."""
+    if not isinstance(variant, str):
+        return GemmaVariant(
+            variant.width, variant.depth, variant.mlp_dim, variant.num_heads, variant.num_kv_heads, variant.head_dim
+        )
+    if variant == "dummy":
+        return GemmaVariant(64, 4, 128, 8, 1, 16)
+    if variant == "gemma_300m":
+        return GemmaVariant(1024, 18, 4096, 8, 1, 256)
+    if variant == "gemma_2b":
+        return GemmaVariant(2048, 18, 16_384, 8, 1, 256)
+    raise ValueError(f"Unknown variant: {variant}")
+
+
+@dataclasses.dataclass
+class Pi05EngineConfig:
+    """What PI0Pytorch.__init__ reads from its config (pi0_pytorch.py:85-98,307,380) plus engine-side knobs.
+    Any object with these attribute names works (the reference's `Pi0Config` does)."""
+
+    pi05: bool = True
+    paligemma_variant: object = "gemma_2b"
+    action_expert_variant: object = "gemma_300m"
+    dtype: str = "bfloat16"
+    action_dim: int = 32
+    action_horizon: int = 50
+    max_token_len: int = 200
+    # vision tower (gemma_pytorch.py:38-41 + SiglipVisionConfig defaults of the PaliGemma config)
+    vit_width: int = 1152
+    vit_depth: int = 27
+    vit_mlp_dim: int = 4304
+    vit_heads: int = 16
+    vit_patch: int = 14
+    image_size: int = 224
+    vocab_size: int = PALIGEMMA_VOCAB_SIZE
+    num_images: int = 3
+
+
+def _cfg_get(config, name, default):
+    return getattr(config, name, default)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter table: reference names, shapes, dtypes, in ARENA ORDER (q|k|v and gate|up adjacent: the engine
+# treats them as single fused weights)
+# ------------------------------------------------------------------------------------------------------------
+_PWE = "paligemma_with_expert."
+_VT = _PWE + "paligemma.model.vision_tower.vision_model."
+_LM = _PWE + "paligemma.model.language_model."
+_EX = _PWE + "gemma_expert.model."
+_KEEP_F32 = (  # gemma_pytorch.py:72-79
+    "vision_tower.vision_model.embeddings.patch_embedding.weight",
+    "vision_tower.vision_model.embeddings.patch_embedding.bias",
+    "vision_tower.vision_model.embeddings.position_embedding.weight",
+    "input_layernorm",
+    "post_attention_layernorm",
+    "model.norm",
+)
+
+
+def parameter_table(cfg: Pi05EngineConfig, pg: GemmaVariant, ex: GemmaVariant, value_head: bool = False):
+    """[(name, shape, dtype, init_kind)] for every parameter of the reference module tree."""
+    out = []
+
+    def add(name, shape, kind):
+        dt = torch.bfloat16 if name.startswith(_PWE) else torch.float32
+        if name.startswith(_PWE) and any(k in name for k in _KEEP_F32):
+            dt = torch.float32
+        out.append((name, tuple(int(s) for s in shape), dt, kind))
+
+    W, p = cfg.vit_width, cfg.vit_patch
+    T = (cfg.image_size // p) ** 2
+    add(_VT + "embeddings.patch_embedding.weight", (W, 3, p, p), "linear")
+    add(_VT + "embeddings.patch_embedding.bias", (W,), "zeros")
+    add(_VT + "embeddings.position_embedding.weight", (T, W), "embed")
+    for i in range(cfg.vit_depth):
+        L = f"{_VT}encoder.layers.{i}."
+        add(L + "layer_norm1.weight", (W,), "ones")
+        add(L + "layer_norm1.bias", (W,), "zeros")
+        add(L + "layer_norm2.weight", (W,), "ones")
+        add(L + "layer_norm2.bias", (W,), "zeros")
+        for pj in ("q_proj", "k_proj", "v_proj"):
+            add(L + f"self_attn.{pj}.weight", (W, W), "linear")
+        for pj in ("q_proj", "k_proj", "v_proj"):
+            add(L + f"self_attn.{pj}.bias", (W,), "zeros")
+        add(L + "self_attn.out_proj.weight", (W, W), "linear")
+        add(L + "self_attn.out_proj.bias", (W,), "zeros")
+        add(L + "mlp.fc1.weight", (cfg.vit_mlp_dim, W), "linear")
+        add(L + "mlp.fc1.bias", (cfg.vit_mlp_dim,), "zeros")
+        add(L + "mlp.fc2.weight", (W, cfg.vit_mlp_dim), "linear")
+        add(L + "mlp.fc2.bias", (W,), "zeros")
+    add(_VT + "post_layernorm.weight", (W,), "ones")
+    add(_VT + "post_layernorm.bias", (W,), "zeros")
+    D = pg.width
+    add(_PWE + "paligemma.model.multi_modal_projector.linear.weight", (D, W), "linear")
+    add(_PWE + "paligemma.model.multi_modal_projector.linear.bias", (D,), "zeros")
+    add(_LM + "embed_tokens.weight", (cfg.vocab_size, D), "embed")
+    for prefix, g, ada in ((_LM, pg, False), (_EX, ex, True)):
+        for i in range(g.depth):
+            L = f"{prefix}layers.{i}."
+            add(L + "self_attn.q_proj.weight", (g.num_heads * g.head_dim, g.width), "linear")
+            add(L + "self_attn.k_proj.weight", (g.num_kv_heads * g.head_dim, g.width), "linear")
+            add(L + "self_attn.v_proj.weight", (g.num_kv_heads * g.head_dim, g.width), "linear")
+            add(L + "self_attn.o_proj.weight", (g.width, g.num_heads * g.head_dim), "linear")
+            add(L + "mlp.gate_proj.weight", (g.mlp_dim, g.width), "linear")
+            add(L + "mlp.up_proj.weight", (g.mlp_dim, g.width), "linear")
+            add(L + "mlp.down_proj.weight", (g.width, g.mlp_dim), "linear")
+            for nm in ("input_layernorm", "post_attention_layernorm"):
+                if ada:
+                    add(L + nm + ".dense.weight", (3 * g.width, g.width), "zeros")  # modeling_gemma.py:59-61
+                    add(L + nm + ".dense.bias", (3 * g.width,), "zeros")
+                else:
+                    add(L + nm + ".weight", (g.width,), "zeros")  # modeling_gemma.py:63
+        if ada:
+            add(prefix + "norm.dense.weight", (3 * g.width, g.width), "zeros")
+            add(prefix + "norm.dense.bias", (3 * g.width,), "zeros")
+        else:
+            add(prefix + "norm.weight", (g.width,), "zeros")
+    # the expert's never-used lm_head (kept so checkpoints round-trip)
+    add(_PWE + "gemma_expert.lm_head.weight", (cfg.vocab_size, ex.width), "embed")
+    E = ex.width
+    add("action_in_proj.weight", (E, cfg.action_dim), "linear")
+    add("action_in_proj.bias", (E,), "zeros")
+    add("action_out_proj.weight", (cfg.action_dim, E), "linear")
+    add("action_out_proj.bias", (cfg.action_dim,), "zeros")
+    add("time_mlp_in.weight", (E, E), "linear")
+    add("time_mlp_in.bias", (E,), "zeros")
+    add("time_mlp_out.weight", (E, E), "linear")
+    add("time_mlp_out.bias", (E,), "zeros")
+    if value_head:
+        add("value_head.0.weight", (E, E), "linear")
+        add("value_head.0.bias", (E,), "zeros")
+        add("value_head.2.weight", (E, E), "linear")
+        add("value_head.2.bias", (E,), "zeros")
+        add("value_head.4.weight", (1, E), "linear")
+        add("value_head.4.bias", (1,), "zeros")
+    return out
+
+
+_UNUSED = (_PWE + "gemma_expert.lm_head.weight",)  # parameters the path never reads (no gradient)
+
+
+class _Node(nn.Module):
+    """Parameter-only skeleton module: gives parameters the reference's dotted state_dict paths."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("skeleton module of the pi0.5 engine: call the top-level PI0Pytorch instead")
+
+
+class _PaliGemmaWithExpert(_Node):
+    def to_bfloat16_for_selected_params(self, precision: str = "bfloat16"):
+        """gemma_pytorch.py:63-83.  The engine's parameters are created with exactly that dtype map, so this only
+        validates the request."""
+        if precision != "bfloat16":
+            raise ValueError(f"the B200 engine implements the bfloat16 dtype map only (got {precision!r})")
+        return self
+
+
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter, top_cls=_Node):
+    parts = dotted.split(".")
+    mod = root
+    for i, name in enumerate(parts[:-1]):
+        if name not in mod._modules:
+            cls = _PaliGemmaWithExpert if (i == 0 and name == "paligemma_with_expert") else _Node
+            mod.add_module(name, cls())
+        mod = mod._modules[name]
+    mod.register_parameter(parts[-1], param)
+
+
+class _EngineFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward = pi05_forward, backward = pi05_backward."""
+
+    @staticmethod
+    def forward(ctx, model, batch, actions, noise, time, *params):
+        ctx.model = model
+        loss = model._engine_forward(batch, actions, noise, time)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        model = ctx.model
+        grads = model._engine_backward(dloss.contiguous())
+        return (None, None, None, None, None, *grads)
+
+
+class PI0Pytorch(nn.Module):
+    """B200-native pi0.5 model with the reference's surface (pi0_pytorch.py:84-461)."""
+
+    _value_head = False
+
+    def __init__(self, config, *, max_batch: int | None = None):
+        super().__init__()
+        self.config = config
+        self.pi05 = bool(_cfg_get(config, "pi05", True))
+        if not self.pi05:
+            raise ValueError("the B200 engine implements the pi0.5 branch (config.pi05=True) only")
+        if _cfg_get(config, "dtype", "bfloat16") != "bfloat16":
+            raise ValueError("the B200 engine implements dtype='bfloat16' only")
+        d = Pi05EngineConfig()
+        self.ecfg = Pi05EngineConfig(
+            pi05=True,
+            paligemma_variant=_cfg_get(config, "paligemma_variant", d.paligemma_variant),
+            action_expert_variant=_cfg_get(config, "action_expert_variant", d.action_expert_variant),
+            action_dim=_cfg_get(config, "action_dim", d.action_dim),
+            action_horizon=_cfg_get(config, "action_horizon", d.action_horizon),
+            max_token_len=_cfg_get(config, "max_token_len", d.max_token_len) or d.max_token_len,
+            vit_width=_cfg_get(config, "vit_width", d.vit_width),
+            vit_depth=_cfg_get(config, "vit_depth", d.vit_depth),
+            vit_mlp_dim=_cfg_get(config, "vit_mlp_dim", d.vit_mlp_dim),
+            vit_heads=_cfg_get(config, "vit_heads", d.vit_heads),
+            vit_patch=_cfg_get(config, "vit_patch", d.vit_patch),
+            image_size=_cfg_get(config, "image_size", d.image_size),
+            vocab_size=_cfg_get(config, "vocab_size", d.vocab_size),
+            num_images=_cfg_get(config, "num_images", d.num_images),
+        )
+        self.pg = get_gemma_config(self.ecfg.paligemma_variant)
+        self.ex = get_gemma_config(self.ecfg.action_expert_variant)
+        self._max_batch_hint = max_batch
+        self.gradient_checkpointing_enabled = False
+        self.augment = False  # train-time image augmentation (preprocessing_pytorch.py:52-142): see DESIGN.md
+
+        # ---- flat arenas + parameter views
+        table = parameter_table(self.ecfg, self.pg, self.ex, self._value_head)
+        self._table = table
+        n_bf16 = sum(math.prod(s) for _, s, dt, _ in table if dt == torch.bfloat16)
+        n_f32 = sum(math.prod(s) for _, s, dt, _ in table if dt == torch.float32)
+        # 8-element alignment of every tensor inside an arena (TMA needs 16B-aligned bases)
+        self._offsets = OrderedDict()
+        off = {torch.bfloat16: 0, torch.float32: 0}
+        for name, shape, dt, _ in table:
+            n = math.prod(shape)
+            self._offsets[name] = (dt, off[dt], n, shape)
+            off[dt] += (n + 7) // 8 * 8
+        self._flat = {
+            torch.bfloat16: torch.zeros(off[torch.bfloat16], dtype=torch.bfloat16),
+            torch.float32: torch.zeros(off[torch.float32], dtype=torch.float32),
+        }
+        del n_bf16, n_f32
+        self._flat_grad = {torch.bfloat16: None, torch.float32: None}
+        for name, shape, dt, _ in table:
+            _, o, n, _ = self._offsets[name]
+            p = nn.Parameter(self._flat[dt][o : o + n].view(shape), requires_grad=True)
+            _attach(self, name, p)
+        # tied head (modeling_paligemma.py:389-393): same Parameter object under the second name
+        self.paligemma_with_expert.paligemma.add_module("lm_head", _Node())
+        self.paligemma_with_expert.paligemma.lm_head.register_parameter(
+            "weight", self.paligemma_with_expert.paligemma.model.language_model.embed_tokens.weight
+        )
+        self.reset_parameters()
+
+        self._engine = None
+        self._engine_key = None
+        self._workspace = None
+        self._dp_group = None
+        self._keep = None
+
+    # ------------------------------------------------------------------ init / housekeeping
+    @torch.no_grad()
+    def reset_parameters(self, seed: int | None = None):
+        """Reference init rules: Linear/Embedding N(0, 0.02) (HF initializer_range), LayerNorm ones/zeros, RMSNorm
+        weight and adaRMS dense weight zeros (modeling_gemma.py:59-63), nn.Linear default for the fp32 heads."""
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        params = dict(self.named_parameters())
+        for name, shape, dt, kind in self._table:
+            p = params[name]
+            if kind == "zeros":
+                p.zero_()
+            elif kind == "ones":
+                p.fill_(1.0)
+            elif kind == "embed":
+                p.copy_((torch.randn(shape, generator=g) * 0.02).to(dt))
+            else:
+                fan_in = math.prod(shape[1:])
+                std = 0.02 if name.startswith(_PWE) else 1.0 / math.sqrt(3.0 * fan_in)
+                p.copy_((torch.randn(shape, generator=g) * std).to(dt))
+
+    def _apply(self, fn, recurse=True):
+        """Keep the parameters views of the flat arenas across .to()/.cuda(): move the arenas, re-point the views."""
+        new_flat = {}
+        for dt, t in self._flat.items():
+            nt = fn(t)
+            if nt.dtype != dt:
+                raise TypeError(
+                    "PI0Pytorch keeps the reference's mixed dtype map (bf16 weights, fp32 norms/heads); "
+                    f"casting the whole module to {nt.dtype} is not supported"
+                )
+            new_flat[dt] = nt
+        moved = any(new_flat[dt] is not self._flat[dt] for dt in new_flat)
+        if moved:
+            self._flat = new_flat
+            self._flat_grad = {torch.bfloat16: None, torch.float32: None}
+            params = dict(self.named_parameters())
+            for name, (dt, o, n, shape) in self._offsets.items():
+                p = params[name]
+                p.data = self._flat[dt][o : o + n].view(shape)
+                p.grad = None
+            self._destroy_engine()
+        return self
+
+    def gradient_checkpointing_enable(self):
+        """pi0_pytorch.py:126-133.  Accepted for script compatibility; the engine never recomputes (180 GB HBM)."""
+        self.gradient_checkpointing_enabled = True
+        logger.info("gradient checkpointing requested: no-op on the B200 engine (activations stay resident)")
+
+    def gradient_checkpointing_disable(self):
+        self.gradient_checkpointing_enabled = False
+
+    def is_gradient_checkpointing_enabled(self):
+        return self.gradient_checkpointing_enabled
+
+    def enable_flat_allreduce(self, process_group=None):
+        """Engine-owned data parallelism: one NCCL all-reduce per dtype arena right after backward, averaged over
+        the group (equivalent to DDP's bucketed all-reduce, train_pytorch.py:440-447).  Use INSTEAD of wrapping in
+        DistributedDataParallel."""
+        import torch.distributed as dist
+
+        self._dp_group = process_group if process_group is not None else dist.group.WORLD
+
+    # ------------------------------------------------------------------ engine lifecycle
+    def _device(self):
+        return self._flat[torch.bfloat16].device
+
+    def _destroy_engine(self):
+        if self._engine is not None:
+            _lib.lib().pi05_destroy(self._engine)
+        self._engine = None
+        self._engine_key = None
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            self._destroy_engine()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _ensure_engine(self, batch: int, train: bool):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "PI0Pytorch (B200 engine) has no CPU path: move the module to an sm_100 CUDA device first"
+            )
+        need_b = max(batch, self._max_batch_hint or 0)
+        key = (dev.index, train)
+        if self._engine is not None and self._engine_key[:2] == key and self._engine_key[2] >= batch:
+            return
+        self._destroy_engine()
+        l = _lib.lib()
+        c = _lib.Config()
+        for dst, src in ((c.paligemma, self.pg), (c.expert, self.ex)):
+            dst.width, dst.depth, dst.mlp_dim = src.width, src.depth, src.mlp_dim
+            dst.num_heads, dst.num_kv_heads, dst.head_dim = src.num_heads, src.num_kv_heads, src.head_dim
+        e = self.ecfg
+        c.vit_width, c.vit_depth, c.vit_mlp_dim, c.vit_heads = e.vit_width, e.vit_depth, e.vit_mlp_dim, e.vit_heads
+        c.vit_patch, c.image_size, c.vocab_size = e.vit_patch, e.image_size, e.vocab_size
+        c.action_dim, c.action_horizon, c.max_token_len = e.action_dim, e.action_horizon, e.max_token_len
+        c.num_images, c.max_batch, c.train = e.num_images, need_b, 1 if train else 0
+        c.value_head = 1 if self._value_head else 0
+        nbytes = l.pi05_workspace_bytes(C.byref(c))
+        if nbytes == 0:
+            raise RuntimeError(f"pi05_workspace_bytes: {_lib.last_error()}")
+        with torch.cuda.device(dev):
+            self._workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (self._workspace.data_ptr() + 255) // 256 * 256
+            handle = C.c_void_p()
+            _lib.check(
+                l.pi05_create(C.byref(c), dev.index or 0, C.c_void_p(base), C.c_size_t(nbytes), C.byref(handle)),
+                "pi05_create",
+            )
+        self._engine = handle
+        self._engine_key = (dev.index, train, need_b)
+        if train:
+            for dt in (torch.bfloat16, torch.float32):
+                if self._flat_grad[dt] is None:
+                    self._flat_grad[dt] = torch.zeros_like(self._flat[dt])
+        self._bind()
+
+    def _bind(self):
+        names, arr = [], (_lib.Param * len(self._offsets))()
+        for i, (name, (dt, o, n, _)) in enumerate(self._offsets.items()):
+            esz = 2 if dt == torch.bfloat16 else 4
+            bname = name.encode()
+            names.append(bname)
+            arr[i].name = bname
+            arr[i].dtype = 1 if dt == torch.bfloat16 else 0
+            arr[i].numel = n
+            arr[i].data = self._flat[dt].data_ptr() + o * esz
+            g = self._flat_grad[dt]
+            arr[i].grad = (g.data_ptr() + o * esz) if g is not None else None
+        self._keep = names
+        _lib.check(_lib.lib().pi05_bind_params(self._engine, arr, len(self._offsets)), "pi05_bind_params")
+
+    def set_taps(self, enabled: bool):
+        self._taps = bool(enabled)
+
+    def get_tap(self, name: str) -> Tensor:
+        """Debug/parity hook: a named intermediate of the last call (tests only)."""
+        n, dt = C.c_int64(), C.c_int32()
+        l = _lib.lib()
+        _lib.check(l.pi05_get_tap(self._engine, name.encode(), None, C.byref(n), C.byref(dt), None), "pi05_get_tap")
+        out = torch.empty(n.value, dtype=torch.bfloat16 if dt.value == 1 else torch.float32, device=self._device())
+        stream = C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+        _lib.check(
+            l.pi05_get_tap(self._engine, name.encode(), C.c_void_p(out.data_ptr()), C.byref(n), C.byref(dt), stream),
+            "pi05_get_tap",
+        )
+        return out
+
+    # ------------------------------------------------------------------ inputs
+    def _preprocess_observation(self, observation, *, train=True):
+        """preprocessing_pytorch.py:20-173 for inputs already at 224x224 (resize/augmentation: DESIGN.md 'next')."""
+        images = getattr(observation, "images")
+        if not set(IMAGE_KEYS).issubset(images):
+            raise ValueError(f"images dict missing keys: expected {IMAGE_KEYS}, got {list(images)}")
+        keys = self._image_keys(images)
+        state = observation.state
+        batch_shape = state.shape[:-1]
+        S = self.ecfg.image_size
+        out_images, out_masks = [], []
+        masks = getattr(observation, "image_masks", {}) or {}
+        for key in keys:
+            img = images[key]
+            if img.shape[1] != 3 and img.shape[-1] == 3:
+                img = img.permute(0, 3, 1, 2)  # the tower needs NCHW (SURVEY §8b note on layout sniffing)
+            if tuple(img.shape[-2:]) != (S, S):
+                raise ValueError(
+                    f"image {key} has resolution {tuple(img.shape[-2:])}; this round's engine takes {S}x{S} inputs "
+                    "(resize_with_pad is a 'next' row in DESIGN.md)"
+                )
+            out_images.append(img.to(torch.float32))
+            if key in masks:
+                out_masks.append(masks[key])
+            else:
+                out_masks.append(torch.ones(batch_shape, dtype=torch.bool, device=state.device))
+        return out_images, out_masks, observation.tokenized_prompt, observation.tokenized_prompt_mask, state
+
+    def _image_keys(self, images):
+        return IMAGE_KEYS
+
+    def _make_batch(self, images, img_masks, lang_tokens, lang_masks):
+        dev = self._device()
+        if len(images) != self.ecfg.num_images:
+            raise ValueError(f"expected {self.ecfg.num_images} images, got {len(images)}")
+        imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
+        masks = torch.stack([m.to(dev) for m in img_masks], dim=0).to(torch.uint8).contiguous()
+        toks = lang_tokens.to(dev, torch.int64).contiguous()
+        tmask = lang_masks.to(dev).to(torch.uint8).contiguous()
+        B = toks.shape[0]
+        if toks.shape[1] != self.ecfg.max_token_len:
+            raise ValueError(f"tokenized_prompt length {toks.shape[1]} != max_token_len {self.ecfg.max_token_len}")
+        if int(toks.min()) < 0 or int(toks.max()) >= self.ecfg.vocab_size:
+            raise ValueError("token id out of range")
+        b = _lib.Batch()
+        b.batch = B
+        b.images = imgs.data_ptr()
+        b.image_masks = masks.data_ptr()
+        b.tokens = toks.data_ptr()
+        b.token_mask = tmask.data_ptr()
+        return b, (imgs, masks, toks, tmask)
+
+    def sample_noise(self, shape, device):  # pi0_pytorch.py:172-179
+        return torch.normal(mean=0.0, std=1.0, size=shape, dtype=torch.float32, device=device)
+
+    def sample_time(self, bsize, device):  # pi0_pytorch.py:45-49,181-184
+        alpha_t = torch.as_tensor(1.5, dtype=torch.float32, device=device)
+        beta_t = torch.as_tensor(1.0, dtype=torch.float32, device=device)
+        time_beta = torch.distributions.Beta(alpha_t, beta_t).sample((bsize,))
+        return (time_beta * 0.999 + 0.001).to(dtype=torch.float32, device=device)
+
+    # ------------------------------------------------------------------ engine calls
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+
+    def _engine_forward(self, batch_pack, actions, noise, time):
+        b, keep = batch_pack
+        B = b.batch
+        loss = torch.empty((B, self.ecfg.action_horizon, self.ecfg.action_dim), dtype=torch.float32, device=self._device())
+        l = _lib.lib()
+        l.pi05_set_taps(self._engine, 1 if getattr(self, "_taps", False) else 0)
+        _lib.check(
+            l.pi05_forward(
+                self._engine,
+                C.byref(b),
+                C.c_void_p(actions.data_ptr()),
+                C.c_void_p(noise.data_ptr()),
+                C.c_void_p(time.data_ptr()),
+                C.c_void_p(loss.data_ptr()),
+                self._stream(),
+            ),
+            "pi05_forward",
+        )
+        self._last_inputs = (keep, actions, noise, time)  # keep device buffers alive until backward
+        return loss
+
+    def _engine_backward(self, dloss):
+        _lib.check(_lib.lib().pi05_backward(self._engine, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
+        if self._dp_group is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(self._dp_group)
+            for dt in (torch.bfloat16, torch.float32):
+                g = self._flat_grad[dt]
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp_group)
+                g.mul_(1.0 / world)
+        grads = []
+        for name, p in self._grad_params:
+            dt, o, n, shape = self._offsets[name]
+            grads.append(self._flat_grad[dt][o : o + n].view(shape))
+        return grads
+
+    # ------------------------------------------------------------------ public surface
+    def forward(self, observation, actions, noise=None, time=None) -> Tensor:
+        """Training forward (pi0_pytorch.py:316-373): returns the un-reduced loss [B, horizon, action_dim] fp32."""
+        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=True)
+        dev = self._device()
+        actions = actions.to(dev, torch.float32).contiguous()
+        if noise is None:
+            noise = self.sample_noise(actions.shape, actions.device)
+        if time is None:
+            time = self.sample_time(actions.shape[0], actions.device)
+        noise = noise.to(dev, torch.float32).contiguous()
+        time = time.to(dev, torch.float32).contiguous()
+        B = actions.shape[0]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]))
+        pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        if not need_grad:
+            return self._engine_forward(pack, actions, noise, time)
+        named = dict(self.named_parameters())
+        self._grad_params = [(n, named[n]) for n in self._offsets if n not in _UNUSED and named[n].requires_grad]
+        return _EngineFunction.apply(self, pack, actions, noise, time, *[p for _, p in self._grad_params])
+
+    @torch.no_grad()
+    def sample_actions(self, device, observation, noise=None, num_steps=10) -> Tensor:
+        """Inference (pi0_pytorch.py:375-419): prefix pass + KV cache, then `num_steps` Euler steps."""
+        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(observation, train=False)
+        bsize = state.shape[0]
+        dev = self._device()
+        if noise is None:
+            noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev)
+        noise = noise.to(dev, torch.float32).contiguous()
+        train_engine = self._engine_key is not None and self._engine_key[1]
+        self._ensure_engine(bsize, train=train_engine)
+        b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        l = _lib.lib()
+        l.pi05_set_taps(self._engine, 1 if getattr(self, "_taps", False) else 0)
+        _lib.check(l.pi05_prefill(self._engine, C.byref(b), self._stream()), "pi05_prefill")
+        out = torch.empty_like(noise)
+        _lib.check(
+            l.pi05_denoise(self._engine, C.c_void_p(noise.data_ptr()), int(num_steps), C.c_void_p(out.data_ptr()), self._stream()),
+            "pi05_denoise",
+        )
+        del keep
+        return out
