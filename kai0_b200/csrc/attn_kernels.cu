@@ -2,6 +2,7 @@
 // Reference arithmetic: pi0_pytorch.py:52-81,156-159,207,221,343 (masks, positions),
 // modeling_gemma.py:147-194 (rotary), modeling_gemma.py:243-248 (scale, mask add, fp32 softmax -> bf16).
 #include "common.cuh"
+#include "errors.h"
 #include "kernels.h"
 
 namespace pi05 {
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_k(const bf16* __restrict__ p,
 void prefix_meta(const uint8_t* image_masks, const uint8_t* token_mask, int batch, int num_images, int tokens_per_image,
                  int max_token_len, uint8_t* pad, int* pos, int* nvalid, cudaStream_t st) {
   prefix_meta_k<<<ceil_div(batch, 32), 32, 0, st>>>(image_masks, token_mask, batch, num_images, tokens_per_image,
-                                                    max_token_len, pad, pos, nvalid);
+                                                    max_token_len, pad, pos, nvalid); count_launch();
 }
 
 void rope_pack_fwd(const bf16* qkv, int T, int H, int hd, const int* pos, const int* nvalid, int pos_mode,
@@ -191,7 +192,7 @@ void rope_pack_fwd(const bf16* qkv, int T, int H, int hd, const int* pos, const 
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * (hd / 16);
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
   rope_pack_fwd_k<<<blocks, 256, 0, st>>>(qkv, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, Q, K, V, key_off, kv_len,
-                                          batch);
+                                          batch); count_launch();
 }
 
 void rope_pack_bwd(const bf16* dQ, const float* dK, const float* dV, int T, int H, int hd, const int* pos,
@@ -200,18 +201,18 @@ void rope_pack_bwd(const bf16* dQ, const float* dK, const float* dV, int T, int 
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * (hd / 16);
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
   rope_pack_bwd_k<<<blocks, 256, 0, st>>>(dQ, dK, dV, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, dqkv, key_off,
-                                          kv_len, batch);
+                                          kv_len, batch); count_launch();
 }
 
 void softmax_fwd(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_keys, int n_prefix, const uint8_t* pad,
                  const uint8_t* qpad, int q_per_token, cudaStream_t st) {
   const int64_t rows = static_cast<int64_t>(batch) * rows_per_batch;
   softmax_fwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad,
-                                                   q_per_token > 0 ? q_per_token : 1);
+                                                   q_per_token > 0 ? q_per_token : 1); count_launch();
 }
 
 void softmax_bwd(const bf16* p, bf16* dp, int64_t ld, int rows, int n_keys, float scale, cudaStream_t st) {
-  softmax_bwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(p, dp, ld, rows, n_keys, scale);
+  softmax_bwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(p, dp, ld, rows, n_keys, scale); count_launch();
 }
 
 }  // namespace pi05

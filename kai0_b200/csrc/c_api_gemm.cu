@@ -12,11 +12,17 @@ void set_error(const char* msg) {
   snprintf(g_last_error, sizeof(g_last_error), "%s", msg ? msg : "");
 }
 const char* get_error() { return g_last_error; }
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+unsigned long long launch_count() { return g_launches; }
 }  // namespace pi05
 
 extern "C" {
 
 int pi05_abi_version(void) { return PI05_ABI_VERSION; }
+unsigned long long pi05_launch_count(void) { return pi05::launch_count(); }
+void pi05_gemm_profile_enable(int on) { pi05::gemm_profile_enable(on); }
+int pi05_gemm_profile_report(char* buf, int len) { return pi05::gemm_profile_report(buf, len); }
 const char* pi05_last_error(void) { return pi05::get_error(); }
 
 int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream) {

@@ -53,3 +53,9 @@ struct GemmArgs {
 int gemm_bf16(const GemmArgs& args, cudaStream_t stream, char* err = nullptr, int err_len = 0);
 
 }  // namespace pi05
+
+namespace pi05 {
+// Per-launch CUDA-event timing of the tcgen05 GEMM (used by bench.py for the roofline line).
+void gemm_profile_enable(int on);
+int gemm_profile_report(char* buf, int len);
+}  // namespace pi05

@@ -16,7 +16,9 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
+#include "errors.h"
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -58,6 +60,13 @@ struct KParams {
   int accumulate;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor geometry (overridable for bring-up: PI05_DBG_MN_LBO/SBO)
 };
+
+struct ProfEntry {
+  cudaEvent_t a, b;
+  int M, N, K, batch, epi, majors;
+};
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
 
 struct TileCoord {
   int z, z0, z1, m_blk, n_blk;
@@ -497,7 +506,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cuda
   }
   const int total = kp.num_m * kp.num_n * kp.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, kp);
+  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, kp); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) snprintf(err, err_len, "gemm launch: %s", cudaGetErrorString(e));
@@ -597,8 +606,64 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   kp.mn_sbo = 1024;
   if (const char* e = getenv("PI05_DBG_MN_LBO")) kp.mn_lbo = static_cast<uint32_t>(atoi(e));
   if (const char* e = getenv("PI05_DBG_MN_SBO")) kp.mn_sbo = static_cast<uint32_t>(atoi(e));
-  if (bn == 256) return dispatch_epi<256>(a.epilogue, ta, tb, kp, stream, err, err_len);
-  return dispatch_epi<128>(a.epilogue, ta, tb, kp, stream, err, err_len);
+  ProfEntry pe{};
+  const bool prof = g_prof_on;
+  if (prof) {
+    cudaEventCreate(&pe.a);
+    cudaEventCreate(&pe.b);
+    pe.M = a.M;
+    pe.N = (a.epilogue == EPI_GEGLU) ? 2 * a.N : a.N;
+    pe.K = a.K;
+    pe.batch = a.batch;
+    pe.epi = a.epilogue;
+    pe.majors = a.a_major * 2 + a.b_major;
+    cudaEventRecord(pe.a, stream);
+  }
+  const int rc = (bn == 256) ? dispatch_epi<256>(a.epilogue, ta, tb, kp, stream, err, err_len)
+                             : dispatch_epi<128>(a.epilogue, ta, tb, kp, stream, err, err_len);
+  if (prof) {
+    cudaEventRecord(pe.b, stream);
+    g_prof.push_back(pe);
+  }
+  return rc;
+}
+
+// ---- per-launch timing of the tcgen05 GEMM (bench.py's roofline line): CUDA events around every launch ----------
+void gemm_profile_enable(int on) {
+  g_prof_on = on != 0;
+  if (on) {
+    for (auto& p : g_prof) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+    }
+    g_prof.clear();
+  }
+}
+
+// Synchronises the events and writes one line per GEMM class: "M N K batch epi majors launches total_ms\n".
+int gemm_profile_report(char* buf, int len) {
+  struct Acc {
+    int launches = 0;
+    double ms = 0;
+  };
+  std::map<std::tuple<int, int, int, int, int, int>, Acc> acc;
+  for (auto& p : g_prof) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    Acc& x = acc[std::make_tuple(p.M, p.N, p.K, p.batch, p.epi, p.majors)];
+    x.launches += 1;
+    x.ms += ms;
+  }
+  int off = 0;
+  for (auto& kv : acc) {
+    const int n = snprintf(buf + off, off < len ? len - off : 0, "%d %d %d %d %d %d %d %.6f\n", std::get<0>(kv.first),
+                           std::get<1>(kv.first), std::get<2>(kv.first), std::get<3>(kv.first), std::get<4>(kv.first),
+                           std::get<5>(kv.first), kv.second.launches, kv.second.ms);
+    if (n < 0 || off + n >= len) break;
+    off += n;
+  }
+  return off;
 }
 
 }  // namespace pi05

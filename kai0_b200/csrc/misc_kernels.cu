@@ -2,6 +2,7 @@
 // Reference arithmetic: gemma_pytorch.py:88-89 + pi0_pytorch.py:213-216 (embedding * sqrt(d)),
 // modeling_gemma.py:125 (GeGLU), pi0_pytorch.py:25-42 (sincos, fp64), :326-328,373 (flow matching), :417 (Euler).
 #include "common.cuh"
+#include "errors.h"
 #include "kernels.h"
 
 namespace pi05 {
@@ -266,79 +267,79 @@ __global__ void scatter_rows_bf16_k(const float* __restrict__ in, bf16* __restri
 void embed_tokens_fwd(const int64_t* tok, const bf16* table, bf16* out, int batch, int L, int width, int64_t out_bstride,
                       int row_off, float scale, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(batch) * L * (width / 8);
-  embed_tokens_fwd_k<<<grid_for(total), 256, 0, st>>>(tok, table, out, batch, L, width, out_bstride, row_off, scale);
+  embed_tokens_fwd_k<<<grid_for(total), 256, 0, st>>>(tok, table, out, batch, L, width, out_bstride, row_off, scale); count_launch();
 }
 
 void embed_tokens_bwd(const int64_t* tok, const bf16* dout, int64_t dout_bstride, int row_off, bf16* dtable,
                       float* scratch, int* first, int batch, int L, int width, float scale, cudaStream_t st) {
   const int n = batch * L;
   cudaMemsetAsync(scratch, 0, static_cast<size_t>(n) * width * sizeof(float), st);
-  first_occurrence_k<<<ceil_div(n, 128), 128, 0, st>>>(tok, first, n);
+  first_occurrence_k<<<ceil_div(n, 128), 128, 0, st>>>(tok, first, n); count_launch();
   const int64_t total = static_cast<int64_t>(n) * width;
   embed_accum_k<<<grid_for(total), 256, 0, st>>>(tok, first, dout, dout_bstride, row_off, scratch, batch, L, width,
-                                                 scale);
-  embed_write_k<<<grid_for(total), 256, 0, st>>>(tok, first, scratch, dtable, n, width);
+                                                 scale); count_launch();
+  embed_write_k<<<grid_for(total), 256, 0, st>>>(tok, first, scratch, dtable, n, width); count_launch();
 }
 
 void geglu_bwd(const bf16* dh, const bf16* gu, bf16* dgu, int64_t rows, int n, cudaStream_t st) {
-  geglu_bwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(dh, gu, dgu, rows, n);
+  geglu_bwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(dh, gu, dgu, rows, n); count_launch();
 }
 void geglu_fwd(const bf16* gu, bf16* h, int64_t rows, int n, cudaStream_t st) {
-  geglu_fwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(gu, h, rows, n);
+  geglu_fwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(gu, h, rows, n); count_launch();
 }
 void gelu_bwd(const bf16* dact, const bf16* pre, bf16* dpre, int64_t n, cudaStream_t st) {
-  gelu_bwd_k<<<grid_for(n / 8), 256, 0, st>>>(dact, pre, dpre, n / 8);
+  gelu_bwd_k<<<grid_for(n / 8), 256, 0, st>>>(dact, pre, dpre, n / 8); count_launch();
 }
 void colsum_bf16(const bf16* x, int64_t ld, int64_t rows, int cols, float* acc32, cudaStream_t st) {
   dim3 grid(ceil_div(cols, 256), ceil_div(rows, 256));
-  colsum_bf16_k<<<grid, 256, 0, st>>>(x, ld, rows, cols, acc32);
+  colsum_bf16_k<<<grid, 256, 0, st>>>(x, ld, rows, cols, acc32); count_launch();
 }
 void cast_f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st) {
-  cast_f32_to_bf16_k<<<grid_for(n), 256, 0, st>>>(in, out, n);
+  cast_f32_to_bf16_k<<<grid_for(n), 256, 0, st>>>(in, out, n); count_launch();
 }
 void cast_bf16_to_f32(const bf16* in, float* out, int64_t n, cudaStream_t st) {
-  cast_bf16_to_f32_k<<<grid_for(n), 256, 0, st>>>(in, out, n);
+  cast_bf16_to_f32_k<<<grid_for(n), 256, 0, st>>>(in, out, n); count_launch();
 }
 void add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t st) {
-  add_bf16_k<<<grid_for(n / 8), 256, 0, st>>>(a, b, out, n / 8);
+  add_bf16_k<<<grid_for(n / 8), 256, 0, st>>>(a, b, out, n / 8); count_launch();
 }
-void add_f32(float* a, const float* b, int64_t n, cudaStream_t st) { add_f32_k<<<grid_for(n), 256, 0, st>>>(a, b, n); }
+void add_f32(float* a, const float* b, int64_t n, cudaStream_t st) { add_f32_k<<<grid_for(n), 256, 0, st>>>(a, b, n); count_launch(); }
 void fill_zero(void* p, size_t bytes, cudaStream_t st) { cudaMemsetAsync(p, 0, bytes, st); }
-void fill_f32(float* p, float v, int64_t n, cudaStream_t st) { fill_f32_k<<<grid_for(n), 256, 0, st>>>(p, v, n); }
+void fill_f32(float* p, float v, int64_t n, cudaStream_t st) { fill_f32_k<<<grid_for(n), 256, 0, st>>>(p, v, n); count_launch(); }
 void time_embedding(const float* time, const double* scaling, float* out, int batch, int half, cudaStream_t st) {
-  time_embedding_k<<<grid_for(static_cast<int64_t>(batch) * half), 256, 0, st>>>(time, scaling, out, batch, half);
+  time_embedding_k<<<grid_for(static_cast<int64_t>(batch) * half), 256, 0, st>>>(time, scaling, out, batch, half); count_launch();
 }
-void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st) { silu_fwd_k<<<grid_for(n), 256, 0, st>>>(x, y, n); }
+void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st) { silu_fwd_k<<<grid_for(n), 256, 0, st>>>(x, y, n); count_launch(); }
 void silu_bwd(const float* dy, const float* x, float* dx, int64_t n, cudaStream_t st) {
-  silu_bwd_k<<<grid_for(n), 256, 0, st>>>(dy, x, dx, n);
+  silu_bwd_k<<<grid_for(n), 256, 0, st>>>(dy, x, dx, n); count_launch();
 }
 void flow_inputs(const float* actions, const float* noise, const float* time, float* x_t, float* u_t, int batch, int per,
                  cudaStream_t st) {
-  flow_inputs_k<<<grid_for(static_cast<int64_t>(batch) * per), 256, 0, st>>>(actions, noise, time, x_t, u_t, batch, per);
+  flow_inputs_k<<<grid_for(static_cast<int64_t>(batch) * per), 256, 0, st>>>(actions, noise, time, x_t, u_t, batch, per); count_launch();
 }
 void flow_loss(const float* u_t, const float* v_t, float* loss, int64_t n, cudaStream_t st) {
-  flow_loss_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, loss, n);
+  flow_loss_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, loss, n); count_launch();
 }
 void flow_loss_bwd(const float* u_t, const float* v_t, const float* dloss, float* dv, int64_t n, cudaStream_t st) {
-  flow_loss_bwd_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, dloss, dv, n);
+  flow_loss_bwd_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, dloss, dv, n); count_launch();
 }
 void euler_step(float* x, const float* v, float dt, int64_t n, cudaStream_t st) {
-  euler_step_k<<<grid_for(n), 256, 0, st>>>(x, v, dt, n);
+  euler_step_k<<<grid_for(n), 256, 0, st>>>(x, v, dt, n); count_launch();
 }
 void gather_rows_f32(const bf16* in, int64_t in_bstride, int row_off, int T, int width, float* out, int batch,
                      cudaStream_t st) {
   gather_rows_f32_k<<<grid_for(static_cast<int64_t>(batch) * T * width), 256, 0, st>>>(in, in_bstride, row_off, T, width,
-                                                                                       out, batch);
+                                                                                       out, batch); count_launch();
 }
 void copy_rows_bf16(const bf16* in, int64_t in_bstride, int row_off, int T, int width, bf16* out, int batch,
                     cudaStream_t st) {
   copy_rows_bf16_k<<<grid_for(static_cast<int64_t>(batch) * T * (width / 8)), 256, 0, st>>>(in, in_bstride, row_off, T,
-                                                                                            width, out, batch);
+                                                                                            width, out, batch); count_launch();
 }
 void scatter_rows_bf16(const float* in, bf16* out, int64_t out_bstride, int row_off, int T, int width, int batch,
                        cudaStream_t st) {
   scatter_rows_bf16_k<<<grid_for(static_cast<int64_t>(batch) * T * width), 256, 0, st>>>(in, out, out_bstride, row_off,
-                                                                                         T, width, batch);
+                                                                                         T, width, batch); count_launch();
 }
 
 }  // namespace pi05

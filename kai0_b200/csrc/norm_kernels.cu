@@ -3,6 +3,7 @@
 // Reference arithmetic: modeling_siglip.py:466,474,787 (nn.LayerNorm), modeling_gemma.py:49-104 (GemmaRMSNorm),
 // modeling_gemma.py:209-227 (_gated_residual).
 #include "common.cuh"
+#include "errors.h"
 #include "kernels.h"
 
 namespace pi05 {
@@ -286,36 +287,36 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
 
 void layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int rows, int width,
                    float eps, cudaStream_t st) {
-  layernorm_fwd_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(x, w, b, y, mean, rstd, rows, width, eps);
+  layernorm_fwd_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(x, w, b, y, mean, rstd, rows, width, eps); count_launch();
 }
 
 void layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd,
                    const bf16* dres, bf16* dx, float* dw32, float* db32, int rows, int width, cudaStream_t st) {
-  layernorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mean, rstd, dres, dx, rows, width);
-  norm_bwd_dwdb_k<true><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, mean, rstd, dw32, db32, rows, width);
+  layernorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mean, rstd, dres, dx, rows, width); count_launch();
+  norm_bwd_dwdb_k<true><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, mean, rstd, dw32, db32, rows, width); count_launch();
 }
 
 void rmsnorm_fwd(const bf16* x, const float* w, const float* mod, int rows_per_batch, bf16* y, float* rstd,
                  bf16* gate_out, int rows, int width, float eps, cudaStream_t st) {
   rmsnorm_fwd_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(x, w, mod, rows_per_batch > 0 ? rows_per_batch : rows,
-                                                              y, rstd, gate_out, rows, width, eps);
+                                                              y, rstd, gate_out, rows, width, eps); count_launch();
 }
 
 void rmsnorm_bwd(const bf16* dy, const bf16* x, const float* w, const float* mod, int rows_per_batch,
                  const float* rstd, const bf16* dres, bf16* dx, float* dw32, float* dmod, int rows, int width,
                  cudaStream_t st) {
   const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
-  rmsnorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mod, rpb, rstd, dres, dx, rows, width);
+  rmsnorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mod, rpb, rstd, dres, dx, rows, width); count_launch();
   if (mod == nullptr) {
-    norm_bwd_dwdb_k<false><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, nullptr, rstd, dw32, nullptr, rows, width);
+    norm_bwd_dwdb_k<false><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, nullptr, rstd, dw32, nullptr, rows, width); count_launch();
   } else {
-    adarms_bwd_dmod_k<<<rows / rpb, 256, 0, st>>>(dy, x, rstd, rpb, dmod, width);
+    adarms_bwd_dmod_k<<<rows / rpb, 256, 0, st>>>(dy, x, rstd, rpb, dmod, width); count_launch();
   }
 }
 
 void gated_residual_bwd(const bf16* dy, const bf16* o, const bf16* gate, int rows_per_batch, bf16* d_o, float* dmod,
                         int rows, int width, cudaStream_t st) {
-  gated_residual_bwd_k<<<rows / rows_per_batch, 256, 0, st>>>(dy, o, gate, rows_per_batch, d_o, dmod, width);
+  gated_residual_bwd_k<<<rows / rows_per_batch, 256, 0, st>>>(dy, o, gate, rows_per_batch, d_o, dmod, width); count_launch();
 }
 
 }  // namespace pi05

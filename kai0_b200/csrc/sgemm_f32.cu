@@ -5,6 +5,7 @@
 // C[i,j] (+)= sum_k A(i,k) * B(j,k) with operand access through small loader functors; 64x64x16 tiles,
 // 256 threads, 4x4 register micro-tiles.  These are <1% of the step's FLOPs and must stay fp32-exact.
 #include "common.cuh"
+#include "errors.h"
 #include "kernels.h"
 
 namespace pi05 {
@@ -117,7 +118,7 @@ void run(LA la, LB lb, EPI epi, int M, int N, int K, int splits, cudaStream_t st
   kps = ((kps + TK - 1) / TK) * TK;
   splits = (K + kps - 1) / kps;
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
-  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps);
+  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps); count_launch();
 }
 
 __global__ void colsum_f32_k(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
@@ -153,7 +154,7 @@ void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, 
 void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
   // dW[n, k] = sum_i dY[i, n] X[i, k] -> A(n, i) = dY[i*N + n], B(k, i) = X[i*K + k]
   run(LinearF32{dY, 1, N}, LinearF32{X, 1, K}, EpiF32{dW, K, nullptr, 0}, N, K, M, 1, st);
-  if (db) colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY, M, N, db);
+  if (db) colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY, M, N, db); count_launch();
 }
 
 void patch_embed_fwd(const float* images, const float* W, const float* bias, const float* pos, bf16* out, int n_img,
@@ -176,9 +177,9 @@ void patch_embed_bwd(const float* images, const bf16* dout, float* dW, float* db
   run(LinearBF16{dout, 1, width}, Im2colT{Im2col{images, image_size, patch, P}}, EpiF32{dW, K, nullptr, 2}, width, K,
       rows, splits, st);
   const int64_t total = static_cast<int64_t>(P) * P * width;
-  patch_dpos_k<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(dout, dpos, n_img, P * P, width);
+  patch_dpos_k<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(dout, dpos, n_img, P * P, width); count_launch();
   // dbias = column sum of dpos
-  colsum_f32_k<<<(width + 127) / 128, 128, 0, st>>>(dpos, P * P, width, dbias);
+  colsum_f32_k<<<(width + 127) / 128, 128, 0, st>>>(dpos, P * P, width, dbias); count_launch();
 }
 
 }  // namespace pi05
