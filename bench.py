@@ -1,0 +1,387 @@
+"""bench.py — the pi0.5 training step on N B200s (one process per GPU), in the driver's contract.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                    # N > 1 (NCCL, one flat all-reduce per dtype arena)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU arm (oracle port of the reference)
+
+A step = what scripts/train_pytorch.py:531-561 does per iteration for BASELINE.json configs[1]
+("pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32, 1xB200"): uint8 batch -> Observation.from_dict ->
+model(observation, actions) -> loss.mean().backward() -> (gradient all-reduce) -> clip_grad_norm_(1.0) -> AdamW step ->
+zero_grad(set_to_none).  Weights are seeded random-init of the full pi0.5 architecture (3.35 B trainable parameters),
+data is synthetic.  `value` times the step with the uint8 batch already in HBM; `e2e` times the same
+step fed from pinned host memory, with the H2D copies and the loss read-back inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# forward FLOPs per sample (SURVEY.md §8d, 2 flops/MAC, block-sparse attention) and the training multiplier
+FWD_TFLOP_PER_SAMPLE = 4.674
+TRAIN_TFLOP_PER_SAMPLE = 3 * FWD_TFLOP_PER_SAMPLE
+METRIC = "train_samples_per_sec"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic data in pinned host memory
+# ------------------------------------------------------------------------------------------------------------
+KEYS = ("base_0_rgb", "left_wrist_0_rgb", "right_wrist_0_rgb")
+
+
+def make_host_batch(B, rank, image_size=224, L=200, vocab=257152, horizon=50, adim=32, pin=True):
+    g = torch.Generator().manual_seed(1234 + rank)
+    d = {"image": {}, "image_mask": {}}
+    for k in KEYS:
+        d["image"][k] = torch.randint(0, 256, (B, image_size, image_size, 3), generator=g, dtype=torch.uint8)
+        d["image_mask"][k] = torch.ones(B, dtype=torch.bool)
+    state = torch.zeros(B, 32)
+    state[:, :14] = torch.rand(B, 14, generator=g) * 2 - 1
+    d["state"] = state
+    toks = torch.zeros(B, L, dtype=torch.int64)
+    nv = min(96, L)
+    toks[:, :nv] = torch.randint(0, vocab, (B, nv), generator=g)
+    mask = torch.zeros(B, L, dtype=torch.bool)
+    mask[:, :nv] = True
+    d["tokenized_prompt"] = toks
+    d["tokenized_prompt_mask"] = mask
+    actions = torch.randn(B, horizon, adim, generator=g)
+    actions[..., 14:] = 0
+    if pin and torch.cuda.is_available():
+        for k in KEYS:
+            d["image"][k] = d["image"][k].pin_memory()
+            d["image_mask"][k] = d["image_mask"][k].pin_memory()
+        d["state"] = d["state"].pin_memory()
+        d["tokenized_prompt"] = toks.pin_memory()
+        d["tokenized_prompt_mask"] = mask.pin_memory()
+        actions = actions.pin_memory()
+    return d, actions
+
+
+def h2d_bytes(d, actions):
+    n = actions.numel() * actions.element_size()
+    for k in KEYS:
+        n += d["image"][k].numel() + d["image_mask"][k].numel()
+    for k in ("state", "tokenized_prompt", "tokenized_prompt_mask"):
+        n += d[k].numel() * d[k].element_size()
+    return n
+
+
+def to_device(d, actions, dev):
+    out = {"image": {}, "image_mask": {}}
+    for k in KEYS:
+        out["image"][k] = d["image"][k].to(dev, non_blocking=True)
+        out["image_mask"][k] = d["image_mask"][k].to(dev, non_blocking=True)
+    for k in ("state", "tokenized_prompt", "tokenized_prompt_mask"):
+        out[k] = d[k].to(dev, non_blocking=True)
+    return out, actions.to(dev, non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, timed on the host cores (cpu_baseline / --impl reference)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
+    """Times forward + backward (torch.autograd through the oracle) of ONE sample per step on all host threads.
+    Returns (samples_per_sec, cores, sample_description, steps_done)."""
+    from oracle import pi05_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oc = O.OracleConfig() if full else O.tiny_config()
+    params = {}
+    for name, (shape, dt) in O.param_specs(oc).items():
+        params[name] = torch.empty(shape, dtype=dt).normal_(0, 0.02).requires_grad_(True)
+    b = O.synthetic_batch(oc, 1)
+
+    def one():
+        for p in params.values():
+            p.grad = None
+        loss = O.forward_loss(params, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"],
+                              b["noise"], b["time"])
+        loss.mean().backward()
+
+    t0 = time.time()
+    one()  # first step doubles as the cost probe
+    t_first = time.time() - t0
+    done_warm = 1
+    while done_warm < warmup and (time.time() - t0) + t_first * (1 + steps) < budget_s:
+        one()
+        done_warm += 1
+    k = max(1, min(steps, int((budget_s - (time.time() - t0)) / max(t_first, 1e-3))))
+    t1 = time.time()
+    for _ in range(k):
+        one()
+    dt = time.time() - t1
+    desc = (f"B=1 forward+backward of the full pi0.5 oracle per step (14.0 TFLOP), {k} timed step(s) after {done_warm} "
+            f"warm-up, {cores} threads, bf16 weights as the reference")
+    return k / dt, cores, desc, k
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]/[2]: 32)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the CPU legs may take")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="debug: tiny architecture (not a valid bench number)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32 per GPU (BASELINE.json configs[1]; configs[2] at N=8)"
+
+    # ---------------------------------------------------------------- CPU arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sps, cores, desc, k = cpu_reference(args.steps, min(args.warmup, 1), max(60.0, args.cpu_budget * 1.5),
+                                            full=not args.small)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "note": "reference's PyTorch path cannot be imported (needs patched "
+                       "transformers 4.53.2 + jax); this is its CPU oracle port (oracle/pi05_oracle.py)"},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the B200 arm needs a CUDA device (there is no CPU fallback)")
+    import torch.distributed as dist
+
+    from kai0_b200 import _lib
+    from kai0_b200.model import Observation
+    from kai0_b200.pi0_pytorch import GemmaVariant, Pi05EngineConfig, PI0Pytorch
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
+    B = args.batch
+    if args.small:
+        cfg = Pi05EngineConfig(paligemma_variant=GemmaVariant(512, 2, 1024, 8, 1, 256),
+                               action_expert_variant=GemmaVariant(256, 2, 512, 8, 1, 256), vit_width=288, vit_depth=2,
+                               vit_mlp_dim=560, vit_heads=4, vocab_size=4096)
+    else:
+        cfg = Pi05EngineConfig()
+    torch.manual_seed(1234)  # same weights on every rank (DDP would broadcast rank 0's, train_pytorch.py:441)
+    model = PI0Pytorch(cfg, max_batch=B, init_weights=False).to(dev)
+    model.reset_parameters()
+    model.check_inputs = False
+    model.train()
+    if world > 1:
+        model.enable_flat_allreduce()
+    params = [p for p in model.parameters() if p.requires_grad]
+    optim = torch.optim.AdamW(params, lr=2.5e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10, fused=True)
+
+    host_d, host_a = make_host_batch(B, rank, image_size=cfg.image_size, L=cfg.max_token_len, vocab=cfg.vocab_size,
+                                     horizon=cfg.action_horizon, adim=cfg.action_dim)
+    dev_d, dev_a = to_device(host_d, host_a, dev)
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+    lib.pi05_launch_count.restype = C.c_ulonglong
+
+    def step(from_host: bool):
+        if from_host:
+            d, a = to_device(host_d, host_a, dev)
+        else:
+            d = {"image": dict(dev_d["image"]), "image_mask": dev_d["image_mask"], "state": dev_d["state"],
+                 "tokenized_prompt": dev_d["tokenized_prompt"],
+                 "tokenized_prompt_mask": dev_d["tokenized_prompt_mask"]}
+            a = dev_a
+        obs = Observation.from_dict(d)  # uint8 NHWC -> fp32 NCHW in [-1,1] (models/model.py:129-133)
+        losses = model(obs, a)
+        loss = losses.mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+        optim.step()
+        optim.zero_grad(set_to_none=True)
+        if from_host:
+            return float(loss.item())  # device -> host read of the step's result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, from_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(k):
+            last = step(from_host)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    step(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.pi05_gemm_profile_enable(1)
+    n0 = lib.pi05_launch_count()
+    ms_dev, _ = timed(args.steps, False)
+    n1 = lib.pi05_launch_count()
+    lib.pi05_gemm_profile_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    lib.pi05_gemm_profile_report(buf, len(buf))
+    ms_e2e, last_loss = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks, peaks_kind = load_peaks()
+        samples = world * B * args.steps
+        value = samples / (ms_dev / 1e3)
+        e2e = samples / (ms_e2e / 1e3)
+        # dominant kernel: the tcgen05 GEMM class with the largest share of event time in the timed region
+        classes = []
+        for ln in buf.value.decode().strip().splitlines():
+            M, N, K, bt, epi, maj, cnt, ms = ln.split()
+            fl = 2.0 * int(M) * int(N) * int(K) * int(bt) * int(cnt)
+            classes.append({"M": int(M), "N": int(N), "K": int(K), "batch": int(bt), "epi": int(epi),
+                            "majors": int(maj), "launches": int(cnt), "ms": float(ms), "flop": fl})
+        if os.environ.get("PI05_BENCH_VERBOSE"):
+            for c in sorted(classes, key=lambda c: -c["ms"])[:40]:
+                print(f"  gemm M={c['M']:6d} N={c['N']:6d} K={c['K']:6d} b={c['batch']:5d} epi={c['epi']} maj={c['majors']} "
+                      f"x{c['launches']:4d}  {c['ms'] / args.steps:8.3f} ms/step  "
+                      f"{c['flop'] / (c['ms'] / 1e3) / 1e12:7.1f} TFLOP/s", file=sys.stderr)
+            print(f"  step {ms_dev / args.steps:.2f} ms, tcgen05 GEMMs {sum(c['ms'] for c in classes) / args.steps:.2f} ms",
+                  file=sys.stderr)
+        gemm_ms = sum(c["ms"] for c in classes)
+        gemm_flop = sum(c["flop"] for c in classes)
+        top = max(classes, key=lambda c: c["ms"]) if classes else None
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1470.0)))
+        roofline = None
+        if top:
+            ach = top["flop"] / (top["ms"] / 1e3) / 1e12
+            roofline = {
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None,
+                "kernel": f"gemm_kernel<256,{top['epi']}> M={top['M']} N={top['N']} K={top['K']} "
+                          f"majors={top['majors']} ({top['launches']} launches in the timed region)",
+                "peak_source": f"{peaks_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+                "all_tcgen05_gemms": {"tflops": gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms else None,
+                                      "share_of_step": gemm_ms / ms_dev},
+                "step_model_flops_utilisation": (value / world) * TRAIN_TFLOP_PER_SAMPLE / peak_tf,
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload if not args.small else "DEBUG small architecture (invalid as a bench number)",
+                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "optimizer": "torch.optim.AdamW(fused) + clip_grad_norm_(1.0), as scripts/train_pytorch.py",
+                       "l2": "per-step activations (>100 GB) and weights (7 GB) far exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host_d, host_a),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+            "gpu_launches": int(n1 - n0),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            del optim
+            torch.cuda.empty_cache()
+            sps, cores, desc, _ = cpu_reference(1, 0, args.cpu_budget, full=not args.small)
+            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
