@@ -131,6 +131,12 @@ typedef struct pi05_gemm_desc {
 } pi05_gemm_desc;
 int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream);
 
+/* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the GEMM -------- */
+unsigned long long pi05_launch_count(void);
+void pi05_gemm_profile_enable(int on);
+/* one text line per GEMM class: "M N K batch epilogue majors launches total_ms"; returns bytes written (host buf) */
+int pi05_gemm_profile_report(char* buf, int len);
+
 #ifdef __cplusplus
 }
 #endif

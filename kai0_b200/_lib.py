@@ -121,6 +121,9 @@ EXPORTS = (
     "pi05_forward_value",
     "pi05_get_tap",
     "pi05_gemm_bf16",
+    "pi05_launch_count",
+    "pi05_gemm_profile_enable",
+    "pi05_gemm_profile_report",
 )
 
 

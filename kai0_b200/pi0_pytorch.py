@@ -190,6 +190,13 @@ class _Node(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("skeleton module of the pi0.5 engine: call the top-level PI0Pytorch instead")
 
+    # `layers` containers index like the reference's nn.ModuleList (children are named "0", "1", ...)
+    def __getitem__(self, i):
+        return self._modules[str(int(i))]
+
+    def __len__(self):
+        return sum(1 for k in self._modules if k.isdigit())
+
 
 class _PaliGemmaWithExpert(_Node):
     def to_bfloat16_for_selected_params(self, precision: str = "bfloat16"):
@@ -541,18 +548,25 @@ class PI0Pytorch(nn.Module):
     def _engine_backward(self, dloss):
         _lib.check(_lib.lib().pi05_backward(self._engine, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
         if self._dp_group is not None:
-            import torch.distributed as dist
-
-            world = dist.get_world_size(self._dp_group)
-            for dt in (torch.bfloat16, torch.float32):
-                g = self._flat_grad[dt]
-                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp_group)
-                g.mul_(1.0 / world)
+            self._allreduce_flat_grads()
         grads = []
         for name, p in self._grad_params:
             dt, o, n, shape = self._offsets[name]
             grads.append(self._flat_grad[dt][o : o + n].view(shape))
         return grads
+
+    def _allreduce_flat_grads(self):
+        """The single exchange step of the data-parallel path: SUM all-reduce of each dtype arena over NVLink, then
+        the 1/world average DDP applies (train_pytorch.py:440-447).  Two collectives per step (bf16, fp32)."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self._dp_group)
+        for dt in (torch.bfloat16, torch.float32):
+            g = self._flat_grad[dt]
+            if g is None:
+                continue
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp_group)
+            g.mul_(1.0 / world)
 
     # ------------------------------------------------------------------ public surface
     def forward(self, observation, actions, noise=None, time=None) -> Tensor:

@@ -116,14 +116,18 @@ def test_gemma_prefix_matches_stock_transformers():
     assert not unexpected and not missing, (missing, unexpected)
     B, T = 2, 12
     x = torch.randn(B, T, g.width, generator=torch.Generator().manual_seed(0))
-    pos = torch.arange(T)[None].expand(B, T)
-    full = torch.ones(B, T, dtype=torch.bool)
-    mask4d = O.prepare_attention_masks_4d(O.make_att_2d_masks(full, torch.zeros(B, T, dtype=torch.int64)))
+    # causal attention with right-padding on the second sequence: expressible both as the reference's
+    # (pad_masks, att_masks) pair and as stock HF's 2-D attention_mask
+    pad = torch.ones(B, T, dtype=torch.bool)
+    pad[1, T - 3:] = False
+    pos = torch.cumsum(pad, dim=1) - 1
+    mask4d = O.prepare_attention_masks_4d(O.make_att_2d_masks(pad, torch.ones(B, T, dtype=torch.int64)))
     with torch.no_grad():
         got, _ = O.single_stream_forward(p, oc, "prefix", x, mask4d, pos)
-        # stock Gemma multiplies inputs_embeds by sqrt(hidden); the reference removed that (modeling_gemma.py:515-516)
-        ref = hf(inputs_embeds=x / (g.width ** 0.5), attention_mask=mask4d, position_ids=pos).last_hidden_state
-    assert H.rel_err(got, ref) < 1e-4
+        # transformers 5.x applies Gemma's sqrt(hidden) normaliser inside the token embedding only, so inputs_embeds
+        # pass through unscaled exactly as in the reference's patched file (modeling_gemma.py:515-516)
+        ref = hf(inputs_embeds=x, attention_mask=pad.to(torch.int64), position_ids=pos).last_hidden_state
+    assert H.rel_err(got[pad], ref[pad]) < 1e-5
 
 
 def test_kv_cache_decode_equals_joint_forward():
