@@ -259,6 +259,7 @@ def main():
     model = PI0Pytorch(cfg, max_batch=B, init_weights=False).to(dev)
     model.reset_parameters()
     model.check_inputs = False
+    model.direct_grads = True  # public knob: .grad = views of the flat gradient arena (no per-parameter autograd copies)
     model.train()
     if world > 1:
         model.enable_flat_allreduce()
@@ -302,8 +303,14 @@ def main():
         e0.record()
         last = None
         torch.cuda.nvtx.range_push("pi05_timed_host" if from_host else "pi05_timed_dev")
+        prof = (not from_host) and os.environ.get("PI05_CUDA_PROFILER")  # ncu --profile-from-start off
+        if prof:
+            torch.cuda.profiler.start()
         for _ in range(k):
             last = step(from_host)
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         torch.cuda.nvtx.range_pop()
         e1.record()
         barrier()

@@ -7,6 +7,11 @@
 
 namespace pi05 {
 
+// softmax_kernels.cu: vectorised single-pass variants (return false when the shape is not eligible)
+bool softmax_fwd_vec(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_keys, int n_prefix, const uint8_t* pad,
+                     const uint8_t* qpad, int q_per_token, cudaStream_t st);
+bool softmax_bwd_vec(const bf16* p, bf16* dp, int64_t ld, int64_t rows, int n_keys, float scale, cudaStream_t st);
+
 namespace {
 
 constexpr float kMaskValue = -2.3819763e38f;  // pi0_pytorch.py:159
@@ -206,12 +211,15 @@ void rope_pack_bwd(const bf16* dQ, const float* dK, const float* dV, int T, int 
 
 void softmax_fwd(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_keys, int n_prefix, const uint8_t* pad,
                  const uint8_t* qpad, int q_per_token, cudaStream_t st) {
+  if (softmax_fwd_vec(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad, q_per_token > 0 ? q_per_token : 1, st))
+    return;
   const int64_t rows = static_cast<int64_t>(batch) * rows_per_batch;
   softmax_fwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad,
                                                    q_per_token > 0 ? q_per_token : 1); count_launch();
 }
 
 void softmax_bwd(const bf16* p, bf16* dp, int64_t ld, int rows, int n_keys, float scale, cudaStream_t st) {
+  if (softmax_bwd_vec(p, dp, ld, rows, n_keys, scale, st)) return;
   softmax_bwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(p, dp, ld, rows, n_keys, scale); count_launch();
 }
 

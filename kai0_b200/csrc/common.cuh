@@ -49,18 +49,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// same 2-MUFU tanh as the GEMM epilogue (ptx.cuh::fast_tanh) so recomputed activations match the stored ones
+__device__ __forceinline__ float fast_tanh_c(float x) {
+  const float e = exp2f(x * 2.8853900817779268f);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 __device__ __forceinline__ float gelu_tanh_fw(float x) {
   const float kBeta = 0.7978845608028654f;
   const float kKappa = 0.044715f;
   const float inner = kBeta * (x + kKappa * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  return 0.5f * x * (1.0f + fast_tanh_c(inner));
 }
 __device__ __forceinline__ float gelu_tanh_bw(float x) {
   const float kBeta = 0.7978845608028654f;
   const float kKappa = 0.044715f;
   const float x2 = x * x;
   const float inner = kBeta * (x + kKappa * x2 * x);
-  const float t = tanhf(inner);
+  const float t = fast_tanh_c(inner);
   const float left = 0.5f * x * ((1.0f - t * t) * (kBeta * (1.0f + 3.0f * kKappa * x2)));
   const float right = 0.5f * (1.0f + t);
   return left + right;

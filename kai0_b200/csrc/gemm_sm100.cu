@@ -7,8 +7,8 @@
 //  modeling_paligemma.py:96-99) and all of their autograd counterparts (dgrad / wgrad), which is why both
 // operands may be K-major or MN-major.
 //
-// Warp roles (192 threads):  warp 0 = TMA producer (1 thread)   warp 1 = MMA issuer (1 thread) + TMEM owner
-//                            warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3)
+// Warp roles (320 threads):  warp 0 = TMA producer (1 thread)   warp 1 = MMA issuer (1 thread) + TMEM owner
+//                            warps 2..9 = epilogue (TMEM lane quarter = warp_idx & 3, column half = (warp-2)>>2)
 #include <cudaTypedefs.h>
 #include <cstdio>
 #include <cstdlib>
@@ -29,7 +29,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                    // two warps per TMEM lane quarter, each takes half the columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int GROUP_M = 8;
 
 template <int BN>
@@ -162,7 +163,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar0 + 8 * a, 1);
-      mbar_init(tempty_bar0 + 8 * a, 128);
+      mbar_init(tempty_bar0 + 8 * a, 32 * NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -262,6 +263,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ============================== epilogue ==============================
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
+    const int chalf = (warp_idx - 2) >> 2;  // which half of the tile's column chunks this warp drains
+    constexpr int NCH = BN_OUT / 32;
+    constexpr int CH_PER_WARP = NCH / (NUM_EPI_WARPS / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -274,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < BN_OUT / 32; ++c) {
+      for (int c = chalf * CH_PER_WARP; c < (chalf + 1) * CH_PER_WARP; ++c) {
         const int col = n0 + c * 32;
         if (col >= p.N) break;  // warp-uniform
         const int nvalid = min(32, p.N - col);

@@ -1,0 +1,171 @@
+// Vectorised single-pass masked softmax (forward / backward): one warp per score row, the whole row held in
+// registers (CH x 8 bf16 per lane, 16-byte loads), one HBM read and one write per element.
+// Same arithmetic as attn_kernels.cu::softmax_{fwd,bwd}_k (modeling_gemma.py:243-248); those remain the fallback for
+// rows longer than 2048 keys or pitches that are not a multiple of 8.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "errors.h"
+#include "kernels.h"
+
+namespace pi05 {
+
+namespace {
+
+constexpr float kMaskValue = -2.3819763e38f;  // pi0_pytorch.py:159
+
+template <int CH>
+__global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, int64_t ld, int rows_per_batch, int batch,
+                                                         int n_keys, int n_prefix, const uint8_t* __restrict__ pad,
+                                                         const uint8_t* __restrict__ qpad, int q_per_token) {
+  const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<int64_t>(batch) * rows_per_batch) return;
+  const int b = static_cast<int>(row / rows_per_batch);
+  bf16* sr = s + row * ld;
+  const uint8_t* padb = pad ? pad + static_cast<int64_t>(b) * n_prefix : nullptr;
+  bool qmasked = false;
+  if (qpad) {
+    const int tokens = rows_per_batch / q_per_token;
+    const int tok = static_cast<int>(row % rows_per_batch) / q_per_token;
+    qmasked = qpad[static_cast<int64_t>(b) * tokens + tok] == 0;
+  }
+  float v[CH][8];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int j0 = (i * 32 + lane) * 8;
+    if (j0 < ld) {
+      load8(sr + j0, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = j0 + e;
+        if (j >= n_keys) {
+          v[i][e] = -CUDART_INF_F;  // pitch padding: excluded from max / sum
+        } else {
+          const bool valid = !qmasked && (j >= n_prefix || padb == nullptr || padb[j] != 0);
+          if (!valid) v[i][e] += kMaskValue;
+          mx = fmaxf(mx, v[i][e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = -CUDART_INF_F;
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[i][e] = expf(v[i][e] - mx);  // exp(-inf) = 0 for the padding
+      sum += v[i][e];
+    }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int j0 = (i * 32 + lane) * 8;
+    if (j0 < ld) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = v[i][e] / sum;
+      store8(sr + j0, v[i]);
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) softmax_bwd_vec_k(const bf16* __restrict__ p, bf16* __restrict__ dp, int64_t ld,
+                                                         int64_t rows, int n_keys, float scale) {
+  const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* pr = p + row * ld;
+  bf16* dr = dp + row * ld;
+  float pv[CH][8], dv[CH][8];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int j0 = (i * 32 + lane) * 8;
+    if (j0 < ld) {
+      load8(pr + j0, pv[i]);
+      load8(dr + j0, dv[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (j0 + e >= n_keys) {
+          pv[i][e] = 0.f;
+          dv[i][e] = 0.f;
+        }
+        dot += pv[i][e] * dv[i][e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pv[i][e] = 0.f;
+        dv[i][e] = 0.f;
+      }
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int j0 = (i * 32 + lane) * 8;
+    if (j0 < ld) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = bfr(pv[i][e] * (dv[i][e] - dot)) * scale;
+      store8(dr + j0, o);
+    }
+  }
+}
+
+}  // namespace
+
+bool softmax_fwd_vec(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_keys, int n_prefix, const uint8_t* pad,
+                     const uint8_t* qpad, int q_per_token, cudaStream_t st) {
+  if (ld % 8 != 0 || ld > 2048 || (reinterpret_cast<uintptr_t>(s) & 15)) return false;
+  const int64_t rows = static_cast<int64_t>(batch) * rows_per_batch;
+  const int grid = ceil_div(rows, 8);
+  const int ch = static_cast<int>((ld + 255) / 256);
+#define LAUNCH_F(C)                                                                                                   \
+  softmax_fwd_vec_k<C><<<grid, 256, 0, st>>>(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad, q_per_token); \
+  count_launch();                                                                                                     \
+  break;
+  switch (ch) {
+    case 1: LAUNCH_F(1)
+    case 2: LAUNCH_F(2)
+    case 3: LAUNCH_F(3)
+    case 4: LAUNCH_F(4)
+    case 5: LAUNCH_F(5)
+    case 6: LAUNCH_F(6)
+    case 7: LAUNCH_F(7)
+    default: LAUNCH_F(8)
+  }
+#undef LAUNCH_F
+  return true;
+}
+
+bool softmax_bwd_vec(const bf16* p, bf16* dp, int64_t ld, int64_t rows, int n_keys, float scale, cudaStream_t st) {
+  if (ld % 8 != 0 || ld > 2048 || (reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(dp) & 15))
+    return false;
+  const int grid = ceil_div(rows, 8);
+  const int ch = static_cast<int>((ld + 255) / 256);
+#define LAUNCH_B(C)                                                               \
+  softmax_bwd_vec_k<C><<<grid, 256, 0, st>>>(p, dp, ld, rows, n_keys, scale);    \
+  count_launch();                                                                 \
+  break;
+  switch (ch) {
+    case 1: LAUNCH_B(1)
+    case 2: LAUNCH_B(2)
+    case 3: LAUNCH_B(3)
+    case 4: LAUNCH_B(4)
+    case 5: LAUNCH_B(5)
+    case 6: LAUNCH_B(6)
+    case 7: LAUNCH_B(7)
+    default: LAUNCH_B(8)
+  }
+#undef LAUNCH_B
+  return true;
+}
+
+}  // namespace pi05

@@ -231,6 +231,12 @@ class _EngineFunction(torch.autograd.Function):
     def backward(ctx, dloss):
         model = ctx.model
         grads = model._engine_backward(dloss.contiguous())
+        if model.direct_grads:
+            # engine-owned gradients: .grad of every parameter is (a view of) the flat gradient arena; autograd only
+            # sees the anchor.  Skips ~700 per-parameter AccumulateGrad copies per step.
+            for (_, p), g in zip(model._grad_params, grads):
+                p.grad = g
+            return (None, None, None, None, None, torch.zeros_like(model._grad_anchor))
         return (None, None, None, None, None, *grads)
 
 
@@ -300,6 +306,10 @@ class PI0Pytorch(nn.Module):
         if init_weights:
             self.reset_parameters()
         self.check_inputs = True  # validate token ids on the host (one sync); benchmarks turn it off
+        # False (default): gradients flow through autograd per parameter (DDP hooks work, as train_pytorch.py:441 needs).
+        # True: backward assigns .grad = view of the flat gradient arena directly (single GPU or enable_flat_allreduce).
+        self.direct_grads = False
+        self._grad_anchor = None
 
         self._engine = None
         self._engine_key = None
@@ -351,6 +361,22 @@ class PI0Pytorch(nn.Module):
             self._destroy_engine()
         return self
 
+    def state_dict(self, *args, **kwargs):
+        """Checkpoints must not see the flat arenas: `safetensors.torch.save_model` (train_pytorch.py:167) refuses
+        tensors that are partial views of a larger storage.  Values are therefore returned as independent copies
+        (the tied `paligemma.lm_head.weight` / `embed_tokens.weight` pair shares ONE copy, as in the reference)."""
+        sd = super().state_dict(*args, **kwargs)
+        if kwargs.get("keep_vars", False):
+            return sd
+        seen = {}
+        for k in list(sd.keys()):
+            t = sd[k]
+            key = (t.data_ptr(), t.numel(), t.dtype)
+            if key not in seen:
+                seen[key] = t.detach().clone()
+            sd[k] = seen[key]
+        return sd
+
     def gradient_checkpointing_enable(self):
         """pi0_pytorch.py:126-133.  Accepted for script compatibility; the engine never recomputes (180 GB HBM)."""
         self.gradient_checkpointing_enabled = True
@@ -369,6 +395,7 @@ class PI0Pytorch(nn.Module):
         import torch.distributed as dist
 
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        self.direct_grads = True  # no DDP hooks to feed, so gradients can be handed over without autograd copies
 
     # ------------------------------------------------------------------ engine lifecycle
     def _device(self):
@@ -588,6 +615,10 @@ class PI0Pytorch(nn.Module):
             return self._engine_forward(pack, actions, noise, time)
         named = dict(self.named_parameters())
         self._grad_params = [(n, named[n]) for n in self._offsets if n not in _UNUSED and named[n].requires_grad]
+        if self.direct_grads:
+            if self._grad_anchor is None or self._grad_anchor.device != dev:
+                self._grad_anchor = torch.zeros(1, device=dev, requires_grad=True)
+            return _EngineFunction.apply(self, pack, actions, noise, time, self._grad_anchor)
         return _EngineFunction.apply(self, pack, actions, noise, time, *[p for _, p in self._grad_params])
 
     @torch.no_grad()
