@@ -1,0 +1,297 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 bf16 GEMM: a cluster of two CTAs on one TPC computes a 256 x 256
+// output tile.  Each CTA stages its own 128 x 64 A slice and HALF of the 256 x 64 B slice; the leader CTA's single
+// MMA thread issues UMMA 256x256x16 that reads A and B from both CTAs' shared memory and writes 128 accumulator rows
+// into each CTA's TMEM.  Per-CTA shared-memory fill traffic per flop is 2/3 of the 1-CTA kernel's (32 KB instead of
+// 48 KB per 128x256x64 MMA block) and the ring is 6 stages deep instead of 4.
+//
+// Synchronisation (all mbarriers live at identical offsets in both CTAs):
+//   full[s]   (leader's copy is the one waited on, count 2): leader producer arrive.expect_tx(both CTAs' bytes) +
+//             peer producer remote arrive; both CTAs' TMA loads complete_tx on the LEADER's barrier (.cta_group::2).
+//   empty[s]  (count 1, per CTA): tcgen05.commit ... multicast::cluster to both CTAs frees the slot for both producers.
+//   tfull[a]  (count 1, per CTA): multicast commit after the last k-block -> each CTA's epilogue warps.
+//   tempty[a] (leader's copy, count 2 x 256): every epilogue thread of both CTAs arrives (peer: remote arrive).
+#include <cstdio>
+
+#include "errors.h"
+#include "gemm_host.h"
+
+namespace pi05 {
+
+using namespace gemm_detail;
+
+namespace {
+
+constexpr int BN2 = 256;
+constexpr int STAGES2 = 6;
+constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;              // 16 KiB: this CTA's half of the B tile
+constexpr int STAGE_BYTES2 = A_STAGE_BYTES + B_HALF_BYTES;    // 32 KiB
+constexpr int TILE_BYTES2 = STAGES2 * STAGE_BYTES2;           // 192 KiB
+constexpr int SMEM_BYTES2 = TILE_BYTES2 + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+// Arrive on the barrier at the same offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + STAGES2 * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + TILE_BYTES2;
+  const uint32_t full_bar0 = bar_base;
+  const uint32_t empty_bar0 = bar_base + 8 * STAGES2;
+  const uint32_t tfull_bar0 = bar_base + 16 * STAGES2;
+  const uint32_t tempty_bar0 = tfull_bar0 + 16;
+  const uint32_t tmem_slot = tempty_bar0 + 16;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full_bar0 + 8 * s, 2);
+      mbar_init(empty_bar0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar0 + 8 * a, 1);
+      mbar_init(tempty_bar0 + 8 * a, 2 * 32 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc2(tmem_slot, 2 * BN2);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / multicast
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // the pair walks "pair tiles": two vertically adjacent 128-row blocks x one 256-column block
+  KParams pp = p;
+  pp.num_m = (p.num_m + 1) / 2;
+  const int total_tiles = pp.num_m * pp.num_n * pp.batch;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  constexpr int BN_OUT = (EPI == EPI_GEGLU) ? BN2 / 2 : BN2;
+
+  if (warp_idx == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const TileCoord tc = decode_tile(tile, pp);
+        const int m0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM;
+        const int n0 = tc.n_blk * BN_OUT;
+        const int za0 = p.a_b0 ? tc.z0 : 0, za1 = p.a_b1 ? tc.z1 : 0;
+        const int zb0 = p.b_b0 ? tc.z0 : 0, zb1 = p.b_b1 ? tc.z1 : 0;
+        // this CTA's half of the B tile (rows of the [N, K] operand)
+        const int nb = (EPI == EPI_GEGLU) ? (leader ? n0 : p.N + n0) : n0 + static_cast<int>(rank) * (BN2 / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar0 + 8 * stage, phase ^ 1);
+          const uint32_t full = full_bar0 + 8 * stage;
+          if (leader) mbar_arrive_expect_tx(full, 2 * STAGE_BYTES2);
+          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b0 + stage * B_HALF_BYTES;
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_4d_2sm(sa, &tma_a, full, k0, m0, za0, za1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_4d_2sm(sa + i * (BK * 128), &tma_a, full, m0 + 64 * i, k0, za0, za1);
+          }
+          if (!p.b_mn) {
+            tma_load_4d_2sm(sb, &tma_b, full, k0, nb, zb0, zb1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < (BN2 / 2) / 64; ++i)
+              tma_load_4d_2sm(sb + i * (BK * 128), &tma_b, full, nb + 64 * i, k0, zb0, zb1);
+          }
+          if (!leader) mbar_arrive_cluster(full, 0);  // "my loads for this stage are in flight"
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, a_sbo = p.a_mn ? p.mn_sbo : 1024, a_kstep = p.a_mn ? 2048 : 32;
+      const uint32_t b_lbo = p.b_mn ? p.mn_lbo : 16, b_sbo = p.b_mn ? p.mn_sbo : 1024, b_kstep = p.b_mn ? 2048 : 32;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b0 + stage * B_HALF_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t da = make_smem_desc_sw128(sa + j * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = make_smem_desc_sw128(sb + j * b_kstep, b_lbo, b_sbo);
+            umma2_bf16(d_tmem, da, db, p.idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit2(empty_bar0 + 8 * stage);
+          if (kb == p.num_kb - 1) umma_commit2(tfull_bar0 + 8 * acc);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue (both CTAs, own 128 rows) ==============================
+    const int q = warp_idx & 3;
+    const int chalf = (warp_idx - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const TileCoord tc = decode_tile(tile, pp);
+      const int row = (2 * tc.m_blk + static_cast<int>(rank)) * BM + q * 32 + lane;
+      const int n0 = tc.n_blk * BN_OUT;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
+      epilogue_tile<BN2, EPI>(p, tc.z0, tc.z1, row, row_ok, n0, t_base, chalf);
+      tc_fence_before();
+      if (leader)
+        mbar_arrive(tempty_bar0 + 8 * acc);
+      else
+        mbar_arrive_cluster(tempty_bar0 + 8 * acc, 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still multicast into this CTA
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * BN2);
+  }
+}
+
+template <int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t stream, char* err, int err_len) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2);
+    if (e != cudaSuccess) {
+      if (err) snprintf(err, err_len, "cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  static int sms = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const int pairs = ((kp.num_m + 1) / 2) * kp.num_n * kp.batch;
+  int clusters = sms / 2;
+  if (pairs < clusters) clusters = pairs;
+  gemm2_kernel<EPI><<<2 * clusters, NUM_THREADS, SMEM_BYTES2, stream>>>(ta, tb, kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) snprintf(err, err_len, "gemm2 launch: %s", cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_gemm2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cudaStream_t s, char* err,
+                 int err_len) {
+  switch (epi) {
+    case EPI_STORE: return launch2<EPI_STORE>(ta, tb, kp, s, err, err_len);
+    case EPI_SCALE: return launch2<EPI_SCALE>(ta, tb, kp, s, err, err_len);
+    case EPI_BIAS: return launch2<EPI_BIAS>(ta, tb, kp, s, err, err_len);
+    case EPI_BIAS_GELU: return launch2<EPI_BIAS_GELU>(ta, tb, kp, s, err, err_len);
+    case EPI_RES: return launch2<EPI_RES>(ta, tb, kp, s, err, err_len);
+    case EPI_GEGLU: return launch2<EPI_GEGLU>(ta, tb, kp, s, err, err_len);
+    case EPI_F32: return launch2<EPI_F32>(ta, tb, kp, s, err, err_len);
+    default:
+      if (err) snprintf(err, err_len, "unknown epilogue %d", epi);
+      return 1;
+  }
+}
+
+}  // namespace pi05

@@ -16,11 +16,13 @@ struct LinearF32 {  // element (r,k) at p[r*sr + k*sk]
   const float* p;
   int64_t sr, sk;
   __device__ __forceinline__ float operator()(int r, int k) const { return p[r * sr + k * sk]; }
+  __device__ __forceinline__ bool k_fast() const { return sk == 1; }  // which index is contiguous in memory
 };
 struct LinearBF16 {
   const bf16* p;
   int64_t sr, sk;
   __device__ __forceinline__ float operator()(int r, int k) const { return __bfloat162float(p[r * sr + k * sk]); }
+  __device__ __forceinline__ bool k_fast() const { return sk == 1; }
 };
 struct Im2col {  // row = img*P*P + prow*P + pcol ; k = ch*p*p + py*p + px
   const float* img;
@@ -31,10 +33,12 @@ struct Im2col {  // row = img*P*P + prow*P + pcol ; k = ch*p*p + py*p + px
     const int ch = k / pp, py = (k % pp) / p, px = k % p;
     return img[(static_cast<int64_t>(im) * 3 + ch) * S * S + static_cast<int64_t>(pr * p + py) * S + pc * p + px];
   }
+  __device__ __forceinline__ bool k_fast() const { return true; }
 };
 struct Im2colT {  // transposed roles: "row" = k-feature index, "k" = patch-row index  (for wgrad: B(j=feature, kk=row))
   Im2col base;
   __device__ __forceinline__ float operator()(int feat, int row) const { return base(row, feat); }
+  __device__ __forceinline__ bool k_fast() const { return false; }
 };
 
 struct EpiF32 {  // C fp32 [M,N] row-major (+bias[j]) ; accumulate / atomic variants
@@ -42,8 +46,8 @@ struct EpiF32 {  // C fp32 [M,N] row-major (+bias[j]) ; accumulate / atomic vari
   int64_t ldc;
   const float* bias;
   int mode;  // 0 store, 1 accumulate (+=), 2 atomicAdd
-  __device__ __forceinline__ void operator()(int i, int j, float v) const {
-    if (bias) v = __fadd_rn(v, bias[j]);
+  __device__ __forceinline__ void operator()(int i, int j, float v, bool first) const {
+    if (bias && first) v = __fadd_rn(v, bias[j]);
     float* c = C + i * ldc + j;
     if (mode == 0) *c = v;
     else if (mode == 1) *c += v;
@@ -55,7 +59,7 @@ struct EpiPatch {  // out bf16 [rows, width] = bf( (acc + bias[c]) + pos[patch, 
   int width, patches;
   const float* bias;
   const float* pos;
-  __device__ __forceinline__ void operator()(int i, int j, float v) const {
+  __device__ __forceinline__ void operator()(int i, int j, float v, bool) const {
     v = __fadd_rn(v, bias[j]);
     v = __fadd_rn(v, pos[static_cast<int64_t>(i % patches) * width + j]);
     out[static_cast<int64_t>(i) * width + j] = __float2bfloat16_rn(v);
@@ -78,13 +82,21 @@ __global__ void __launch_bounds__(256) sgemm_k(LA la, LB lb, EPI epi, int M, int
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += TK) {
+    // consecutive threads walk whichever index is contiguous in memory for that operand (coalesced tile loads)
+    const bool ak = la.k_fast(), bk = lb.k_fast();
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int e = threadIdx.x + r * 256;  // 0..1023
-      const int kk = e & 15, ii = e >> 4;
-      const int gi = i0 + ii, gj = j0 + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < M && gk < kend) ? la(gi, gk) : 0.f;
-      Bs[kk][ii] = (gj < N && gk < kend) ? lb(gj, gk) : 0.f;
+      {
+        const int kk = ak ? (e & 15) : (e >> 6), ii = ak ? (e >> 4) : (e & 63);
+        const int gi = i0 + ii, gk = k0 + kk;
+        As[kk][ii] = (gi < M && gk < kend) ? la(gi, gk) : 0.f;
+      }
+      {
+        const int kk = bk ? (e & 15) : (e >> 6), ii = bk ? (e >> 4) : (e & 63);
+        const int gj = j0 + ii, gk = k0 + kk;
+        Bs[kk][ii] = (gj < N && gk < kend) ? lb(gj, gk) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(256) sgemm_k(LA la, LB lb, EPI epi, int M, int
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
-      if (i < M && j < N) epi(i, j, acc[x][y]);
+      if (i < M && j < N) epi(i, j, acc[x][y], blockIdx.z == 0);
     }
 }
 
@@ -142,13 +154,27 @@ __global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ 
 
 }  // namespace
 
+// Small-M problems (M = batch) expose only a handful of 64x64 tiles: split the contraction across blockIdx.z and
+// combine with atomics so the weight stream is pulled by enough SMs (these linears are weight-bandwidth bound).
+static int auto_splits(int M, int N, int K) {
+  const int blocks = ((M + TM - 1) / TM) * ((N + TN - 1) / TN);
+  if (blocks >= 120 || K < 256) return 1;
+  int s = (296 + blocks - 1) / blocks;
+  const int maxs = K / 64;
+  return s < maxs ? s : (maxs > 0 ? maxs : 1);
+}
+
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st) {
-  run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, 0}, M, N, K, 1, st);
+  const int sp = auto_splits(M, N, K);
+  if (sp > 1) cudaMemsetAsync(Y, 0, static_cast<size_t>(M) * N * sizeof(float), st);
+  run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, sp > 1 ? 2 : 0}, M, N, K, sp, st);
 }
 
 void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, int accumulate, cudaStream_t st) {
   // dX[i, k] = sum_n dY[i, n] W[n, k]  -> A(i, n) = dY, B(k, n) = W[n*K + k]
-  run(LinearF32{dY, N, 1}, LinearF32{W, 1, K}, EpiF32{dX, K, nullptr, accumulate ? 1 : 0}, M, K, N, 1, st);
+  const int sp = auto_splits(M, K, N);
+  if (sp > 1 && !accumulate) cudaMemsetAsync(dX, 0, static_cast<size_t>(M) * K * sizeof(float), st);
+  run(LinearF32{dY, N, 1}, LinearF32{W, 1, K}, EpiF32{dX, K, nullptr, sp > 1 ? 2 : (accumulate ? 1 : 0)}, M, K, N, sp, st);
 }
 
 void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
