@@ -229,6 +229,7 @@ int engine_plan(Engine& e, bool dry) {
     e.g_f32a = ar.get<float>(mx(M2 * E, B * 3 * E));
     e.g_f32b = ar.get<float>(mx(M2 * E, B * 3 * E));
     e.g_f32c = ar.get<float>(mx(M2 * E, B * 3 * E));
+    e.g_dcond_part = ar.get<float>(nmods * B * E);
     e.g_acc_elems = static_cast<size_t>(mx(mx(4 * W + 2 * vmlp, 4 * D), mx(T * W + W, 3 * W * 14 * 14 * 3)) + 1024);
     e.g_acc = ar.get<float>(e.g_acc_elems);
     e.g_embed_scratch = ar.get<float>(B * e.L * D);
@@ -411,6 +412,24 @@ int engine_resolve_params(Engine& e) {
     set_error(e.err);
     return 7;
   }
+  {  // are the 2*depth+1 adaRMS dense weights / biases (and their grads) uniformly strided?  (arena order makes them so)
+    const int depth = c.paligemma.depth, nm = 2 * depth + 1;
+    auto W = [&](int j) -> const PRef& { return j == 2 * depth ? e.ex_norm_dw : ((j & 1) ? e.ex[j / 2].post_dw : e.ex[j / 2].in_dw); };
+    auto Bz = [&](int j) -> const PRef& { return j == 2 * depth ? e.ex_norm_db : ((j & 1) ? e.ex[j / 2].post_db : e.ex[j / 2].in_db); };
+    e.ada_uniform = nm >= 2;
+    e.ada_uniform_grad = nm >= 2 && W(0).grad != nullptr;
+    if (nm >= 2) {
+      e.ada_wstride = W(1).d<float>() - W(0).d<float>();
+      e.ada_bstride = Bz(1).d<float>() - Bz(0).d<float>();
+      for (int j = 0; j < nm; ++j) {
+        if (W(j).d<float>() != W(0).d<float>() + j * e.ada_wstride || Bz(j).d<float>() != Bz(0).d<float>() + j * e.ada_bstride)
+          e.ada_uniform = false;
+        if (e.ada_uniform_grad && (W(j).g<float>() != W(0).g<float>() + j * e.ada_wstride ||
+                                   Bz(j).g<float>() != Bz(0).g<float>() + j * e.ada_bstride))
+          e.ada_uniform_grad = false;
+      }
+    }
+  }
   e.bound = true;
   return 0;
 }
@@ -536,6 +555,14 @@ int suffix_frontend(Engine& e, const float* x_t, const float* time, int B) {
   linear_f32(e.t1s, e.tout_w.d<float>(), e.tout_b.d<float>(), e.t2, B, E, E, st);
   silu_fwd(e.t2, e.cond, static_cast<int64_t>(B) * E, st);
   const int64_t ms = static_cast<int64_t>(B) * 3 * E;
+  if (e.ada_uniform && depth > 0) {
+    // all 2*depth+1 modulation layers in ONE launch (weights uniformly strided in the fp32 arena)
+    linear_f32_batched(e.cond, e.ex[0].in_dw.d<float>(), e.ex[0].in_db.d<float>(), e.mods, B, 3 * E, E, 2 * depth + 1,
+                       e.ada_wstride, e.ada_bstride, ms, st);
+    add_tap(e, "suffix_embs", e.a2[0].x_in, static_cast<int64_t>(M2) * E, PI05_BF16);
+    add_tap(e, "adarms_cond", e.cond, static_cast<int64_t>(B) * E, PI05_F32);
+    return 0;
+  }
   for (int l = 0; l < depth; ++l) {
     linear_f32(e.cond, e.ex[l].in_dw.d<float>(), e.ex[l].in_db.d<float>(), e.mods + (2 * l) * ms, B, 3 * E, E, st);
     linear_f32(e.cond, e.ex[l].post_dw.d<float>(), e.ex[l].post_db.d<float>(), e.mods + (2 * l + 1) * ms, B, 3 * E, E,

@@ -118,6 +118,10 @@ struct Engine {
   int* g_first = nullptr;
   size_t g_acc_elems = 0;
 
+  // adaRMS dense layers laid out with one uniform stride (fp32 arena order) -> batched single-launch linears
+  bool ada_uniform = false, ada_uniform_grad = false;
+  int64_t ada_wstride = 0, ada_bstride = 0;
+  float* g_dcond_part = nullptr;
   bool taps_enabled = false;
   std::map<std::string, Tap> taps;
   cudaStream_t stream = nullptr;

@@ -357,6 +357,12 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
   linear_f32_wgrad(e.g_f32a, e.x_t, e.ain_w.g<float>(), e.ain_b.g<float>(), M2, E, ad, st);
   float* dcond = e.g_f32b;
   fill_zero(dcond, static_cast<size_t>(B) * E * sizeof(float), st);
+  if (e.ada_uniform && e.ada_uniform_grad && depth > 0) {
+    linear_f32_wgrad_batched(e.g_dmods, e.cond, e.ex[0].in_dw.g<float>(), e.ex[0].in_db.g<float>(), B, 3 * E, E, nmods, ms,
+                             e.ada_wstride, e.ada_bstride, st);
+    linear_f32_dgrad_batched_sum(e.g_dmods, e.ex[0].in_dw.d<float>(), dcond, e.g_dcond_part, B, 3 * E, E, nmods, ms,
+                                 e.ada_wstride, st);
+  } else
   for (int j = 0; j < nmods; ++j) {
     const PRef& dw = (j == 2 * depth) ? e.ex_norm_dw : ((j & 1) ? e.ex[j / 2].post_dw : e.ex[j / 2].in_dw);
     const PRef& db = (j == 2 * depth) ? e.ex_norm_db : ((j & 1) ? e.ex[j / 2].post_db : e.ex[j / 2].in_db);

@@ -98,6 +98,13 @@ void linear_f32(const float* X, const float* W, const float* bias, float* Y, int
 void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, int accumulate, cudaStream_t st);
 // dW[N,K] = dY[M,N]^T X[M,K];  db[N] = colsum(dY)  (db may be null)
 void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st);
+// Batched variants for the 2*depth+1 adaRMS dense layers (uniformly strided weights): one launch each.
+void linear_f32_batched(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int batch,
+                        int64_t w_stride, int64_t b_stride, int64_t y_stride, cudaStream_t st);
+void linear_f32_wgrad_batched(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, int batch,
+                              int64_t dy_stride, int64_t w_stride, int64_t b_stride, cudaStream_t st);
+void linear_f32_dgrad_batched_sum(const float* dY, const float* W, float* dX, float* scratch, int M, int N, int K,
+                                  int batch, int64_t dy_stride, int64_t w_stride, cudaStream_t st);
 // Patch embedding = conv 14x14/14 as an fp32 GEMM over an implicit im2col (modeling_siglip.py:220-226,271-282):
 // out[img, patch, c] = bf( sum W[c, ch,py,px] * img[ch, ...] + bias[c] + pos[patch, c] )
 void patch_embed_fwd(const float* images, const float* W, const float* bias, const float* pos, bf16* out, int n_img,

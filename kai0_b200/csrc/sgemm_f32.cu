@@ -12,21 +12,25 @@ namespace pi05 {
 
 namespace {
 
-struct LinearF32 {  // element (r,k) at p[r*sr + k*sk]
+struct LinearF32 {  // element (r,k) at p[r*sr + k*sk]; batch z at p + z*sz
   const float* p;
   int64_t sr, sk;
+  int64_t sz = 0;
+  __device__ __forceinline__ LinearF32 at(int z) const { return LinearF32{p + z * sz, sr, sk, sz}; }
   __device__ __forceinline__ float operator()(int r, int k) const { return p[r * sr + k * sk]; }
   __device__ __forceinline__ bool k_fast() const { return sk == 1; }  // which index is contiguous in memory
 };
 struct LinearBF16 {
   const bf16* p;
   int64_t sr, sk;
+  __device__ __forceinline__ LinearBF16 at(int) const { return *this; }
   __device__ __forceinline__ float operator()(int r, int k) const { return __bfloat162float(p[r * sr + k * sk]); }
   __device__ __forceinline__ bool k_fast() const { return sk == 1; }
 };
 struct Im2col {  // row = img*P*P + prow*P + pcol ; k = ch*p*p + py*p + px
   const float* img;
   int S, p, P;  // image size, patch, patches per side
+  __device__ __forceinline__ Im2col at(int) const { return *this; }
   __device__ __forceinline__ float operator()(int r, int k) const {
     const int pp = p * p;
     const int im = r / (P * P), pr = (r / P) % P, pc = r % P;
@@ -37,6 +41,7 @@ struct Im2col {  // row = img*P*P + prow*P + pcol ; k = ch*p*p + py*p + px
 };
 struct Im2colT {  // transposed roles: "row" = k-feature index, "k" = patch-row index  (for wgrad: B(j=feature, kk=row))
   Im2col base;
+  __device__ __forceinline__ Im2colT at(int) const { return *this; }
   __device__ __forceinline__ float operator()(int feat, int row) const { return base(row, feat); }
   __device__ __forceinline__ bool k_fast() const { return false; }
 };
@@ -46,6 +51,10 @@ struct EpiF32 {  // C fp32 [M,N] row-major (+bias[j]) ; accumulate / atomic vari
   int64_t ldc;
   const float* bias;
   int mode;  // 0 store, 1 accumulate (+=), 2 atomicAdd
+  int64_t cz = 0, bz = 0;  // batch strides of C and bias
+  __device__ __forceinline__ EpiF32 at(int z) const {
+    return EpiF32{C + z * cz, ldc, bias ? bias + z * bz : nullptr, mode, cz, bz};
+  }
   __device__ __forceinline__ void operator()(int i, int j, float v, bool first) const {
     if (bias && first) v = __fadd_rn(v, bias[j]);
     float* c = C + i * ldc + j;
@@ -59,6 +68,7 @@ struct EpiPatch {  // out bf16 [rows, width] = bf( (acc + bias[c]) + pos[patch, 
   int width, patches;
   const float* bias;
   const float* pos;
+  __device__ __forceinline__ EpiPatch at(int) const { return *this; }
   __device__ __forceinline__ void operator()(int i, int j, float v, bool) const {
     v = __fadd_rn(v, bias[j]);
     v = __fadd_rn(v, pos[static_cast<int64_t>(i % patches) * width + j]);
@@ -69,12 +79,17 @@ struct EpiPatch {  // out bf16 [rows, width] = bf( (acc + bias[c]) + pos[patch, 
 constexpr int TM = 64, TN = 64, TK = 16;
 
 template <class LA, class LB, class EPI>
-__global__ void __launch_bounds__(256) sgemm_k(LA la, LB lb, EPI epi, int M, int N, int K, int k_per_split) {
+__global__ void __launch_bounds__(256) sgemm_k(LA la_, LB lb_, EPI epi_, int M, int N, int K, int k_per_split,
+                                               int batched) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
+  // blockIdx.z is either a split-K slice (atomic epilogue) or, in batched mode, an independent problem
+  const LA la = batched ? la_.at(blockIdx.z) : la_;
+  const LB lb = batched ? lb_.at(blockIdx.z) : lb_;
+  const EPI epi = batched ? epi_.at(blockIdx.z) : epi_;
   const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
-  const int kbeg = blockIdx.z * k_per_split;
-  const int kend = min(K, kbeg + k_per_split);
+  const int kbeg = batched ? 0 : blockIdx.z * k_per_split;
+  const int kend = batched ? K : min(K, kbeg + k_per_split);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -119,7 +134,7 @@ __global__ void __launch_bounds__(256) sgemm_k(LA la, LB lb, EPI epi, int M, int
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
-      if (i < M && j < N) epi(i, j, acc[x][y], blockIdx.z == 0);
+      if (i < M && j < N) epi(i, j, acc[x][y], batched || blockIdx.z == 0);
     }
 }
 
@@ -130,7 +145,22 @@ void run(LA la, LB lb, EPI epi, int M, int N, int K, int splits, cudaStream_t st
   kps = ((kps + TK - 1) / TK) * TK;
   splits = (K + kps - 1) / kps;
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
-  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps); count_launch();
+  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps, 0); count_launch();
+}
+
+template <class LA, class LB, class EPI>
+void run_batched(LA la, LB lb, EPI epi, int M, int N, int K, int batch, cudaStream_t st) {
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, batch);
+  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, K, 1); count_launch();
+}
+
+__global__ void reduce_batches_k(const float* __restrict__ part, float* __restrict__ out, int64_t n, int batch) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < batch; ++z) s += part[z * n + i];  // fixed order: deterministic
+    out[i] = s;
+  }
 }
 
 __global__ void colsum_f32_k(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
@@ -154,33 +184,45 @@ __global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ 
 
 }  // namespace
 
-// Small-M problems (M = batch) expose only a handful of 64x64 tiles: split the contraction across blockIdx.z and
-// combine with atomics so the weight stream is pulled by enough SMs (these linears are weight-bandwidth bound).
-static int auto_splits(int M, int N, int K) {
-  const int blocks = ((M + TM - 1) / TM) * ((N + TN - 1) / TN);
-  if (blocks >= 120 || K < 256) return 1;
-  int s = (296 + blocks - 1) / blocks;
-  const int maxs = K / 64;
-  return s < maxs ? s : (maxs > 0 ? maxs : 1);
-}
-
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st) {
-  const int sp = auto_splits(M, N, K);
-  if (sp > 1) cudaMemsetAsync(Y, 0, static_cast<size_t>(M) * N * sizeof(float), st);
-  run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, sp > 1 ? 2 : 0}, M, N, K, sp, st);
+  run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, 0}, M, N, K, 1, st);
 }
 
 void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, int accumulate, cudaStream_t st) {
   // dX[i, k] = sum_n dY[i, n] W[n, k]  -> A(i, n) = dY, B(k, n) = W[n*K + k]
-  const int sp = auto_splits(M, K, N);
-  if (sp > 1 && !accumulate) cudaMemsetAsync(dX, 0, static_cast<size_t>(M) * K * sizeof(float), st);
-  run(LinearF32{dY, N, 1}, LinearF32{W, 1, K}, EpiF32{dX, K, nullptr, sp > 1 ? 2 : (accumulate ? 1 : 0)}, M, K, N, sp, st);
+  run(LinearF32{dY, N, 1}, LinearF32{W, 1, K}, EpiF32{dX, K, nullptr, accumulate ? 1 : 0}, M, K, N, 1, st);
 }
 
 void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
   // dW[n, k] = sum_i dY[i, n] X[i, k] -> A(n, i) = dY[i*N + n], B(k, i) = X[i*K + k]
   run(LinearF32{dY, 1, N}, LinearF32{X, 1, K}, EpiF32{dW, K, nullptr, 0}, N, K, M, 1, st);
   if (db) colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY, M, N, db); count_launch();
+}
+
+// `batch` independent linears that share X: Y[z] = X W[z]^T + bias[z]  (all 37 adaRMS modulation layers in one launch)
+void linear_f32_batched(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int batch,
+                        int64_t w_stride, int64_t b_stride, int64_t y_stride, cudaStream_t st) {
+  run_batched(LinearF32{X, K, 1, 0}, LinearF32{W, K, 1, w_stride}, EpiF32{Y, N, bias, 0, y_stride, b_stride}, M, N, K,
+              batch, st);
+}
+// dW[z] = dY[z]^T X ; db[z] = colsum(dY[z])
+void linear_f32_wgrad_batched(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, int batch,
+                              int64_t dy_stride, int64_t w_stride, int64_t b_stride, cudaStream_t st) {
+  run_batched(LinearF32{dY, 1, N, dy_stride}, LinearF32{X, 1, K, 0}, EpiF32{dW, K, nullptr, 0, w_stride, 0}, N, K, M,
+              batch, st);
+  for (int z = 0; z < batch; ++z) {
+    colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY + z * dy_stride, M, N, db + z * b_stride);
+    count_launch();
+  }
+}
+// dX = sum_z dY[z] W[z]: per-z partials into `scratch` [batch, M, K], then a fixed-order reduction (deterministic)
+void linear_f32_dgrad_batched_sum(const float* dY, const float* W, float* dX, float* scratch, int M, int N, int K,
+                                  int batch, int64_t dy_stride, int64_t w_stride, cudaStream_t st) {
+  run_batched(LinearF32{dY, N, 1, dy_stride}, LinearF32{W, 1, K, w_stride},
+              EpiF32{scratch, K, nullptr, 0, static_cast<int64_t>(M) * K, 0}, M, K, N, batch, st);
+  const int64_t n = static_cast<int64_t>(M) * K;
+  reduce_batches_k<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(scratch, dX, n, batch);
+  count_launch();
 }
 
 void patch_embed_fwd(const float* images, const float* W, const float* bias, const float* pos, bf16* out, int n_img,

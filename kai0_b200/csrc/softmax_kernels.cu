@@ -36,7 +36,12 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
   for (int i = 0; i < CH; ++i) {
     const int j0 = (i * 32 + lane) * 8;
     if (j0 < ld) {
-      load8(sr + j0, v[i]);
+      if (j0 + 8 <= n_keys) {
+        load8(sr + j0, v[i]);
+      } else {  // last chunk: never read the (unwritten) pitch padding
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = (j0 + e < n_keys) ? __bfloat162float(sr[j0 + e]) : 0.f;
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = j0 + e;
@@ -88,16 +93,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_vec_k(const bf16* __restrict_
   for (int i = 0; i < CH; ++i) {
     const int j0 = (i * 32 + lane) * 8;
     if (j0 < ld) {
-      load8(pr + j0, pv[i]);
-      load8(dr + j0, dv[i]);
+      if (j0 + 8 <= n_keys) {
+        load8(pr + j0, pv[i]);
+        load8(dr + j0, dv[i]);
+      } else {  // last chunk: the dP pitch padding was never written
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (j0 + e >= n_keys) {
-          pv[i][e] = 0.f;
-          dv[i][e] = 0.f;
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = j0 + e < n_keys;
+          pv[i][e] = ok ? __bfloat162float(pr[j0 + e]) : 0.f;
+          dv[i][e] = ok ? __bfloat162float(dr[j0 + e]) : 0.f;
         }
-        dot += pv[i][e] * dv[i][e];
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot += pv[i][e] * dv[i][e];
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
