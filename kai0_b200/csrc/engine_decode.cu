@@ -185,7 +185,10 @@ int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_
     rmsnorm_fwd(x2f, nullptr, e.mods + (2 * depth) * ms, A, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
     cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * E, st);
     linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, ad, E, st);
-    if (e.taps_enabled && step == 0) add_tap(e, "v_t_step0", e.v_t, n, PI05_F32);
+    if (e.taps_enabled && step == 0) {  // keep a copy: v_t is overwritten by the following steps (u_t is free in decode)
+      cudaMemcpyAsync(e.u_t, e.v_t, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      add_tap(e, "v_t_step0", e.u_t, n, PI05_F32);
+    }
     euler_step(actions_out, e.v_t, dt, n, st);
     time = time + dt;
     ++step;

@@ -57,15 +57,6 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -176,30 +167,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
   } else if (warp_idx == 1) {
     // ============================== MMA issuer (leader CTA only) ==============================
-    if (leader && lane == 0) {
+    // The WHOLE warp walks the loop with warp-uniform values (so descriptors live in uniform registers) and one
+    // elected lane issues; a lane-0-only loop costs ~170 SASS instructions per k-block (ELECT/R2UR per operand) and
+    // makes the single issuing thread, not the tensor pipe, the bottleneck (ncu: 76% tensor-active before this).
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, a_sbo = p.a_mn ? p.mn_sbo : 1024, a_kstep = p.a_mn ? 2048 : 32;
       const uint32_t b_lbo = p.b_mn ? p.mn_lbo : 16, b_sbo = p.b_mn ? p.mn_sbo : 1024, b_kstep = p.b_mn ? 2048 : 32;
+      const uint32_t a_hi = smem_desc_hi_sw128(a_sbo), b_hi = smem_desc_hi_sw128(b_sbo);
+      const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;
+      const uint32_t idesc = p.idesc;
+      const int num_kb = p.num_kb;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
-          const uint32_t sb = smem_b0 + stage * B_HALF_BYTES;
+          const uint32_t a_lo = smem_desc_lo(smem_a0 + stage * A_STAGE_BYTES, a_lbo);
+          const uint32_t b_lo = smem_desc_lo(smem_b0 + stage * B_HALF_BYTES, b_lbo);
+          if (elect_one()) {
+            umma2_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t da = make_smem_desc_sw128(sa + j * a_kstep, a_lbo, a_sbo);
-            const uint64_t db = make_smem_desc_sw128(sb + j * b_kstep, b_lbo, b_sbo);
-            umma2_bf16(d_tmem, da, db, p.idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 1; j < BK / 16; ++j)
+              umma2_lohi(d_tmem, a_lo + j * a_step, a_hi, b_lo + j * b_step, b_hi, idesc, 1u);
+            umma_commit2(empty_bar0 + 8 * stage);
+            if (kb == num_kb - 1) umma_commit2(tfull_bar0 + 8 * acc);
           }
-          umma_commit2(empty_bar0 + 8 * stage);
-          if (kb == p.num_kb - 1) umma_commit2(tfull_bar0 + 8 * acc);
+          __syncwarp();
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1;

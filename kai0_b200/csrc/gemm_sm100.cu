@@ -126,7 +126,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp_idx == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // Whole warp walks the loop with warp-uniform values; one elected lane issues (see gemm2_sm100.cu for why).
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -136,23 +137,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       //           MN atoms BK*128 B apart (LBO), k-step (16 k rows) = 2048 B.
       const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, a_sbo = p.a_mn ? p.mn_sbo : 1024, a_kstep = p.a_mn ? 2048 : 32;
       const uint32_t b_lbo = p.b_mn ? p.mn_lbo : 16, b_sbo = p.b_mn ? p.mn_sbo : 1024, b_kstep = p.b_mn ? 2048 : 32;
+      const uint32_t a_hi = smem_desc_hi_sw128(a_sbo), b_hi = smem_desc_hi_sw128(b_sbo);
+      const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;
+      const uint32_t idesc = p.idesc;
+      const int num_kb = p.num_kb;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_a0 + stage * A_STAGE_BYTES;
-          const uint32_t sb = smem_b0 + stage * C::B_STAGE_BYTES;
+          const uint32_t a_lo = smem_desc_lo(smem_a0 + stage * A_STAGE_BYTES, a_lbo);
+          const uint32_t b_lo = smem_desc_lo(smem_b0 + stage * C::B_STAGE_BYTES, b_lbo);
+          if (elect_one()) {
+            umma_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t da = make_smem_desc_sw128(sa + j * a_kstep, a_lbo, a_sbo);
-            const uint64_t db = make_smem_desc_sw128(sb + j * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, da, db, p.idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 1; j < BK / 16; ++j)
+              umma_lohi(d_tmem, a_lo + j * a_step, a_hi, b_lo + j * b_step, b_hi, idesc, 1u);
+            umma_commit(empty_bar0 + 8 * stage);  // frees the smem slot when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar0 + 8 * acc);
           }
-          umma_commit(empty_bar0 + 8 * stage);  // frees the smem slot when these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(tfull_bar0 + 8 * acc);
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
