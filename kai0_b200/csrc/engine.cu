@@ -598,8 +598,12 @@ int joint_layer_forward(Engine& e, int l, int B) {
   rope_pack_fwd(p1.qkv, P, H, hd, e.pos, e.nvalid, 0, e.rope_cos, e.rope_sin, p1.Q, Kc, Vc, 0, S, B, st);
   rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
   const float scaling = 1.0f / sqrtf(static_cast<float>(hd));
+  // The last layer's prefix-stream output only feeds prefix_out, which nothing on the loss path reads
+  // (pi0_pytorch.py:350-358 keeps suffix_out only): its prefix-query attention, o_proj and MLP are dead code here.
+  // They are computed only when taps are recorded (parity tests compare prefix_out too).
+  const bool prefix_live = !(l == c.paligemma.depth - 1) || e.taps_enabled;
   // scores: prefix queries see prefix keys; suffix queries see everything (pi0_pytorch.py:52-81)
-  {
+  if (prefix_live) {
     GemmArgs g = mk_gemm(P * H, P, hd, p1.Q, hd, Kc, hd, p1.P, e.Ppad, EPI_SCALE);
     g.batch = B;
     g.a_batch_stride = static_cast<int64_t>(P) * H * hd;
@@ -617,9 +621,9 @@ int joint_layer_forward(Engine& e, int l, int B) {
     g.scale = scaling;
     CHECK_RC(engine_gemm(e, g));
   }
-  softmax_fwd(p1.P, e.Ppad, P * H, B, P, P, e.pad, e.pad, H, st);
+  if (prefix_live) softmax_fwd(p1.P, e.Ppad, P * H, B, P, P, e.pad, e.pad, H, st);
   softmax_fwd(p2.P, e.Spad, A * H, B, S, P, e.pad, nullptr, H, st);
-  {  // O = P V  (V stored [keys, hd] -> N-major B operand)
+  if (prefix_live) {  // O = P V  (V stored [keys, hd] -> N-major B operand)
     GemmArgs g = mk_gemm(P * H, hd, P, p1.P, e.Ppad, Vc, hd, p1.O, hd, EPI_STORE);
     g.b_major = 1;
     g.batch = B;
@@ -638,10 +642,12 @@ int joint_layer_forward(Engine& e, int l, int B) {
     CHECK_RC(engine_gemm(e, g));
   }
   {  // o_proj + (gated) residual
-    GemmArgs g = mk_gemm(M1, D, H * hd, p1.O, H * hd, w1.o_w.data, H * hd, p1.x_mid, D, EPI_RES);
-    g.res = p1.x_in;
-    g.ldres = D;
-    CHECK_RC(engine_gemm(e, g));
+    if (prefix_live) {
+      GemmArgs g = mk_gemm(M1, D, H * hd, p1.O, H * hd, w1.o_w.data, H * hd, p1.x_mid, D, EPI_RES);
+      g.res = p1.x_in;
+      g.ldres = D;
+      CHECK_RC(engine_gemm(e, g));
+    }
     GemmArgs g2 = mk_gemm(M2, E, H * hd, p2.O, H * hd, w2.o_w.data, H * hd, p2.x_mid, E, EPI_RES);
     g2.res = p2.x_in;
     g2.ldres = E;
@@ -653,25 +659,29 @@ int joint_layer_forward(Engine& e, int l, int B) {
     CHECK_RC(engine_gemm(e, g2));
   }
   // post-attention norms
-  rmsnorm_fwd(p1.x_mid, w1.post_w.d<float>(), nullptr, 0, p1.n2, p1.rstd2, nullptr, M1, D, eps, st);
+  if (prefix_live) rmsnorm_fwd(p1.x_mid, w1.post_w.d<float>(), nullptr, 0, p1.n2, p1.rstd2, nullptr, M1, D, eps, st);
   rmsnorm_fwd(p2.x_mid, nullptr, mod_post, A, p2.n2, p2.rstd2, p2.gate2, M2, E, eps, st);
   {  // GeGLU up-projection (fused gate|up weight) then down-projection + (gated) residual
-    GemmArgs g = mk_gemm(M1, c.paligemma.mlp_dim, D, p1.n2, D, w1.gate_w.data, D, p1.GU, 2 * c.paligemma.mlp_dim,
-                         EPI_GEGLU);
-    g.D2 = p1.Hh;
-    g.ldd2 = c.paligemma.mlp_dim;
-    CHECK_RC(engine_gemm(e, g));
+    if (prefix_live) {
+      GemmArgs g = mk_gemm(M1, c.paligemma.mlp_dim, D, p1.n2, D, w1.gate_w.data, D, p1.GU, 2 * c.paligemma.mlp_dim,
+                           EPI_GEGLU);
+      g.D2 = p1.Hh;
+      g.ldd2 = c.paligemma.mlp_dim;
+      CHECK_RC(engine_gemm(e, g));
+    }
     GemmArgs g2 = mk_gemm(M2, c.expert.mlp_dim, E, p2.n2, E, w2.gate_w.data, E, p2.GU, 2 * c.expert.mlp_dim, EPI_GEGLU);
     g2.D2 = p2.Hh;
     g2.ldd2 = c.expert.mlp_dim;
     CHECK_RC(engine_gemm(e, g2));
   }
   {
-    GemmArgs g = mk_gemm(M1, D, c.paligemma.mlp_dim, p1.Hh, c.paligemma.mlp_dim, w1.down_w.data, c.paligemma.mlp_dim,
-                         p1.x_out, D, EPI_RES);
-    g.res = p1.x_mid;
-    g.ldres = D;
-    CHECK_RC(engine_gemm(e, g));
+    if (prefix_live) {
+      GemmArgs g = mk_gemm(M1, D, c.paligemma.mlp_dim, p1.Hh, c.paligemma.mlp_dim, w1.down_w.data, c.paligemma.mlp_dim,
+                           p1.x_out, D, EPI_RES);
+      g.res = p1.x_mid;
+      g.ldres = D;
+      CHECK_RC(engine_gemm(e, g));
+    }
     GemmArgs g2 =
         mk_gemm(M2, E, c.expert.mlp_dim, p2.Hh, c.expert.mlp_dim, w2.down_w.data, c.expert.mlp_dim, p2.x_out, E, EPI_RES);
     g2.res = p2.x_mid;

@@ -26,7 +26,7 @@ constexpr int STAGES2 = 6;
 constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;              // 16 KiB: this CTA's half of the B tile
 constexpr int STAGE_BYTES2 = A_STAGE_BYTES + B_HALF_BYTES;    // 32 KiB
 constexpr int TILE_BYTES2 = STAGES2 * STAGE_BYTES2;           // 192 KiB
-constexpr int SMEM_BYTES2 = TILE_BYTES2 + 1024 + 256;
+constexpr int SMEM_BYTES2 = TILE_BYTES2 + 1024 + 256 + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -218,13 +218,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const TileCoord tc = decode_tile(tile, pp);
-      const int row = (2 * tc.m_blk + static_cast<int>(rank)) * BM + q * 32 + lane;
+      const int row0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM + q * 32;
       const int n0 = tc.n_blk * BN_OUT;
-      const bool row_ok = row < p.M;
       mbar_wait(tfull_bar0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
-      epilogue_tile<BN2, EPI>(p, tc.z0, tc.z1, row, row_ok, n0, t_base, chalf);
+      epilogue_tile<BN2, EPI>(p, tc.z0, tc.z1, row0, lane, n0, t_base, chalf,
+                              bar_base + 256 + (warp_idx - 2) * STAGE_BYTES_PER_WARP);
       tc_fence_before();
       if (leader)
         mbar_arrive(tempty_bar0 + 8 * acc);

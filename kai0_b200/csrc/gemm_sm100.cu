@@ -178,14 +178,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
-      const int row = tc.m_blk * BM + q * 32 + lane;
+      const int row0 = tc.m_blk * BM + q * 32;
       const int n0 = tc.n_blk * BN_OUT;
-      const bool row_ok = row < p.M;
       mbar_wait(tfull_bar0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-
-      epilogue_tile<BN, EPI>(p, tc.z0, tc.z1, row, row_ok, n0, t_base, chalf);
+      epilogue_tile<BN, EPI>(p, tc.z0, tc.z1, row0, lane, n0, t_base, chalf,
+                             bar_base + 256 + (warp_idx - 2) * STAGE_BYTES_PER_WARP);
       tc_fence_before();
       mbar_arrive(tempty_bar0 + 8 * acc);  // 128 arrivals release this accumulator stage to the MMA warp
       if (++acc == 2) {
