@@ -340,6 +340,25 @@ def main():
     ms_e2e, last_loss = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
+    if rank == 0 and os.environ.get("PI05_TORCH_PROFILE"):
+        # low-overhead per-kernel breakdown of ONE step (CUPTI via torch.profiler): where the non-GEMM time goes
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(False)
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type is not None and str(ev.device_type).endswith("CUDA"):
+                name = ev.name[:90]
+                a = agg.setdefault(name, [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+        tot = sum(v[1] for v in agg.values())
+        print(f"  [torch.profiler] one step: {tot / 1e3:.2f} ms of kernel time", file=sys.stderr)
+        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+            print(f"  {us / 1e3:9.3f} ms {100 * us / tot:5.1f}%  x{cnt:5d}  {name}", file=sys.stderr)
+
     # secondary metric of BASELINE.json (configs[3]): single-frame 10-step action decode, p50 latency through the
     # public API with host inputs (H2D of one uint8 observation, D2H of the [1,50,32] action chunk), rank 0 only
     decode = None
