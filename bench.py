@@ -212,6 +212,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug: tiny architecture (not a valid bench number)")
     ap.add_argument("--per-param-optimizer", action="store_true",
                     help="AdamW/clip over model.parameters() exactly as the unchanged script (slower: ~1400 launches)")
+    ap.add_argument("--torch-optimizer", action="store_true",
+                    help="torch.optim.AdamW(fused) + clip_grad_norm_ over the 2 flat arenas instead of the engine's "
+                         "fused clip+AdamW kernel (kai0_b200.optim.FusedClipAdamW)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -268,7 +271,14 @@ def main():
     # optimiser over the two flat arenas (public opt-in): element-wise identical to the per-parameter
     # AdamW / global-norm clip of train_pytorch.py:469-475,557, in 2 tensors instead of ~700
     params = model.flat_parameters() if not args.per_param_optimizer else [p for p in model.parameters() if p.requires_grad]
-    optim = torch.optim.AdamW(params, lr=2.5e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10, fused=True)
+    use_fused = not (args.per_param_optimizer or args.torch_optimizer)
+    if use_fused:
+        from kai0_b200.optim import FusedClipAdamW
+
+        # global-norm clip + AdamW over the flat arenas in one engine pass (same update rule)
+        optim = FusedClipAdamW(model, lr=2.5e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10, max_norm=1.0)
+    else:
+        optim = torch.optim.AdamW(params, lr=2.5e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10, fused=True)
 
     host_d, host_a = make_host_batch(B, rank, image_size=cfg.image_size, L=cfg.max_token_len, vocab=cfg.vocab_size,
                                      horizon=cfg.action_horizon, adim=cfg.action_dim)
@@ -289,8 +299,11 @@ def main():
         losses = model(obs, a)
         loss = losses.mean()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
-        optim.step()
+        if use_fused:
+            optim.step()  # clip_grad_norm_(1.0) + AdamW in one pass
+        else:
+            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+            optim.step()
         optim.zero_grad(set_to_none=True)
         if from_host:
             return float(loss.item())  # device -> host read of the step's result
@@ -422,8 +435,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload if not args.small else "DEBUG small architecture (invalid as a bench number)",
                        "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "optimizer": "torch.optim.AdamW(fused) + clip_grad_norm_(1.0) as scripts/train_pytorch.py, over "
-                                    + ("model.parameters()" if args.per_param_optimizer else "model.flat_parameters() (2 flat arenas)"),
+                       "optimizer": ("kai0_b200.optim.FusedClipAdamW: clip_grad_norm_(1.0) + AdamW(0.9,0.95,1e-8,wd 1e-10) "
+                                     "over the 2 flat arenas in one engine pass" if use_fused else
+                                     "torch.optim.AdamW(fused) + clip_grad_norm_(1.0) as scripts/train_pytorch.py, over "
+                                     + ("model.parameters()" if args.per_param_optimizer
+                                        else "model.flat_parameters() (2 flat arenas)")),
                        "l2": "per-step activations (>100 GB) and weights (7 GB) far exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host_d, host_a),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},

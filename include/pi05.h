@@ -131,6 +131,16 @@ typedef struct pi05_gemm_desc {
 } pi05_gemm_desc;
 int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream);
 
+/* ---- caller-side step right after the path: global-norm clip + AdamW in one pass --------
+ * Replaces torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() of scripts/train_pytorch.py:
+ * 557-560 over the two flat arenas (state m, v in the parameter dtype).  `step` is the 1-based update count,
+ * max_norm <= 0 disables clipping.  scratch: >= 4096 floats (device); after the call scratch[0] = total gradient
+ * norm, scratch[1] = applied clip coefficient.                                                                   */
+int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_bf16, void* v_bf16, int64_t n_bf16, float* p_f32,
+                          const float* g_f32, float* m_f32, float* v_f32, int64_t n_f32, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int64_t step, float max_norm, float* scratch,
+                          void* stream);
+
 /* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the GEMM -------- */
 unsigned long long pi05_launch_count(void);
 void pi05_gemm_profile_enable(int on);

@@ -121,6 +121,7 @@ EXPORTS = (
     "pi05_forward_value",
     "pi05_get_tap",
     "pi05_gemm_bf16",
+    "pi05_fused_clip_adamw",
     "pi05_launch_count",
     "pi05_gemm_profile_enable",
     "pi05_gemm_profile_report",
@@ -183,6 +184,12 @@ def lib() -> C.CDLL:
                 C.POINTER(C.c_int32),
                 C.c_void_p,
             ]
+        if hasattr(l, "pi05_fused_clip_adamw"):
+            l.pi05_fused_clip_adamw.restype = C.c_int
+            l.pi05_fused_clip_adamw.argtypes = (
+                [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5
+                + [C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+            )
         _lib = l
         return _lib
 

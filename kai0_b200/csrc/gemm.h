@@ -16,7 +16,12 @@ enum GemmEpilogue : int {
   EPI_GEGLU = 5,      // B tile = [gate rows | up rows]; g = bf(acc_g), u = bf(acc_u), D[:, n] = g, D[:, N + n] = u,
                       // D2[:, n] = bf(bf(gelu_tanh(g)) * u)          (GemmaMLP, modeling_gemma.py:125)
   EPI_F32 = 6,        // Df32 = acc (+ Df32 if accumulate)
-  EPI_COUNT = 7,
+  // Backward of the GeGLU fused into the down-projection dgrad: acc = dH tile; res = GU = [g | u] (ld 2N) from the
+  // forward; D = dGU = [dg | du] (ld 2N):  a = bf(gelu(g)); du = bf(bf(acc)*a); dg = bf(bf(bf(acc)*u) * gelu'(g))
+  EPI_GEGLU_BWD = 7,
+  // Backward of gelu_tanh fused into the fc2 dgrad (SigLIP): acc = d(act); res = pre-activation; D = bf(bf(acc)*gelu'(pre))
+  EPI_GELU_BWD = 8,
+  EPI_COUNT = 9,
 };
 
 struct GemmArgs {

@@ -196,6 +196,40 @@ __device__ __forceinline__ void stage_flush_f32(uint32_t stage, int lane, float*
   __syncwarp();
 }
 
+// Coalesced load of a 32-row x 32-column bf16 chunk (the reverse of stage_flush_bf16): lanes walk along the rows into
+// the staging area, then every thread picks up its own row.  Rows / columns outside the matrix read as zero.
+__device__ __forceinline__ void stage_load_bf16(uint32_t stage, int lane, const __nv_bfloat16* src, long long ld,
+                                                int rows_valid, int cols_valid, float (&out)[32]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), c = lane & 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < rows_valid && c * 8 < cols_valid) {
+      const __nv_bfloat16* g = src + r * ld + c * 8;
+      if (c * 8 + 8 <= cols_valid && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        val = *reinterpret_cast<const uint4*>(g);
+      } else {
+        __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&val);
+        for (int k = 0; k < 8; ++k)
+          if (c * 8 + k < cols_valid) e[k] = g[k];
+      }
+    }
+    st_shared_v4(stage + r * 128 + ((c ^ (r & 7)) << 4), val);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 w4 = ld_shared_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out[j * 8 + k * 2 + 0] = __uint_as_float(w[k] << 16);
+      out[j * 8 + k * 2 + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+  }
+  __syncwarp();
+}
+
 // Drains this warp's share (column half `chalf`) of one 128 x BN accumulator tile: thread <-> row, 32 columns per
 // tcgen05.ld, fused epilogue math in registers, then the staged coalesced store above.  `row0` is the warp's first
 // row (row = row0 + lane); `stage` is this warp's staging area in shared memory.
@@ -244,6 +278,34 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, int z0, int z1, 
           static_cast<__nv_bfloat16*>(p.D2) + z0 * p.d2bs + z1 * p.d2bs1 + static_cast<long long>(row0) * p.ldd2;
       stage_write_bf16(stage, lane, h);
       stage_flush_bf16(stage, lane, d2 + col, p.ldd2, rows_valid, nvalid);
+    } else if constexpr (EPI == EPI_GEGLU_BWD) {
+      const __nv_bfloat16* gu = p.res + z0 * p.resbs + z1 * p.resbs1 + static_cast<long long>(row0) * p.ldres;
+      float g[32], u[32];
+      stage_load_bf16(stage, lane, gu + col, p.ldres, rows_valid, nvalid, g);
+      stage_load_bf16(stage, lane, gu + p.N + col, p.ldres, rows_valid, nvalid, u);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float d = bf16_round(v[i]);                   // dH as the bf16 tensor autograd would hold
+        const float a = bf16_round(gelu_tanh_f(g[i]));
+        const float da = bf16_round(d * u[i]);
+        u[i] = d * a;                                       // du
+        v[i] = da * gelu_tanh_grad_f(g[i]);                 // dg
+      }
+      __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.D) + z0 * p.dbs + z1 * p.dbs1 + static_cast<long long>(row0) * p.ldd;
+      stage_write_bf16(stage, lane, v);
+      stage_flush_bf16(stage, lane, d + col, p.ldd, rows_valid, nvalid);
+      stage_write_bf16(stage, lane, u);
+      stage_flush_bf16(stage, lane, d + p.N + col, p.ldd, rows_valid, nvalid);
+    } else if constexpr (EPI == EPI_GELU_BWD) {
+      const __nv_bfloat16* pre = p.res + z0 * p.resbs + z1 * p.resbs1 + static_cast<long long>(row0) * p.ldres;
+      float x[32];
+      stage_load_bf16(stage, lane, pre + col, p.ldres, rows_valid, nvalid, x);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]) * gelu_tanh_grad_f(x[i]);
+      __nv_bfloat16* d =
+          static_cast<__nv_bfloat16*>(p.D) + z0 * p.dbs + z1 * p.dbs1 + static_cast<long long>(row0) * p.ldd + col;
+      stage_write_bf16(stage, lane, v);
+      stage_flush_bf16(stage, lane, d, p.ldd, rows_valid, nvalid);
     } else if constexpr (EPI == EPI_F32) {
       float* d = static_cast<float*>(p.D) + z0 * p.dbs + z1 * p.dbs1 + static_cast<long long>(row0) * p.ldd + col;
       stage_write_f32(stage, lane, v);

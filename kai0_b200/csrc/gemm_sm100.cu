@@ -336,6 +336,8 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KP
     case EPI_RES: return launch<BN, EPI_RES>(ta, tb, kp, s, err, err_len);
     case EPI_GEGLU: return launch<BN, EPI_GEGLU>(ta, tb, kp, s, err, err_len);
     case EPI_F32: return launch<BN, EPI_F32>(ta, tb, kp, s, err, err_len);
+    case EPI_GEGLU_BWD: return launch<BN, EPI_GEGLU_BWD>(ta, tb, kp, s, err, err_len);
+    case EPI_GELU_BWD: return launch<BN, EPI_GELU_BWD>(ta, tb, kp, s, err, err_len);
     default:
       if (err) snprintf(err, err_len, "unknown epilogue %d", epi);
       return 1;

@@ -211,7 +211,7 @@ __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float kKappa = 0.044715f;
   float x2 = x * x;
   float inner = kBeta * (x + kKappa * x2 * x);
-  float t = tanhf(inner);
+  float t = fast_tanh(inner);
   float left = 0.5f * x * ((1.0f - t * t) * (kBeta * (1.0f + 3.0f * kKappa * x2)));
   float right = 0.5f * (1.0f + t);
   return left + right;

@@ -68,12 +68,15 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
       sum += v[i][e];
     }
   sum = warp_sum(sum);
+  // one IEEE reciprocal per row instead of 1024 divisions (<= 1 ulp from x/sum in fp32, i.e. far below the bf16
+  // rounding applied next); the per-element fp32 division was the dominant cost of this kernel
+  const float inv = 1.0f / sum;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const int j0 = (i * 32 + lane) * 8;
     if (j0 < ld) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[i][e] = v[i][e] / sum;
+      for (int e = 0; e < 8; ++e) v[i][e] = v[i][e] * inv;
       store8(sr + j0, v[i]);
     }
   }
