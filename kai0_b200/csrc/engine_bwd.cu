@@ -79,15 +79,18 @@ static int joint_layer_backward(Engine& e, int l, int B, bool g1_zero) {
   // ================= expert stream: MLP half =================
   bf16* do2 = e.g2_do;
   gated_residual_bwd(g2, p2.d_lin, p2.gate2, A, do2, dmod_post, M2, E, st);                 // x_out = x_mid + d*gate
-  CHECK_RC(dgrad_geglu(e, do2, M2, E, w2.down_w.data, mlp2, p2.GU, e.g2_big));                // dH -> dGU (fused)
+  CHECK_RC(dgrad_geglu(e, do2, M2, E, w2.down_w.data, mlp2, p2.GU, e.g2_big));  // small M: dH -> dGU fused in the epilogue
   CHECK_RC(wgrad(e, do2, M2, E, p2.Hh, mlp2, w2.down_w.grad));
   CHECK_RC(dgrad(e, e.g2_big, M2, 2 * mlp2, w2.gate_w.data, E, e.g2_t1));                    // dn2
   CHECK_RC(wgrad(e, e.g2_big, M2, 2 * mlp2, p2.n2, E, w2.gate_w.grad));
   rmsnorm_bwd(e.g2_t1, p2.x_mid, nullptr, mod_post, A, p2.rstd2, g2, g2m, nullptr, dmod_post, M2, E, st);
   // ================= prefix stream: MLP half =================
   if (!g1_zero) {
-    CHECK_RC(dgrad_geglu(e, g1, M1, D, w1.down_w.data, mlp1, p1.GU, e.g_big));  // dH never touches HBM
+    // Measured (profiles/r01): fusing the GeGLU backward into this dgrad's epilogue makes the K = 2048 GEMM
+    // epilogue-bound (1.88 ms vs 0.84 + 0.67 ms unfused), so the big stream keeps the separate streaming kernel.
+    CHECK_RC(dgrad(e, g1, M1, D, w1.down_w.data, mlp1, e.g_big2));
     CHECK_RC(wgrad(e, g1, M1, D, p1.Hh, mlp1, w1.down_w.grad));
+    geglu_bwd(e.g_big2, p1.GU, e.g_big, M1, mlp1, st);
     CHECK_RC(dgrad(e, e.g_big, M1, 2 * mlp1, w1.gate_w.data, D, e.g_t1));
     CHECK_RC(wgrad(e, e.g_big, M1, 2 * mlp1, p1.n2, D, w1.gate_w.grad));
     fill_zero(w1.post_w.grad, static_cast<size_t>(D) * sizeof(float), st);
@@ -216,15 +219,10 @@ static int vit_layer_backward(Engine& e, int l, int B) {
   bf16 *g = e.g_x1, *gm = e.g_x1b;
   float* acc = e.g_acc;
   // ---- MLP half: x_out = x_mid + fc2(act) + b
-  {  // d act = g @ Wfc2, with the GELU backward fused into the epilogue: d pre = bf(bf(d act) * gelu'(pre))
-    GemmArgs q = mk_gemm(Mv, mlp, W, g, W, p.fc2_w.data, mlp, e.g_big, mlp, EPI_GELU_BWD);
-    q.b_major = 1;
-    q.res = a.pre;
-    q.ldres = mlp;
-    CHECK_RC(engine_gemm(e, q));
-  }
+  CHECK_RC(dgrad(e, g, Mv, W, p.fc2_w.data, mlp, e.g_big2));  // d act
   CHECK_RC(wgrad(e, g, Mv, W, a.act, mlp, p.fc2_w.grad));
   bias_grad(e, g, W, Mv, W, p.fc2_b.g<bf16>());
+  gelu_bwd(e.g_big2, a.pre, e.g_big, static_cast<int64_t>(Mv) * mlp, st);  // d pre (EPI_GELU_BWD fusion measured slower)
   CHECK_RC(dgrad(e, e.g_big, Mv, mlp, p.fc1_w.data, W, e.g_t1));         // d h2
   CHECK_RC(wgrad(e, e.g_big, Mv, mlp, a.h2, W, p.fc1_w.grad));
   bias_grad(e, e.g_big, mlp, Mv, mlp, p.fc1_b.g<bf16>());

@@ -111,6 +111,42 @@ def test_gemm_epilogues():
     assert H.rel_err(h, bf(bf(gelu(g)) * u)) < tol
 
 
+def test_gemm_fused_backward_epilogues():
+    """EPI_GEGLU_BWD / EPI_GELU_BWD (used for the small expert stream): dgrad with the activation backward fused."""
+    import ctypes as C
+
+    from kai0_b200 import _lib
+
+    M, Nh, K = 300, 264, 136
+    dy, wd = _mk((M, K), 1), _mk((K, Nh), 2, 0.2)       # dH = dY @ Wd, Wd stored [K, Nh] (N-major B)
+    gu = _mk((M, 2 * Nh), 3)
+    bf = lambda x: x.to(torch.bfloat16).float()  # noqa: E731
+    dh = bf(dy.float() @ wd.float())
+    g, u = gu[:, :Nh].float().requires_grad_(True), gu[:, Nh:].float()
+    a = torch.nn.functional.gelu(g, approximate="tanh")
+    (dgelu,) = torch.autograd.grad(a.sum(), g)
+    du_ref = bf(dh * bf(a.detach()))
+    dg_ref = bf(bf(dh * u) * dgelu)
+
+    def run(epi, res, ldres, out, ldd, N):
+        d = _lib.GemmDesc()
+        d.M, d.N, d.K, d.batch = M, N, K, 1
+        d.A, d.B, d.lda, d.ldb, d.b_major = dy.data_ptr(), wd.data_ptr(), K, Nh, 1
+        d.epilogue, d.D, d.ldd, d.res, d.ldres = epi, out.data_ptr(), ldd, res.data_ptr(), ldres
+        _lib.check(_lib.lib().pi05_gemm_bf16(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "gemm")
+        torch.cuda.synchronize()
+
+    dgu = torch.zeros(M, 2 * Nh, device="cuda", dtype=torch.bfloat16)
+    run(7, gu, 2 * Nh, dgu, 2 * Nh, Nh)
+    assert H.rel_err(dgu[:, :Nh], dg_ref) < 2e-3 and H.rel_err(dgu[:, Nh:], du_ref) < 2e-3
+    pre = _mk((M, Nh), 4)
+    x = pre.float().requires_grad_(True)
+    (dpre_gelu,) = torch.autograd.grad(torch.nn.functional.gelu(x, approximate="tanh").sum(), x)
+    dpre = torch.zeros(M, Nh, device="cuda", dtype=torch.bfloat16)
+    run(8, pre, Nh, dpre, Nh, Nh)
+    assert H.rel_err(dpre, bf(dh * dpre_gelu)) < 2e-3
+
+
 def test_gemm_linearity_and_determinism_at_full_size():
     """Size-independent properties at the real MLP shape: D(a1 + a2) ~= D(a1) + D(a2) in fp32 accumulation, and two
     launches of the same problem are bit-identical."""

@@ -28,8 +28,8 @@ def test_fused_clip_adamw_matches_torch():
     for it in range(3):
         model(obs, *args).mean().backward()
         ref(obs, *args).mean().backward()
-        # identical gradients going in (the engines are deterministic)
-        assert torch.equal(model.flat_parameters()[0].grad, rparams[0].grad)
+        # same gradients going in (bias / norm-weight reductions use fp32 atomics, so allow last-bit differences)
+        assert H.rel_err(model.flat_parameters()[0].grad, rparams[0].grad) < 1e-4
         norm = opt.step()
         rnorm = torch.nn.utils.clip_grad_norm_(rparams, max_norm=1.0)
         ropt.step()
