@@ -26,7 +26,10 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 int engine_gemm(Engine& e, const GemmArgs& a) {
   char err[512] = "";
-  int rc = gemm_bf16(a, e.stream, err, sizeof(err));
+  GemmArgs b = a;
+  b.splitk_ws = e.splitk_ws;
+  b.splitk_ws_bytes = e.splitk_ws_bytes;
+  int rc = gemm_bf16(b, e.stream, err, sizeof(err));
   if (rc != 0) {
     snprintf(e.err, sizeof(e.err), "%s", err);
     set_error(e.err);
@@ -201,6 +204,18 @@ int engine_plan(Engine& e, bool dry) {
   e.so32 = ar.get<float>(M2 * E);
   e.v_t = ar.get<float>(M2 * c.action_dim);
   e.timevec = ar.get<float>(B);
+  e.splitk_ws_bytes = static_cast<size_t>(16) << 20;
+  e.splitk_ws = ar.get<float>(e.splitk_ws_bytes / sizeof(float));
+  {
+    const int64_t ns = Engine::kMaxDecodeSteps;
+    e.dec_times = ar.get<float>(ns);
+    e.dec_temb = ar.get<float>(ns * E);
+    e.dec_t1 = ar.get<float>(ns * E);
+    e.dec_t1s = ar.get<float>(ns * E);
+    e.dec_t2 = ar.get<float>(ns * E);
+    e.dec_cond = ar.get<float>(ns * E);
+    e.dec_mods = ar.get<float>(static_cast<int64_t>(nmods) * ns * 3 * E);
+  }
 
   // ---- backward scratch
   if (tr) {

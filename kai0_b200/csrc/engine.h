@@ -122,6 +122,12 @@ struct Engine {
   bool ada_uniform = false, ada_uniform_grad = false;
   int64_t ada_wstride = 0, ada_bstride = 0;
   float* g_dcond_part = nullptr;
+  // decode: per-call tables of the time conditioning (depends only on the step index, not on x_t)
+  static constexpr int kMaxDecodeSteps = 64;
+  float *dec_times = nullptr, *dec_temb = nullptr, *dec_t1 = nullptr, *dec_t1s = nullptr, *dec_t2 = nullptr,
+        *dec_cond = nullptr, *dec_mods = nullptr;
+  float* splitk_ws = nullptr;  // fp32 scratch of the small-M split-K GEMM path
+  size_t splitk_ws_bytes = 0;
   bool taps_enabled = false;
   std::map<std::string, Tap> taps;
   cudaStream_t stream = nullptr;

@@ -80,16 +80,15 @@ static int prefix_layer(Engine& e, int l, int B, bool kv_only) {
 }
 
 // Expert-only layer reading the cache: K,V = cat(cache, new) (modeling_gemma.py:308-310).
-static int suffix_layer(Engine& e, int l, int B) {
+static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const float* mod_post, int rpb) {
   cudaStream_t st = e.stream;
   const pi05_config& c = e.cfg;
   const int P = e.P, A = e.A, S = e.S, E = e.E, H = e.H, hd = e.hd;
   const int M2 = B * A, QW = (H + 2) * hd;
   GemmaLayerA& p2 = e.a2[l];
   const GemmaLayerP& w2 = e.ex[l];
-  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
   bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
-  rmsnorm_fwd(p2.x_in, nullptr, e.mods + (2 * l) * ms, A, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
+  rmsnorm_fwd(p2.x_in, nullptr, mod_in, rpb, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
   CHECK_RC(engine_gemm(e, mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE)));
   rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
   {
@@ -116,11 +115,11 @@ static int suffix_layer(Engine& e, int l, int B) {
     g.res = p2.x_in;
     g.ldres = E;
     g.gate = p2.gate1;
-    g.gate_rows = A;
+    g.gate_rows = rpb;
     g.ldgate = E;
     CHECK_RC(engine_gemm(e, g));
   }
-  rmsnorm_fwd(p2.x_mid, nullptr, e.mods + (2 * l + 1) * ms, A, p2.n2, p2.rstd2, p2.gate2, M2, E, 1e-6f, st);
+  rmsnorm_fwd(p2.x_mid, nullptr, mod_post, rpb, p2.n2, p2.rstd2, p2.gate2, M2, E, 1e-6f, st);
   {
     GemmArgs g = mk_gemm(M2, c.expert.mlp_dim, E, p2.n2, E, w2.gate_w.data, E, p2.GU, 2 * c.expert.mlp_dim, EPI_GEGLU);
     g.D2 = p2.Hh;
@@ -133,7 +132,7 @@ static int suffix_layer(Engine& e, int l, int B) {
     g.res = p2.x_mid;
     g.ldres = E;
     g.gate = p2.gate2;
-    g.gate_rows = A;
+    g.gate_rows = rpb;
     g.ldgate = E;
     CHECK_RC(engine_gemm(e, g));
   }
@@ -174,15 +173,43 @@ int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_
   cudaMemcpyAsync(actions_out, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
   // pi0_pytorch.py:401-418: dt and time are fp32 tensors; time is a running fp32 sum; loop while time >= -dt/2
   const float dt = static_cast<float>(-1.0 / static_cast<double>(num_steps));
-  float time = 1.0f;
-  const int64_t ms = static_cast<int64_t>(B) * 3 * E;
-  int step = 0;
-  while (time >= -dt / 2) {
-    fill_f32(e.timevec, time, B, st);  // time.expand(bsize), pi0_pytorch.py:407
-    CHECK_RC(suffix_frontend(e, actions_out, e.timevec, B));
-    for (int l = 0; l < depth; ++l) CHECK_RC(suffix_layer(e, l, B));
+  int nsteps = 0;
+  for (float time = 1.0f; time >= -dt / 2; time = time + dt) ++nsteps;
+  if (nsteps > Engine::kMaxDecodeSteps) {
+    snprintf(e.err, sizeof(e.err), "pi05_denoise: num_steps %d exceeds the engine's table (%d)", num_steps,
+             Engine::kMaxDecodeSteps);
+    set_error(e.err);
+    return 8;
+  }
+  // The time conditioning depends only on the step index: sincos embedding -> time MLP -> all 2*depth+1 adaRMS
+  // modulation layers are evaluated ONCE per call for every step (M = nsteps), instead of once per step with M = B.
+  // (time.expand(bsize) in the reference: every batch row shares the step's modulation, so rows_per_batch = B*A.)
+  const int nm = 2 * depth + 1;
+  const int64_t srow = static_cast<int64_t>(3) * E;
+  decode_times(e.dec_times, nsteps, dt, st);
+  time_embedding(e.dec_times, e.time_scaling, e.dec_temb, nsteps, E / 2, st);
+  linear_f32(e.dec_temb, e.tin_w.d<float>(), e.tin_b.d<float>(), e.dec_t1, nsteps, E, E, st);
+  silu_fwd(e.dec_t1, e.dec_t1s, static_cast<int64_t>(nsteps) * E, st);
+  linear_f32(e.dec_t1s, e.tout_w.d<float>(), e.tout_b.d<float>(), e.dec_t2, nsteps, E, E, st);
+  silu_fwd(e.dec_t2, e.dec_cond, static_cast<int64_t>(nsteps) * E, st);
+  if (e.ada_uniform && depth > 0) {
+    linear_f32_batched(e.dec_cond, e.ex[0].in_dw.d<float>(), e.ex[0].in_db.d<float>(), e.dec_mods, nsteps, 3 * E, E, nm,
+                       e.ada_wstride, e.ada_bstride, nsteps * srow, st);
+  } else {
+    for (int j = 0; j < nm; ++j) {
+      const PRef& dw = (j == 2 * depth) ? e.ex_norm_dw : ((j & 1) ? e.ex[j / 2].post_dw : e.ex[j / 2].in_dw);
+      const PRef& db = (j == 2 * depth) ? e.ex_norm_db : ((j & 1) ? e.ex[j / 2].post_db : e.ex[j / 2].in_db);
+      linear_f32(e.dec_cond, dw.d<float>(), db.d<float>(), e.dec_mods + j * nsteps * srow, nsteps, 3 * E, E, st);
+    }
+  }
+  auto mod_at = [&](int j, int s) { return e.dec_mods + (static_cast<int64_t>(j) * nsteps + s) * srow; };
+  for (int step = 0; step < nsteps; ++step) {
+    // embed_suffix (pi05): action_in_proj of the current x_t, cast to bf16 (pi0_pytorch.py:270-273,332-337)
+    linear_f32(actions_out, e.ain_w.d<float>(), e.ain_b.d<float>(), e.aemb32, M2, E, ad, st);
+    cast_f32_to_bf16(e.aemb32, e.a2[0].x_in, static_cast<int64_t>(M2) * E, st);
+    for (int l = 0; l < depth; ++l) CHECK_RC(suffix_layer(e, l, B, mod_at(2 * l, step), mod_at(2 * l + 1, step), M2));
     const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;
-    rmsnorm_fwd(x2f, nullptr, e.mods + (2 * depth) * ms, A, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
+    rmsnorm_fwd(x2f, nullptr, mod_at(2 * depth, step), M2, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
     cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * E, st);
     linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, ad, E, st);
     if (e.taps_enabled && step == 0) {  // keep a copy: v_t is overwritten by the following steps (u_t is free in decode)
@@ -190,8 +217,6 @@ int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_
       add_tap(e, "v_t_step0", e.u_t, n, PI05_F32);
     }
     euler_step(actions_out, e.v_t, dt, n, st);
-    time = time + dt;
-    ++step;
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {

@@ -51,6 +51,10 @@ struct GemmArgs {
   int64_t ldgate = 0;
   float scale = 1.0f;
   int accumulate = 0;  // EPI_F32 only
+  // Optional fp32 scratch for the small-M split-K path (decode: M = action horizon, one 128-row tile, long K):
+  // the K loop is split across CTAs as a batch dimension and a finish kernel applies the epilogue.
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_bytes = 0;
   int block_n = 0;     // 0 = auto (256 when N >= 256 else 128)
 };
 

@@ -346,10 +346,76 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KP
 
 }  // namespace
 
+namespace {
+// Finish of the small-M split-K path: sum the fp32 partials in a fixed order, then the STORE / RES epilogue.
+__global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__ ws, int splits, int M, int N, int epi,
+                                                       __nv_bfloat16* __restrict__ D, long long ldd,
+                                                       __nv_bfloat16* __restrict__ D2, long long ldd2,
+                                                       const __nv_bfloat16* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ res, long long ldres,
+                                                       const __nv_bfloat16* __restrict__ gate, int gate_rows,
+                                                       long long ldgate) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / N), n = static_cast<int>(idx % N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += ws[z * total + idx];
+    if (epi == EPI_RES) {
+      if (bias) acc += __bfloat162float(bias[n]);
+      float t = bf16_round(acc);
+      if (D2) D2[m * ldd2 + n] = __float2bfloat16_rn(t);
+      if (gate) t = bf16_round(t * __bfloat162float(gate[static_cast<long long>(m / gate_rows) * ldgate + n]));
+      acc = t + __bfloat162float(res[m * ldres + n]);
+    }
+    D[m * ldd + n] = __float2bfloat16_rn(acc);
+  }
+}
+}  // namespace
+
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) {
     if (err) snprintf(err, err_len, "gemm: empty problem M=%d N=%d K=%d batch=%d", a.M, a.N, a.K, a.batch);
     return 1;
+  }
+  // ---- small-M latency path (decode): one 128-row tile, few N tiles, long serial K loop -> split K across CTAs
+  if (a.M <= BM && a.batch == 1 && a.splitk_ws != nullptr && a.a_major == 0 && a.b_major == 0 &&
+      (a.epilogue == EPI_STORE || a.epilogue == EPI_RES) && a.K % BK == 0 && a.block_n == 0) {
+    const int tiles = (a.N + 127) / 128;
+    const int kb = a.K / BK;
+    int s = 1;
+    while (s * 2 <= 32 && kb % (s * 2) == 0 && kb / (s * 2) >= 4 && tiles * s * 2 <= 160) s *= 2;
+    if (s > 1 && static_cast<size_t>(s) * a.M * a.N * sizeof(float) <= a.splitk_ws_bytes) {
+      const int Kc = a.K / s;
+      GemmArgs part = a;
+      part.splitk_ws = nullptr;
+      part.K = Kc;
+      part.batch = s;
+      part.a_batch_stride = Kc;
+      part.b_batch_stride = Kc;
+      part.epilogue = EPI_F32;
+      part.accumulate = 0;
+      part.D = a.splitk_ws;
+      part.ldd = a.N;
+      part.d_batch_stride = static_cast<int64_t>(a.M) * a.N;
+      part.block_n = 128;
+      part.bias = nullptr;
+      part.res = nullptr;
+      part.gate = nullptr;
+      part.D2 = nullptr;
+      int rc = gemm_bf16(part, stream, err, err_len);
+      if (rc != 0) return rc;
+      const long long total = static_cast<long long>(a.M) * a.N;
+      const int grid = static_cast<int>((total + 255) / 256);
+      splitk_finish_k<<<grid, 256, 0, stream>>>(a.splitk_ws, s, a.M, a.N, a.epilogue, static_cast<__nv_bfloat16*>(a.D), a.ldd,
+                                                static_cast<__nv_bfloat16*>(a.D2), a.ldd2,
+                                                static_cast<const __nv_bfloat16*>(a.bias),
+                                                static_cast<const __nv_bfloat16*>(a.res), a.ldres,
+                                                static_cast<const __nv_bfloat16*>(a.gate), a.gate_rows > 0 ? a.gate_rows : 1,
+                                                a.ldgate);
+      count_launch();
+      return 0;
+    }
   }
   if (a.epilogue == EPI_GEGLU && a.b_major != 0) {
     if (err) snprintf(err, err_len, "gemm: GEGLU epilogue needs a K-major [2N,K] weight");
@@ -357,6 +423,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.epilogue == EPI_GEGLU) ? 256 : (a.N > 128 ? 256 : 128);
+  if (a.block_n == 0 && a.M <= BM && a.epilogue != EPI_GEGLU) bn = 128;  // one row of tiles: prefer more, narrower CTAs
   if (bn != 128 && bn != 256) {
     if (err) snprintf(err, err_len, "gemm: unsupported block_n %d", bn);
     return 1;

@@ -72,6 +72,8 @@ void add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s
 void add_f32(float* a, const float* b, int64_t n, cudaStream_t st);                  // a += b
 void fill_zero(void* p, size_t bytes, cudaStream_t st);
 void fill_f32(float* p, float v, int64_t n, cudaStream_t st);
+// out[s] = the fp32 running sum 1, 1+dt, (1+dt)+dt, ... of sample_actions' time variable (pi0_pytorch.py:401-418)
+void decode_times(float* out, int n, float dt, cudaStream_t st);
 // sincos time embedding in fp64 (pi0_pytorch.py:25-42,264-267): out[b, :] fp32 [2*half]
 void time_embedding(const float* time, const double* scaling /*[half]*/, float* out, int batch, int half, cudaStream_t st);
 void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st);

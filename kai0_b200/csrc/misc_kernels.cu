@@ -180,6 +180,13 @@ __global__ void add_f32_k(float* __restrict__ a, const float* __restrict__ b, in
 __global__ void fill_f32_k(float* __restrict__ p, float v, int64_t n) {
   GRID_STRIDE(i, n) p[i] = v;
 }
+__global__ void decode_times_k(float* __restrict__ out, int n, float dt) {
+  float t = 1.0f;
+  for (int s = 0; s < n; ++s) {
+    out[s] = t;
+    t = __fadd_rn(t, dt);
+  }
+}
 __global__ void time_embedding_k(const float* __restrict__ time, const double* __restrict__ scaling,
                                  float* __restrict__ out, int batch, int half) {
   const int64_t total = static_cast<int64_t>(batch) * half;
@@ -306,6 +313,9 @@ void add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t s
 void add_f32(float* a, const float* b, int64_t n, cudaStream_t st) { add_f32_k<<<grid_for(n), 256, 0, st>>>(a, b, n); count_launch(); }
 void fill_zero(void* p, size_t bytes, cudaStream_t st) { cudaMemsetAsync(p, 0, bytes, st); }
 void fill_f32(float* p, float v, int64_t n, cudaStream_t st) { fill_f32_k<<<grid_for(n), 256, 0, st>>>(p, v, n); count_launch(); }
+void decode_times(float* out, int n, float dt, cudaStream_t st) {
+  decode_times_k<<<1, 1, 0, st>>>(out, n, dt); count_launch();
+}
 void time_embedding(const float* time, const double* scaling, float* out, int batch, int half, cudaStream_t st) {
   time_embedding_k<<<grid_for(static_cast<int64_t>(batch) * half), 256, 0, st>>>(time, scaling, out, batch, half); count_launch();
 }

@@ -316,10 +316,13 @@ class PI0Pytorch(nn.Module):
         self._grad_anchor = None
         self._flat_params = None
         self._flat_used_bf16 = 0
+        self.use_cuda_graph = True  # sample_actions replays one captured CUDA graph per (batch, num_steps)
+        self._graphs = {}
 
         self._engine = None
         self._engine_key = None
         self._workspace = None
+        self._graphs = {}
         self._dp_group = None
         self._keep = None
 
@@ -661,8 +664,11 @@ class PI0Pytorch(nn.Module):
         train_engine = self._engine_key is not None and self._engine_key[1]
         self._ensure_engine(bsize, train=train_engine)
         b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        taps = bool(getattr(self, "_taps", False))
+        if self.use_cuda_graph and not taps:
+            return self._sample_actions_graphed(b, keep, noise, int(num_steps))
         l = _lib.lib()
-        l.pi05_set_taps(self._engine, 1 if getattr(self, "_taps", False) else 0)
+        l.pi05_set_taps(self._engine, 1 if taps else 0)
         _lib.check(l.pi05_prefill(self._engine, C.byref(b), self._stream()), "pi05_prefill")
         out = torch.empty_like(noise)
         _lib.check(
@@ -671,3 +677,44 @@ class PI0Pytorch(nn.Module):
         )
         del keep
         return out
+
+    def _sample_actions_graphed(self, b, keep, noise, num_steps):
+        """The decode path is ~2400 small launches for one observation; replaying them as ONE CUDA graph removes the
+        per-launch host cost.  Static device buffers hold the inputs; the graph is captured once per (batch, steps)."""
+        imgs, masks, toks, tmask = keep
+        key = (b.batch, num_steps)
+        ent = self._graphs.get(key)
+        l = _lib.lib()
+        if ent is None:
+            st = dict(imgs=imgs.clone(), masks=masks.clone(), toks=toks.clone(), tmask=tmask.clone(), noise=noise.clone(),
+                      out=torch.empty_like(noise))
+            sb = _lib.Batch()
+            sb.batch = b.batch
+            sb.images, sb.image_masks = st["imgs"].data_ptr(), st["masks"].data_ptr()
+            sb.tokens, sb.token_mask = st["toks"].data_ptr(), st["tmask"].data_ptr()
+            l.pi05_set_taps(self._engine, 0)
+
+            def run():
+                _lib.check(l.pi05_prefill(self._engine, C.byref(sb), self._stream()), "pi05_prefill")
+                _lib.check(l.pi05_denoise(self._engine, C.c_void_p(st["noise"].data_ptr()), num_steps,
+                                          C.c_void_p(st["out"].data_ptr()), self._stream()), "pi05_denoise")
+
+            side = torch.cuda.Stream(device=self._device())
+            side.wait_stream(torch.cuda.current_stream(self._device()))
+            with torch.cuda.stream(side):
+                run()  # eager warm-up: function attributes, tensor-map cache
+            torch.cuda.current_stream(self._device()).wait_stream(side)
+            torch.cuda.synchronize(self._device())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            ent = (graph, st, sb)
+            self._graphs[key] = ent
+        graph, st, _ = ent
+        st["imgs"].copy_(imgs)
+        st["masks"].copy_(masks)
+        st["toks"].copy_(toks)
+        st["tmask"].copy_(tmask)
+        st["noise"].copy_(noise)
+        graph.replay()
+        return st["out"].clone()

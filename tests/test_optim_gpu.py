@@ -28,8 +28,9 @@ def test_fused_clip_adamw_matches_torch():
     for it in range(3):
         model(obs, *args).mean().backward()
         ref(obs, *args).mean().backward()
-        # same gradients going in (bias / norm-weight reductions use fp32 atomics, so allow last-bit differences)
-        assert H.rel_err(model.flat_parameters()[0].grad, rparams[0].grad) < 1e-4
+        # both replicas hold the same weights at this point (re-synchronised below), so the gradients agree up to the
+        # fp32 atomics order of the bias / norm-weight reductions
+        assert H.rel_err(model.flat_parameters()[0].grad, rparams[0].grad) < 1e-5
         norm = opt.step()
         rnorm = torch.nn.utils.clip_grad_norm_(rparams, max_norm=1.0)
         ropt.step()
@@ -39,6 +40,12 @@ def test_fused_clip_adamw_matches_torch():
         for a, b in zip(model.flat_parameters(), rparams):
             # same update rule; torch clips with a bf16-rounded norm, so allow a few bf16 ulps on the moved weights
             assert H.rel_err(a, b) < 2e-3, it
+        # compare every step in isolation: copy weights and moments of the fused optimiser into the torch replica
+        with torch.no_grad():
+            for i, (a, b) in enumerate(zip(model.flat_parameters(), rparams)):
+                b.copy_(a)
+                ropt.state[b]["exp_avg"].copy_(opt.m[i])
+                ropt.state[b]["exp_avg_sq"].copy_(opt.v[i])
     # the update actually moved the weights and stayed finite
     assert torch.isfinite(model.flat_parameters()[0].float()).all()
     w0 = H.build_pair(oc, seed=5, device="cuda")[0].flat_parameters()[1]
