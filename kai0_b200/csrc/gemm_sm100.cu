@@ -422,8 +422,15 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
     return 1;
   }
   int bn = a.block_n;
-  if (bn == 0) bn = (a.epilogue == EPI_GEGLU) ? 256 : (a.N > 128 ? 256 : 128);
-  if (a.block_n == 0 && a.M <= BM && a.epilogue != EPI_GEGLU) bn = 128;  // one row of tiles: prefer more, narrower CTAs
+  if (bn == 0) {
+    bn = (a.N > 128 || a.epilogue == EPI_GEGLU) ? 256 : 128;
+    // Under-filled grids (decode / prefill at batch 1: M = 50 or 968): when 256-wide tiles cannot occupy the 148 SMs,
+    // narrower tiles double the number of CTAs streaming the weights.
+    const long long mt = (a.M + BM - 1) / BM;
+    const int out256 = (a.epilogue == EPI_GEGLU) ? 128 : 256;
+    const long long tiles256 = mt * ((a.N + out256 - 1) / out256) * a.batch;
+    if (tiles256 < 120) bn = 128;
+  }
   if (bn != 128 && bn != 256) {
     if (err) snprintf(err, err_len, "gemm: unsupported block_n %d", bn);
     return 1;
