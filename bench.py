@@ -353,6 +353,21 @@ def main():
     ms_e2e, last_loss = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
+    if world > 1 and os.environ.get("PI05_BENCH_VERBOSE"):
+        # cost of the exchange step alone (the two flat all-reduces + the 1/world scaling), all ranks in lock-step
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for i in range(3):
+            ev[i].record()
+            model._allreduce_flat_grads()
+        ev[3].record()
+        barrier()
+        if rank == 0:
+            nbytes = sum(g.numel() * g.element_size() for g in model._flat_grad.values() if g is not None)
+            ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            print(f"  [allreduce] {nbytes / 1e9:.2f} GB of gradients: {ts} ms -> "
+                  f"{nbytes / 1e9 / (min(ts) / 1e3):.0f} GB/s algorithmic", file=sys.stderr)
+
     if rank == 0 and os.environ.get("PI05_TORCH_PROFILE"):
         # low-overhead per-kernel breakdown of ONE step (CUPTI via torch.profiler): where the non-GEMM time goes
         from torch.profiler import ProfilerActivity, profile

@@ -98,8 +98,19 @@ int pi05_prefill(pi05_engine* e, const pi05_batch* b, void* stream);
 /* `num_steps` Euler steps from `noise` [batch,H,A] fp32 -> actions_out (pi0_pytorch.py:401-419,421-461) */
 int pi05_denoise(pi05_engine* e, const float* noise, int num_steps, float* actions_out, void* stream);
 
-/* AdvantageEstimator.sample_values / value head on suffix_out[:,0] (pi0_pytorch.py:596-644) */
-int pi05_forward_value(pi05_engine* e, float* value_out, void* stream);
+/* ---- AdvantageEstimator (pi0_pytorch.py:464-644); engine created with cfg.value_head = 1 ------------------ */
+/* Replaces AdvantageEstimator.forward (pi0_pytorch.py:499-592).  progress: [batch] fp32 (clamped to [-1,1] inside,
+ * :574).  loss_out: [batch, action_horizon] fp32 = w_action * mean_d (u_t - v_t)^2 + w_value * (value - progress)^2
+ * (:564-587, the [batch,1] value loss broadcast over the horizon).  aux_out (device, may be NULL): 2 floats,
+ * {mean(loss_action), mean(w_value * value_loss)} = the reference's loss_aux_dict (:582-583).  Followed by
+ * pi05_backward with dloss of shape [batch, action_horizon]. */
+int pi05_forward_advantage(pi05_engine* e, const pi05_batch* b, const float* actions, const float* noise,
+                           const float* time, const float* progress, float w_action, float w_value, float* loss_out,
+                           float* aux_out, void* stream);
+/* Replaces AdvantageEstimator.sample_values (pi0_pytorch.py:596-644): one joint forward without KV cache on
+ * x_t = noise, t = time (both drawn by the caller as the reference does, :604-605); value_out: [batch] fp32. */
+int pi05_forward_value(pi05_engine* e, const pi05_batch* b, const float* noise, const float* time, float* value_out,
+                       void* stream);
 
 /* Debug taps: copy a named intermediate of the last forward into `dst` (fp32 or bf16 as stored). Returns its
  * element count through *numel and dtype through *dtype; dst may be NULL to query.  Used by parity tests only. */

@@ -118,6 +118,7 @@ EXPORTS = (
     "pi05_set_taps",
     "pi05_prefill",
     "pi05_denoise",
+    "pi05_forward_advantage",
     "pi05_forward_value",
     "pi05_get_tap",
     "pi05_gemm_bf16",
@@ -174,7 +175,11 @@ def lib() -> C.CDLL:
             l.pi05_denoise.restype = C.c_int
             l.pi05_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
             l.pi05_forward_value.restype = C.c_int
-            l.pi05_forward_value.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            l.pi05_forward_value.argtypes = [C.c_void_p, C.POINTER(Batch)] + [C.c_void_p] * 4
+            l.pi05_forward_advantage.restype = C.c_int
+            l.pi05_forward_advantage.argtypes = (
+                [C.c_void_p, C.POINTER(Batch)] + [C.c_void_p] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 3
+            )
             l.pi05_get_tap.restype = C.c_int
             l.pi05_get_tap.argtypes = [
                 C.c_void_p,

@@ -11,7 +11,6 @@ using pi05::Engine;
 
 namespace pi05 {
 int engine_init_tables(Engine& e, cudaStream_t st);
-int engine_value(Engine& e, float* value_out, cudaStream_t st);
 }  // namespace pi05
 
 static Engine* E(pi05_engine* p) { return reinterpret_cast<Engine*>(p); }
@@ -163,12 +162,24 @@ int pi05_denoise(pi05_engine* pe, const float* noise, int num_steps, float* acti
   return pi05::engine_denoise(*E(pe), noise, num_steps, actions_out, static_cast<cudaStream_t>(stream));
 }
 
-int pi05_forward_value(pi05_engine* pe, float* value_out, void* stream) {
-  if (!E(pe) || !value_out) {
+int pi05_forward_advantage(pi05_engine* pe, const pi05_batch* b, const float* actions, const float* noise,
+                           const float* time, const float* progress, float w_action, float w_value, float* loss_out,
+                           float* aux_out, void* stream) {
+  if (!E(pe) || !b || !actions || !noise || !time || !progress || !loss_out) {
+    pi05::set_error("pi05_forward_advantage: null argument");
+    return 1;
+  }
+  return pi05::engine_forward_advantage(*E(pe), b, actions, noise, time, progress, w_action, w_value, loss_out, aux_out,
+                                        static_cast<cudaStream_t>(stream));
+}
+
+int pi05_forward_value(pi05_engine* pe, const pi05_batch* b, const float* noise, const float* time, float* value_out,
+                       void* stream) {
+  if (!E(pe) || !b || !noise || !time || !value_out) {
     pi05::set_error("pi05_forward_value: null argument");
     return 1;
   }
-  return pi05::engine_value(*E(pe), value_out, static_cast<cudaStream_t>(stream));
+  return pi05::engine_value(*E(pe), b, noise, time, value_out, static_cast<cudaStream_t>(stream));
 }
 
 int pi05_get_tap(pi05_engine* pe, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream) {

@@ -204,6 +204,18 @@ int engine_plan(Engine& e, bool dry) {
   e.so32 = ar.get<float>(M2 * E);
   e.v_t = ar.get<float>(M2 * c.action_dim);
   e.timevec = ar.get<float>(B);
+  if (c.value_head) {
+    e.vh_in = ar.get<float>(B * E);
+    e.vh_h1 = ar.get<float>(B * E);
+    e.vh_s1 = ar.get<float>(B * E);
+    e.vh_h2 = ar.get<float>(B * E);
+    e.vh_s2 = ar.get<float>(B * E);
+    e.vh_h3 = ar.get<float>(B);
+    e.vh_val = ar.get<float>(B);
+    e.vh_prog = ar.get<float>(B);
+    e.vh_la = ar.get<float>(M2);
+    e.vh_lv = ar.get<float>(B);
+  }
   e.splitk_ws_bytes = static_cast<size_t>(16) << 20;
   e.splitk_ws = ar.get<float>(e.splitk_ws_bytes / sizeof(float));
   {
@@ -243,7 +255,7 @@ int engine_plan(Engine& e, bool dry) {
     e.g_dmods = ar.get<float>(nmods * B * 3 * E);
     e.g_f32a = ar.get<float>(mx(M2 * E, B * 3 * E));
     e.g_f32b = ar.get<float>(mx(M2 * E, B * 3 * E));
-    e.g_f32c = ar.get<float>(mx(M2 * E, B * 3 * E));
+    e.g_f32c = ar.get<float>(mx(M2 * E, B * 6 * E));  // also the value head's backward scratch (6 x [B, E])
     e.g_dcond_part = ar.get<float>(nmods * B * E);
     e.g_acc_elems = static_cast<size_t>(mx(mx(4 * W + 2 * vmlp, 4 * D), mx(T * W + W, 3 * W * 14 * 14 * 3)) + 1024);
     e.g_acc = ar.get<float>(e.g_acc_elems);
@@ -718,15 +730,16 @@ int joint_layer_forward(Engine& e, int l, int B) {
   return 0;
 }
 
-int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
-                   float* loss_out, cudaStream_t st) {
+// Everything of the training forward up to suffix_out / v_t.  x_t_direct != null: x_t is given (sample_values).
+static int forward_network(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                           const float* x_t_direct, const char* who, cudaStream_t st) {
   if (!e.bound) {
-    snprintf(e.err, sizeof(e.err), "pi05_forward: parameters not bound");
+    snprintf(e.err, sizeof(e.err), "%s: parameters not bound", who);
     set_error(e.err);
     return 8;
   }
   if (b->batch <= 0 || b->batch > e.Bmax) {
-    snprintf(e.err, sizeof(e.err), "pi05_forward: batch %d outside [1, %d]", b->batch, e.Bmax);
+    snprintf(e.err, sizeof(e.err), "%s: batch %d outside [1, %d]", who, b->batch, e.Bmax);
     set_error(e.err);
     return 8;
   }
@@ -738,7 +751,10 @@ int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const f
   const pi05_config& c = e.cfg;
   const int depth = c.paligemma.depth;
   const int M2 = B * e.A;
-  flow_inputs(actions, noise, time, e.x_t, e.u_t, B, e.A * c.action_dim, st);
+  if (x_t_direct != nullptr)
+    cudaMemcpyAsync(e.x_t, x_t_direct, static_cast<size_t>(M2) * c.action_dim * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  else
+    flow_inputs(actions, noise, time, e.x_t, e.u_t, B, e.A * c.action_dim, st);
   CHECK_RC(prefix_forward(e, b));
   CHECK_RC(suffix_frontend(e, e.x_t, time, B));
   for (int l = 0; l < depth; ++l) CHECK_RC(joint_layer_forward(e, l, B));
@@ -751,17 +767,81 @@ int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const f
   }
   rmsnorm_fwd(x2f, nullptr, e.mods + (2 * depth) * ms, e.A, e.suffix_out, e.rstd_f2, nullptr, M2, e.E, 1e-6f, st);
   add_tap(e, "suffix_out", e.suffix_out, static_cast<int64_t>(M2) * e.E, PI05_BF16);
+  return 0;
+}
+
+static void action_head(Engine& e, cudaStream_t st) {
+  const pi05_config& c = e.cfg;
+  const int M2 = e.B * e.A;
   cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * e.E, st);
   linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, c.action_dim, e.E, st);
   add_tap(e, "v_t", e.v_t, static_cast<int64_t>(M2) * c.action_dim, PI05_F32);
-  flow_loss(e.u_t, e.v_t, loss_out, static_cast<int64_t>(M2) * c.action_dim, st);
+}
+
+// value = tanh(MLP3(float(suffix_out[:, 0])))   (pi0_pytorch.py:473-481,571-572)
+static void value_head_forward(Engine& e, cudaStream_t st) {
+  const int B = e.B, E = e.E;
+  gather_rows_f32(e.suffix_out, static_cast<int64_t>(e.A) * E, 0, 1, E, e.vh_in, B, st);
+  linear_f32(e.vh_in, e.vh0_w.d<float>(), e.vh0_b.d<float>(), e.vh_h1, B, E, E, st);
+  silu_fwd(e.vh_h1, e.vh_s1, static_cast<int64_t>(B) * E, st);
+  linear_f32(e.vh_s1, e.vh2_w.d<float>(), e.vh2_b.d<float>(), e.vh_h2, B, E, E, st);
+  silu_fwd(e.vh_h2, e.vh_s2, static_cast<int64_t>(B) * E, st);
+  linear_f32(e.vh_s2, e.vh4_w.d<float>(), e.vh4_b.d<float>(), e.vh_h3, B, 1, E, st);
+  tanh_fwd(e.vh_h3, e.vh_val, B, st);
+  add_tap(e, "value", e.vh_val, B, PI05_F32);
+}
+
+static int finish(Engine& e, const char* who) {
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
-    snprintf(e.err, sizeof(e.err), "pi05_forward: %s", cudaGetErrorString(ce));
+    snprintf(e.err, sizeof(e.err), "%s: %s", who, cudaGetErrorString(ce));
     set_error(e.err);
     return 9;
   }
   return 0;
+}
+
+int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                   float* loss_out, cudaStream_t st) {
+  CHECK_RC(forward_network(e, b, actions, noise, time, nullptr, "pi05_forward", st));
+  e.adv_mode = false;
+  action_head(e, st);
+  flow_loss(e.u_t, e.v_t, loss_out, static_cast<int64_t>(e.B) * e.A * e.cfg.action_dim, st);
+  return finish(e, "pi05_forward");
+}
+
+int engine_forward_advantage(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                             const float* progress, float w_action, float w_value, float* loss_out, float* aux_out,
+                             cudaStream_t st) {
+  if (!e.cfg.value_head) {
+    snprintf(e.err, sizeof(e.err), "pi05_forward_advantage: engine was created without cfg.value_head");
+    set_error(e.err);
+    return 8;
+  }
+  CHECK_RC(forward_network(e, b, actions, noise, time, nullptr, "pi05_forward_advantage", st));
+  e.adv_mode = true;
+  e.w_action = w_action;
+  e.w_value = w_value;
+  action_head(e, st);
+  value_head_forward(e, st);
+  cudaMemcpyAsync(e.vh_prog, progress, static_cast<size_t>(e.B) * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  advantage_loss(e.u_t, e.v_t, e.vh_val, e.vh_prog, w_action, w_value, loss_out, e.vh_la, e.vh_lv, aux_out, e.B, e.A,
+                 e.cfg.action_dim, st);
+  return finish(e, "pi05_forward_advantage");
+}
+
+int engine_value(Engine& e, const pi05_batch* b, const float* noise, const float* time, float* value_out,
+                 cudaStream_t st) {
+  if (!e.cfg.value_head) {
+    snprintf(e.err, sizeof(e.err), "pi05_forward_value: engine was created without cfg.value_head");
+    set_error(e.err);
+    return 8;
+  }
+  CHECK_RC(forward_network(e, b, nullptr, nullptr, time, noise, "pi05_forward_value", st));
+  e.adv_mode = false;
+  value_head_forward(e, st);
+  cudaMemcpyAsync(value_out, e.vh_val, static_cast<size_t>(e.B) * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return finish(e, "pi05_forward_value");
 }
 
 }  // namespace pi05

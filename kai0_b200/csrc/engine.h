@@ -126,6 +126,11 @@ struct Engine {
   static constexpr int kMaxDecodeSteps = 64;
   float *dec_times = nullptr, *dec_temb = nullptr, *dec_t1 = nullptr, *dec_t1s = nullptr, *dec_t2 = nullptr,
         *dec_cond = nullptr, *dec_mods = nullptr;
+  // AdvantageEstimator head (cfg.value_head): fp32 activations of tanh(MLP3(suffix_out[:,0])) and the loss pieces
+  float *vh_in = nullptr, *vh_h1 = nullptr, *vh_s1 = nullptr, *vh_h2 = nullptr, *vh_s2 = nullptr, *vh_h3 = nullptr,
+        *vh_val = nullptr, *vh_prog = nullptr, *vh_la = nullptr, *vh_lv = nullptr;
+  bool adv_mode = false;  // last forward was pi05_forward_advantage
+  float w_action = 1.0f, w_value = 0.0f;
   float* splitk_ws = nullptr;  // fp32 scratch of the small-M split-K GEMM path
   size_t splitk_ws_bytes = 0;
   bool taps_enabled = false;
@@ -139,6 +144,11 @@ int engine_plan(Engine& e, bool dry);
 int engine_resolve_params(Engine& e);
 int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
                    float* loss_out, cudaStream_t st);
+int engine_forward_advantage(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
+                             const float* progress, float w_action, float w_value, float* loss_out, float* aux_out,
+                             cudaStream_t st);
+int engine_value(Engine& e, const pi05_batch* b, const float* noise, const float* time, float* value_out,
+                 cudaStream_t st);
 // engine_bwd.cu
 int engine_backward(Engine& e, const float* dloss, cudaStream_t st);
 // engine_decode.cu

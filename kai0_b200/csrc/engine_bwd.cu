@@ -351,10 +351,37 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
   const int nmods = 2 * depth + 1;
   const int64_t ms = static_cast<int64_t>(B) * 3 * E;
   // ---- head: loss -> v_t -> action_out_proj -> suffix_out
-  flow_loss_bwd(e.u_t, e.v_t, dloss, e.g_f32a, static_cast<int64_t>(M2) * ad, st);  // dv
+  float* d_vh_in = nullptr;
+  if (e.adv_mode) {
+    // AdvantageEstimator (pi0_pytorch.py:560-587): dloss is [B, A]; the value head hangs off suffix_out[:, 0]
+    const int64_t BE = static_cast<int64_t>(B) * E;
+    float *dpre = e.g_f32c, *ds2 = e.g_f32c + BE, *dh2 = e.g_f32c + 2 * BE, *ds1 = e.g_f32c + 3 * BE,
+          *dh1 = e.g_f32c + 4 * BE;
+    d_vh_in = e.g_f32c + 5 * BE;
+    advantage_loss_bwd(e.u_t, e.v_t, e.vh_val, e.vh_prog, dloss, e.w_action, e.w_value, e.g_f32a, dpre, B, A, ad, st);
+    linear_f32_wgrad(dpre, e.vh_s2, e.vh4_w.g<float>(), e.vh4_b.g<float>(), B, 1, E, st);
+    linear_f32_dgrad(dpre, e.vh4_w.d<float>(), ds2, B, 1, E, 0, st);
+    silu_bwd(ds2, e.vh_h2, dh2, BE, st);
+    linear_f32_wgrad(dh2, e.vh_s1, e.vh2_w.g<float>(), e.vh2_b.g<float>(), B, E, E, st);
+    linear_f32_dgrad(dh2, e.vh2_w.d<float>(), ds1, B, E, E, 0, st);
+    silu_bwd(ds1, e.vh_h1, dh1, BE, st);
+    linear_f32_wgrad(dh1, e.vh_in, e.vh0_w.g<float>(), e.vh0_b.g<float>(), B, E, E, st);
+    linear_f32_dgrad(dh1, e.vh0_w.d<float>(), d_vh_in, B, E, E, 0, st);
+  } else {
+    flow_loss_bwd(e.u_t, e.v_t, dloss, e.g_f32a, static_cast<int64_t>(M2) * ad, st);  // dv
+    if (e.cfg.value_head) {  // plain PI0 loss on an engine that carries a value head: the head gets zero gradients
+      fill_zero(e.vh0_w.grad, static_cast<size_t>(E) * E * sizeof(float), st);
+      fill_zero(e.vh0_b.grad, static_cast<size_t>(E) * sizeof(float), st);
+      fill_zero(e.vh2_w.grad, static_cast<size_t>(E) * E * sizeof(float), st);
+      fill_zero(e.vh2_b.grad, static_cast<size_t>(E) * sizeof(float), st);
+      fill_zero(e.vh4_w.grad, static_cast<size_t>(E) * sizeof(float), st);
+      fill_zero(e.vh4_b.grad, sizeof(float), st);
+    }
+  }
   linear_f32_wgrad(e.g_f32a, e.so32, e.aout_w.g<float>(), e.aout_b.g<float>(), M2, ad, E, st);
   linear_f32_dgrad(e.g_f32a, e.aout_w.d<float>(), e.g_f32b, M2, ad, E, 0, st);  // d so32
   cast_f32_to_bf16(e.g_f32b, e.g_x2b, static_cast<int64_t>(M2) * E, st);         // grad of the .to(float32) cast
+  if (d_vh_in != nullptr) add_row0_grad(e.g_x2b, d_vh_in, B, A, E, st);          // + grad of suffix_out[:, 0].float()
   fill_zero(e.g_dmods, static_cast<size_t>(nmods) * ms * sizeof(float), st);
   const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;
   rmsnorm_bwd(e.g_x2b, x2f, nullptr, e.mods + (2 * depth) * ms, A, e.rstd_f2, nullptr, e.g_x2, nullptr,

@@ -227,12 +227,4 @@ int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_
   return 0;
 }
 
-int engine_value(Engine& e, float* value_out, cudaStream_t st) {
-  (void)value_out;
-  (void)st;
-  snprintf(e.err, sizeof(e.err), "pi05_forward_value: value head not built in this round");
-  set_error(e.err);
-  return 10;
-}
-
 }  // namespace pi05

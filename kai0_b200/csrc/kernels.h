@@ -93,6 +93,18 @@ void copy_rows_bf16(const bf16* in, int64_t in_bstride, int row_off, int T, int 
 void scatter_rows_bf16(const float* in, bf16* out, int64_t out_bstride, int row_off, int T, int width, int batch,
                        cudaStream_t st);
 
+// ---------------- AdvantageEstimator head (value_kernels.cu; pi0_pytorch.py:473-481,560-587) ----------------
+void tanh_fwd(const float* x, float* y, int64_t n, cudaStream_t st);
+// loss[b,t] = w_a*mean_d (u-v)^2 + w_v*(value[b]-clamp(progress[b],-1,1))^2; la[b,t] = unweighted action loss,
+// lv[b] = weighted value loss; aux (optional) = {mean(la), mean(lv)}
+void advantage_loss(const float* u, const float* v, const float* value, const float* progress, float w_a, float w_v,
+                    float* loss, float* la, float* lv, float* aux, int B, int A, int ad, cudaStream_t st);
+// dv [B,A,ad] and dpre[b] = d loss / d(pre-tanh value) for dloss [B,A]
+void advantage_loss_bwd(const float* u, const float* v, const float* value, const float* progress, const float* dloss,
+                        float w_a, float w_v, float* dv, float* dpre, int B, int A, int ad, cudaStream_t st);
+// g[b, 0, :] = bf(g[b, 0, :] + bf(dx[b, :]))  for g bf16 [B, A, E]
+void add_row0_grad(bf16* g, const float* dx, int B, int A, int E, cudaStream_t st);
+
 // ---------------- fp32 SIMT linears (sgemm_f32.cu) ----------------
 // Y[M,N] = X[M,K] W[N,K]^T + bias   (nn.Linear in fp32: action_in/out_proj, time MLP, adaRMS dense)
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st);

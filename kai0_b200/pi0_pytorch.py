@@ -445,17 +445,20 @@ class PI0Pytorch(nn.Module):
         except Exception:  # noqa: BLE001
             pass
 
-    def _ensure_engine(self, batch: int, train: bool):
+    def _ensure_engine(self, batch: int, train: bool, num_images: int | None = None):
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError(
                 "PI0Pytorch (B200 engine) has no CPU path: move the module to an sm_100 CUDA device first"
             )
+        ni = int(num_images or self.ecfg.num_images)
         need_b = max(batch, self._max_batch_hint or 0)
         key = (dev.index, train)
-        if self._engine is not None and self._engine_key[:2] == key and self._engine_key[2] >= batch:
+        if (self._engine is not None and self._engine_key[:2] == key and self._engine_key[2] >= batch
+                and self._engine_key[3] == ni):
             return
         self._destroy_engine()
+        self._graphs = {}
         l = _lib.lib()
         c = _lib.Config()
         for dst, src in ((c.paligemma, self.pg), (c.expert, self.ex)):
@@ -465,7 +468,7 @@ class PI0Pytorch(nn.Module):
         c.vit_width, c.vit_depth, c.vit_mlp_dim, c.vit_heads = e.vit_width, e.vit_depth, e.vit_mlp_dim, e.vit_heads
         c.vit_patch, c.image_size, c.vocab_size = e.vit_patch, e.image_size, e.vocab_size
         c.action_dim, c.action_horizon, c.max_token_len = e.action_dim, e.action_horizon, e.max_token_len
-        c.num_images, c.max_batch, c.train = e.num_images, need_b, 1 if train else 0
+        c.num_images, c.max_batch, c.train = ni, need_b, 1 if train else 0
         c.value_head = 1 if self._value_head else 0
         nbytes = l.pi05_workspace_bytes(C.byref(c))
         if nbytes == 0:
@@ -479,7 +482,7 @@ class PI0Pytorch(nn.Module):
                 "pi05_create",
             )
         self._engine = handle
-        self._engine_key = (dev.index, train, need_b)
+        self._engine_key = (dev.index, train, need_b, ni)
         if train:
             for dt in (torch.bfloat16, torch.float32):
                 if self._flat_grad[dt] is None:
@@ -521,8 +524,6 @@ class PI0Pytorch(nn.Module):
     def _preprocess_observation(self, observation, *, train=True):
         """preprocessing_pytorch.py:20-173 for inputs already at 224x224 (resize/augmentation: DESIGN.md 'next')."""
         images = getattr(observation, "images")
-        if not set(IMAGE_KEYS).issubset(images):
-            raise ValueError(f"images dict missing keys: expected {IMAGE_KEYS}, got {list(images)}")
         keys = self._image_keys(images)
         state = observation.state
         batch_shape = state.shape[:-1]
@@ -546,12 +547,14 @@ class PI0Pytorch(nn.Module):
         return out_images, out_masks, observation.tokenized_prompt, observation.tokenized_prompt_mask, state
 
     def _image_keys(self, images):
+        if not set(IMAGE_KEYS).issubset(images):
+            raise ValueError(f"images dict missing keys: expected {IMAGE_KEYS}, got {list(images)}")
         return IMAGE_KEYS
 
     def _make_batch(self, images, img_masks, lang_tokens, lang_masks):
         dev = self._device()
-        if len(images) != self.ecfg.num_images:
-            raise ValueError(f"expected {self.ecfg.num_images} images, got {len(images)}")
+        if len(images) != self._engine_key[3]:
+            raise ValueError(f"expected {self._engine_key[3]} images, got {len(images)}")
         imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
         masks = torch.stack([m.to(dev) for m in img_masks], dim=0).to(torch.uint8).contiguous()
         toks = lang_tokens.to(dev, torch.int64).contiguous()
@@ -640,8 +643,13 @@ class PI0Pytorch(nn.Module):
         time = time.to(dev, torch.float32).contiguous()
         B = actions.shape[0]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]))
+        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]),
+                            num_images=len(images))
         pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        return self._run_training_forward(pack, actions, noise, time, need_grad)
+
+    def _run_training_forward(self, pack, actions, noise, time, need_grad):
+        dev = self._device()
         if not need_grad:
             return self._engine_forward(pack, actions, noise, time)
         named = dict(self.named_parameters())
@@ -662,7 +670,7 @@ class PI0Pytorch(nn.Module):
             noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev)
         noise = noise.to(dev, torch.float32).contiguous()
         train_engine = self._engine_key is not None and self._engine_key[1]
-        self._ensure_engine(bsize, train=train_engine)
+        self._ensure_engine(bsize, train=train_engine, num_images=len(images))
         b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         taps = bool(getattr(self, "_taps", False))
         if self.use_cuda_graph and not taps:
@@ -718,3 +726,104 @@ class PI0Pytorch(nn.Module):
         st["noise"].copy_(noise)
         graph.replay()
         return st["out"].clone()
+
+
+class AdvantageEstimator(PI0Pytorch):
+    """B200-native mirror of `AdvantageEstimator` (pi0_pytorch.py:464-644): the pi0.5 backbone over any number of
+    camera/timestep images plus a 3-layer tanh value head on suffix_out[:, 0].  Same engine, `cfg.value_head = 1`."""
+
+    _value_head = True
+
+    def __init__(self, config, **kw):
+        super().__init__(config, **kw)
+        self.loss_value_weight = float(_cfg_get(config, "loss_value_weight", 0.0))  # pi0_pytorch.py:467-468
+        self.loss_action_weight = float(_cfg_get(config, "loss_action_weight", 1.0))
+        self._adv_progress = None
+        self._adv_aux = None
+
+    _PART_ORDER = {"base": 0, "left_wrist": 1, "right_wrist": 2}
+
+    def _image_keys(self, images):
+        """preprocessing_pytorch.py:196-204: keys `<part>_<timestep>_rgb` sorted by (timestep, part)."""
+
+        def sort_key(k):
+            try:
+                part, timestep, _ = k.rsplit("_", 2)
+                return (int(timestep), self._PART_ORDER[part])
+            except (ValueError, KeyError) as exc:
+                raise ValueError(f"image key {k!r} is not of the form <base|left_wrist|right_wrist>_<timestep>_rgb") from exc
+
+        return sorted(images.keys(), key=sort_key)
+
+    def _engine_forward(self, batch_pack, actions, noise, time):
+        b, keep = batch_pack
+        B = b.batch
+        dev = self._device()
+        loss = torch.empty((B, self.ecfg.action_horizon), dtype=torch.float32, device=dev)
+        self._adv_aux = torch.empty(2, dtype=torch.float32, device=dev)
+        l = _lib.lib()
+        l.pi05_set_taps(self._engine, 1 if getattr(self, "_taps", False) else 0)
+        _lib.check(
+            l.pi05_forward_advantage(
+                self._engine, C.byref(b), C.c_void_p(actions.data_ptr()), C.c_void_p(noise.data_ptr()),
+                C.c_void_p(time.data_ptr()), C.c_void_p(self._adv_progress.data_ptr()),
+                C.c_float(self.loss_action_weight), C.c_float(self.loss_value_weight),
+                C.c_void_p(loss.data_ptr()), C.c_void_p(self._adv_aux.data_ptr()), self._stream(),
+            ),
+            "pi05_forward_advantage",
+        )
+        self._last_inputs = (keep, actions, noise, time, self._adv_progress)
+        return loss
+
+    def forward(self, observation, actions, noise=None, time=None, return_loss_dict=False):
+        """pi0_pytorch.py:499-592: loss [B, horizon] = w_action * mean_d (u_t - v_t)^2 + w_value * (value - progress)^2
+        (and the reference's loss_aux_dict when asked).  Augmentation is never applied here (:488-489)."""
+        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=self.training)
+        progress = getattr(observation, "progress", None)
+        if progress is None:
+            raise ValueError("AdvantageEstimator.forward needs observation.progress (pi0_pytorch.py:574)")
+        dev = self._device()
+        actions = actions.to(dev, torch.float32).contiguous()
+        if noise is None:
+            noise = self.sample_noise(actions.shape, actions.device)
+        if time is None:
+            time = self.sample_time(actions.shape[0], actions.device)
+        noise = noise.to(dev, torch.float32).contiguous()
+        time = time.to(dev, torch.float32).contiguous()
+        B = actions.shape[0]
+        self._adv_progress = progress.to(dev, torch.float32).reshape(B).contiguous()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]),
+                            num_images=len(images))
+        pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        loss = self._run_training_forward(pack, actions, noise, time, need_grad)
+        if return_loss_dict:
+            aux = self._adv_aux
+            return loss, {"loss_action": aux[0], "loss_value": aux[1]}
+        return loss
+
+    @torch.no_grad()
+    def sample_values(self, device, observation) -> Tensor:
+        """pi0_pytorch.py:596-644: value (progress) of the current observation, [B, 1] fp32."""
+        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(observation, train=False)
+        bsize = state.shape[0]
+        dev = self._device()
+        noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev).contiguous()
+        time = self.sample_time(bsize, dev).contiguous()
+        return self._sample_values(images, img_masks, lang_tokens, lang_masks, noise, time)
+
+    def _sample_values(self, images, img_masks, lang_tokens, lang_masks, noise, time):
+        bsize = noise.shape[0]
+        train_engine = self._engine_key is not None and self._engine_key[1]
+        self._ensure_engine(bsize, train=train_engine, num_images=len(images))
+        b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
+        out = torch.empty(bsize, dtype=torch.float32, device=self._device())
+        l = _lib.lib()
+        l.pi05_set_taps(self._engine, 1 if getattr(self, "_taps", False) else 0)
+        _lib.check(
+            l.pi05_forward_value(self._engine, C.byref(b), C.c_void_p(noise.data_ptr()), C.c_void_p(time.data_ptr()),
+                                 C.c_void_p(out.data_ptr()), self._stream()),
+            "pi05_forward_value",
+        )
+        del keep
+        return out.view(bsize, 1)

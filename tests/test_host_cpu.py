@@ -151,3 +151,26 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_advantage_estimator_surface():
+    """pi0_pytorch.py:464-498 and preprocessing_pytorch.py:196-204: extra value_head.* parameters (fp32), loss weights
+    read from the config, image keys sorted by (timestep, part) whatever the dict order."""
+    from kai0_b200.pi0_pytorch import AdvantageEstimator
+
+    oc = O.tiny_config(value_head=True)
+    model, params = H.build_pair(oc, device=None, cls=AdvantageEstimator)
+    sd = model.state_dict()
+    for k in ("value_head.0.weight", "value_head.0.bias", "value_head.2.weight", "value_head.2.bias",
+              "value_head.4.weight", "value_head.4.bias"):
+        assert sd[k].dtype == torch.float32 and sd[k].shape == params[k].shape
+    assert model.loss_value_weight == 0.0 and model.loss_action_weight == 1.0  # getattr defaults, :467-468
+    keys = {"right_wrist_0_rgb": 0, "base_-100_rgb": 0, "left_wrist_0_rgb": 0, "base_0_rgb": 0, "left_wrist_-100_rgb": 0}
+    assert model._image_keys(keys) == ["base_-100_rgb", "left_wrist_-100_rgb", "base_0_rgb", "left_wrist_0_rgb",
+                                       "right_wrist_0_rgb"]
+    with pytest.raises(ValueError, match="not of the form"):
+        model._image_keys({"top_head": 0})
+    batch = O.synthetic_batch(oc, 2)
+    obs = H.Obs(batch)
+    with pytest.raises(ValueError, match="progress"):
+        model(obs, batch["actions"])
