@@ -217,6 +217,15 @@ def main():
                          "fused clip+AdamW kernel (kai0_b200.optim.FusedClipAdamW)")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, torchrun children) are routed to stderr; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,7 +246,7 @@ def main():
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- B200 arm
@@ -468,7 +477,7 @@ def main():
             torch.cuda.empty_cache()
             sps, cores, desc, _ = cpu_reference(1, 0, args.cpu_budget, full=not args.small)
             line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -626,6 +626,9 @@ class PI0Pytorch(nn.Module):
             g = self._flat_grad[dt]
             if g is None:
                 continue
+            if dt == torch.bfloat16:
+                # the unused expert lm_head (0.53 GB of never-written gradient) sits last in the bf16 arena: skip it
+                g = g[: self._offsets[_UNUSED[0]][1]]
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp_group)
             g.mul_(1.0 / world)
 
