@@ -115,6 +115,25 @@ int pi05_forward_value(pi05_engine* e, const pi05_batch* b, const float* noise, 
 /* Debug taps: copy a named intermediate of the last forward into `dst` (fp32 or bf16 as stored). Returns its
  * element count through *numel and dtype through *dtype; dst may be NULL to query.  Used by parity tests only. */
 int pi05_get_tap(pi05_engine* e, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream);
+/* Profiling hook (ncu --profile-from-start off): bracket joint layer `layer` (and ViT layer `layer` when it exists)
+ * of every following forward / backward with cudaProfilerStart/Stop; layer < 0 disables.  Instrumentation only. */
+int pi05_debug_profile_layer(pi05_engine* e, int layer);
+
+/* ---- stand-alone operator: observation preprocessing of ONE image key on the device --------------------------
+ * Replaces the per-image body of preprocess_observation_pytorch (src/openpi/models_pytorch/preprocessing_pytorch.py:
+ * 35-148) and resize_with_pad_torch (src/openpi/shared/image_tools.py:55-126).
+ *   image: fp32 in [-1,1], [batch,3,height,width] (channels_last = 0) or [batch,height,width,3] (1)
+ *   out:   fp32 [batch,3,out_size,out_size]  (what pi05_batch.images holds for this key)
+ *   (height,width) != out_size: aspect-preserving bilinear resize, clamp to [-1,1], pad with -1.
+ *   train != 0: the reference's augmentation with the parameters the caller drew exactly as the reference draws
+ *     them (:70-72,85,124,129,137; ONE draw per batch): params = device pointer to 6 floats
+ *     {crop start_h, crop start_w, angle in degrees, brightness, contrast, saturation}; geometric = 1 for the
+ *     non-wrist cameras (95 % crop + resize, rotation when |angle| > 0.1), 0 for wrist cameras (colour only).
+ *   scratch: device, at least pi05_preprocess_scratch_floats(batch, out_size) floats. */
+size_t pi05_preprocess_scratch_floats(int32_t batch, int32_t out_size);
+int pi05_preprocess_image(const float* image, int32_t height, int32_t width, int32_t channels_last, int32_t batch,
+                          int32_t out_size, int32_t train, int32_t geometric, const float* params, float* scratch,
+                          float* out, void* stream);
 
 /* ---- stand-alone operator: the tcgen05 GEMM that every nn.Linear / matmul of the path maps to ----------- */
 typedef struct pi05_gemm_desc {
@@ -139,6 +158,10 @@ typedef struct pi05_gemm_desc {
   float scale;
   int32_t accumulate;
   int32_t block_n;
+  /* optional fp32 scratch (device): enables the split-K paths (small-M decode GEMMs; weight-gradient shapes whose
+   * tile count quantises badly onto the SMs).  NULL = never split.  Results are deterministic either way. */
+  void* workspace;
+  size_t workspace_bytes;
 } pi05_gemm_desc;
 int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream);
 

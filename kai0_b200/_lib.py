@@ -98,6 +98,8 @@ class GemmDesc(C.Structure):
         ("scale", C.c_float),
         ("accumulate", C.c_int32),
         ("block_n", C.c_int32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -121,6 +123,9 @@ EXPORTS = (
     "pi05_forward_advantage",
     "pi05_forward_value",
     "pi05_get_tap",
+    "pi05_preprocess_scratch_floats",
+    "pi05_preprocess_image",
+    "pi05_debug_profile_layer",
     "pi05_gemm_bf16",
     "pi05_fused_clip_adamw",
     "pi05_launch_count",
@@ -189,6 +194,11 @@ def lib() -> C.CDLL:
                 C.POINTER(C.c_int32),
                 C.c_void_p,
             ]
+        if hasattr(l, "pi05_preprocess_image"):
+            l.pi05_preprocess_scratch_floats.restype = C.c_size_t
+            l.pi05_preprocess_scratch_floats.argtypes = [C.c_int32, C.c_int32]
+            l.pi05_preprocess_image.restype = C.c_int
+            l.pi05_preprocess_image.argtypes = [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p] * 4
         if hasattr(l, "pi05_fused_clip_adamw"):
             l.pi05_fused_clip_adamw.restype = C.c_int
             l.pi05_fused_clip_adamw.argtypes = (

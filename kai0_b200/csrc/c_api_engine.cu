@@ -182,6 +182,38 @@ int pi05_forward_value(pi05_engine* pe, const pi05_batch* b, const float* noise,
   return pi05::engine_value(*E(pe), b, noise, time, value_out, static_cast<cudaStream_t>(stream));
 }
 
+int pi05_debug_profile_layer(pi05_engine* pe, int layer) {
+  if (!E(pe)) return 1;
+  E(pe)->profile_layer = layer;
+  return 0;
+}
+
+size_t pi05_preprocess_scratch_floats(int32_t batch, int32_t out_size) {
+  if (batch <= 0 || out_size <= 0) return 0;
+  return pi05::preprocess_scratch_floats(batch, out_size);
+}
+
+int pi05_preprocess_image(const float* image, int32_t height, int32_t width, int32_t channels_last, int32_t batch,
+                          int32_t out_size, int32_t train, int32_t geometric, const float* params, float* scratch,
+                          float* out, void* stream) {
+  if (!image || !out || !scratch || batch <= 0 || height <= 0 || width <= 0 || out_size <= 1) {
+    pi05::set_error("pi05_preprocess_image: bad argument");
+    return 1;
+  }
+  if (train && !params) {
+    pi05::set_error("pi05_preprocess_image: train != 0 needs the 6 augmentation parameters");
+    return 1;
+  }
+  pi05::preprocess_image(image, height, width, channels_last, batch, out_size, train, geometric, params, scratch, out,
+                         static_cast<cudaStream_t>(stream));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    pi05::set_error(cudaGetErrorString(ce));
+    return 9;
+  }
+  return 0;
+}
+
 int pi05_get_tap(pi05_engine* pe, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream) {
   Engine* e = E(pe);
   if (!e || !name) {

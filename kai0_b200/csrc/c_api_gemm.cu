@@ -43,6 +43,7 @@ int pi05_gemm_bf16(const pi05_gemm_desc* d, void* stream) {
   a.bias = d->bias; a.res = d->res; a.ldres = d->ldres; a.res_batch_stride = d->res_batch_stride;
   a.gate = d->gate; a.gate_rows = d->gate_rows; a.ldgate = d->ldgate;
   a.scale = d->scale; a.accumulate = d->accumulate; a.block_n = d->block_n;
+  a.splitk_ws = static_cast<float*>(d->workspace); a.splitk_ws_bytes = d->workspace_bytes;
   char err[512] = "";
   int rc = pi05::gemm_bf16(a, static_cast<cudaStream_t>(stream), err, sizeof(err));
   if (rc != 0) pi05::set_error(err);

@@ -71,6 +71,19 @@ __device__ __forceinline__ float gelu_tanh_bw(float x) {
   return left + right;
 }
 
+// gelu(x) and gelu'(x) from ONE tanh evaluation (same expressions as the two functions above)
+__device__ __forceinline__ void gelu_tanh_fw_bw(float x, float& fw, float& bw) {
+  const float kBeta = 0.7978845608028654f;
+  const float kKappa = 0.044715f;
+  const float x2 = x * x;
+  const float inner = kBeta * (x + kKappa * x2 * x);
+  const float t = fast_tanh_c(inner);
+  fw = 0.5f * x * (1.0f + t);
+  const float left = 0.5f * x * ((1.0f - t * t) * (kBeta * (1.0f + 3.0f * kKappa * x2)));
+  const float right = 0.5f * (1.0f + t);
+  bw = left + right;
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace pi05

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_profiler_api.h>
+
 #include "engine.h"
 #include "errors.h"
 #include "gemm.h"
@@ -216,7 +218,9 @@ int engine_plan(Engine& e, bool dry) {
     e.vh_la = ar.get<float>(M2);
     e.vh_lv = ar.get<float>(B);
   }
-  e.splitk_ws_bytes = static_cast<size_t>(16) << 20;
+  // small-M split-K (decode) needs a few MB; the training wave-quantisation path up to s * M * N fp32 partials of a
+  // weight-gradient GEMM (largest user: 4 x 2560 x 2048 x 4 B = 84 MB)
+  e.splitk_ws_bytes = static_cast<size_t>(tr ? 128 : 16) << 20;
   e.splitk_ws = ar.get<float>(e.splitk_ws_bytes / sizeof(float));
   {
     const int64_t ns = Engine::kMaxDecodeSteps;
@@ -478,6 +482,7 @@ int vision_forward(Engine& e, const float* images, int B, bf16* prefix_embs) {
   for (int l = 0; l < c.vit_depth; ++l) {
     const VitLayerP& p = e.vit[l];
     VitLayerA& a = e.va[l];
+    if (l == e.profile_layer) cudaProfilerStart();
     layernorm_fwd(a.x_in, p.ln1_w.d<bf16>(), p.ln1_b.d<bf16>(), a.h1, a.mean1, a.rstd1, Mv, W, ln_eps, st);
     {  // fused q|k|v projection (+bias)
       GemmArgs g = mk_gemm(Mv, 3 * W, W, a.h1, W, p.q_w.data, W, a.qkv, 3 * W, EPI_BIAS);
@@ -540,6 +545,7 @@ int vision_forward(Engine& e, const float* images, int B, bf16* prefix_embs) {
       snprintf(nm, sizeof(nm), "vit_layer%d", l);
       add_tap(e, nm, a.x_out, static_cast<int64_t>(Mv) * W, PI05_BF16);
     }
+    if (l == e.profile_layer) cudaProfilerStop();
   }
   const bf16* xl = c.vit_depth > 0 ? e.va[c.vit_depth - 1].x_out : e.vit_x0;
   layernorm_fwd(xl, e.post_ln_w.d<bf16>(), e.post_ln_b.d<bf16>(), e.vit_post, e.vit_post_mean, e.vit_post_rstd, Mv, W,
@@ -757,7 +763,11 @@ static int forward_network(Engine& e, const pi05_batch* b, const float* actions,
     flow_inputs(actions, noise, time, e.x_t, e.u_t, B, e.A * c.action_dim, st);
   CHECK_RC(prefix_forward(e, b));
   CHECK_RC(suffix_frontend(e, e.x_t, time, B));
-  for (int l = 0; l < depth; ++l) CHECK_RC(joint_layer_forward(e, l, B));
+  for (int l = 0; l < depth; ++l) {
+    if (l == e.profile_layer) cudaProfilerStart();
+    CHECK_RC(joint_layer_forward(e, l, B));
+    if (l == e.profile_layer) cudaProfilerStop();
+  }
   const int64_t ms = static_cast<int64_t>(B) * 3 * e.E;
   const bf16* x1f = depth > 0 ? e.a1[depth - 1].x_out : e.a1[0].x_in;
   const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;

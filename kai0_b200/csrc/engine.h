@@ -134,6 +134,7 @@ struct Engine {
   float* splitk_ws = nullptr;  // fp32 scratch of the small-M split-K GEMM path
   size_t splitk_ws_bytes = 0;
   bool taps_enabled = false;
+  int profile_layer = -1;  // pi05_debug_profile_layer
   std::map<std::string, Tap> taps;
   cudaStream_t stream = nullptr;
   char err[1024] = "";

@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <cuda_profiler_api.h>
+
 #include "engine.h"
 #include "errors.h"
 #include "gemm.h"
@@ -325,7 +327,11 @@ static int vision_backward(Engine& e, int B) {
                 st);
   cast_f32_to_bf16(acc, e.post_ln_w.g<bf16>(), W, st);
   cast_f32_to_bf16(acc + W, e.post_ln_b.g<bf16>(), W, st);
-  for (int l = c.vit_depth - 1; l >= 0; --l) CHECK_RC(vit_layer_backward(e, l, B));
+  for (int l = c.vit_depth - 1; l >= 0; --l) {
+    if (l == e.profile_layer) cudaProfilerStart();
+    CHECK_RC(vit_layer_backward(e, l, B));
+    if (l == e.profile_layer) cudaProfilerStop();
+  }
   // patch embedding: fp32 weight / bias / position-embedding gradients (modeling_siglip.py:271-282)
   patch_embed_bwd(e.batch_copy.images, e.g_x1, e.patch_w.g<float>(), e.patch_b.g<float>(), e.pos_emb.g<float>(), nullptr,
                   nimg, c.image_size, c.vit_patch, W, st);
@@ -388,7 +394,11 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
               e.g_dmods + (2 * depth) * ms, M2, E, st);
   fill_zero(e.pg_norm_w.grad, static_cast<size_t>(D) * sizeof(float), st);  // final prefix norm never reaches the loss
   // ---- transformer layers
-  for (int l = depth - 1; l >= 0; --l) CHECK_RC(joint_layer_backward(e, l, B, /*g1_zero=*/l == depth - 1));
+  for (int l = depth - 1; l >= 0; --l) {
+    if (l == e.profile_layer) cudaProfilerStart();
+    CHECK_RC(joint_layer_backward(e, l, B, /*g1_zero=*/l == depth - 1));
+    if (l == e.profile_layer) cudaProfilerStop();
+  }
   if (depth == 0) fill_zero(e.g_x1, static_cast<size_t>(B) * e.P * D * 2, st);
   // ---- suffix front-end: action_in_proj, adaRMS dense layers, time MLP
   cast_bf16_to_f32(e.g_x2, e.g_f32a, static_cast<int64_t>(M2) * E, st);  // grad through the bf16 cast of suffix_embs

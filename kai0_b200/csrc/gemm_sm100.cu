@@ -371,6 +371,29 @@ __global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__
     D[m * ldd + n] = __float2bfloat16_rn(acc);
   }
 }
+// STORE-only finish of the wave-quantisation path: 4 outputs per thread, 16-byte partial loads, fixed summation order.
+__global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restrict__ ws, int splits, long long total4,
+                                                           int n4, __nv_bfloat16* __restrict__ D, long long ldd) {
+  const long long total = total4 * 4;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(ws)[q];
+    for (int z = 1; z < splits; ++z) {
+      const float4 v = reinterpret_cast<const float4*>(ws + z * total)[q];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    const long long m = q / n4;
+    const int n = static_cast<int>(q % n4) * 4;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(D + m * ldd + n) = o;
+  }
+}
 }  // namespace
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
@@ -442,6 +465,65 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   static const bool force_1cta = getenv("PI05_GEMM_1CTA") != nullptr;
   const bool use2 = (bn == 256) && (a.M > BM) && !force_1cta;
   const int b_box_rows = (a.epilogue == EPI_GEGLU || use2) ? bn / 2 : bn;
+
+  // ---- wave-quantisation path: weight-gradient shapes (few output tiles, very long K) leave most of the last wave
+  // idle (e.g. 85 pair-tiles on 74 clusters = 57 %).  Split K into s equal chunks run as a batch with fp32 partials
+  // and sum them in a fixed order.  Cost model in units of the un-split, perfectly balanced GEMM time:
+  // t(s) = 1 / wave_efficiency(s) + s * 933 / K   (fp32 partial write+read at ~6 TB/s against ~1.4 PFLOP/s).
+  if (a.epilogue == EPI_STORE && a.batch == 1 && a.splitk_ws != nullptr && a.K % BK == 0 && a.K >= 8192 &&
+      a.block_n == 0 && a.D2 == nullptr) {
+    const long long mt = (a.M + BM - 1) / BM, nt = (a.N + bn - 1) / bn;
+    const long long tiles = use2 ? ((mt + 1) / 2) * nt : mt * nt;
+    const long long slots = use2 ? num_sms() / 2 : num_sms();
+    const int kb = a.K / BK;
+    auto t_of = [&](int sp) {
+      const long long work = tiles * sp;
+      const long long waves = (work + slots - 1) / slots;
+      return static_cast<double>(waves * slots) / static_cast<double>(work) + sp * 933.0 / a.K;
+    };
+    int best = 1;
+    double tbest = t_of(1);
+    for (int sp = 2; sp <= 8; ++sp) {
+      if (kb % sp != 0 || a.K / sp < 2048) continue;
+      if (static_cast<size_t>(sp) * a.M * a.N * sizeof(float) > a.splitk_ws_bytes) continue;
+      const double t = t_of(sp);
+      if (t < tbest) {
+        tbest = t;
+        best = sp;
+      }
+    }
+    if (best > 1 && tbest < 0.9 * t_of(1)) {
+      const int Kc = a.K / best;
+      GemmArgs part = a;
+      part.splitk_ws = nullptr;
+      part.K = Kc;
+      part.batch = best;
+      part.batch_inner = 0;
+      part.a_batch_stride = a.a_major == 0 ? Kc : static_cast<int64_t>(Kc) * a.lda;
+      part.b_batch_stride = a.b_major == 0 ? Kc : static_cast<int64_t>(Kc) * a.ldb;
+      part.epilogue = EPI_F32;
+      part.accumulate = 0;
+      part.D = a.splitk_ws;
+      part.ldd = a.N;
+      part.d_batch_stride = static_cast<int64_t>(a.M) * a.N;
+      part.block_n = bn;
+      int rc = gemm_bf16(part, stream, err, err_len);
+      if (rc != 0) return rc;
+      const long long total = static_cast<long long>(a.M) * a.N;
+      long long grid = (total / 4 + 255) / 256;
+      if (grid > num_sms() * 16) grid = num_sms() * 16;
+      if (a.N % 4 == 0 && a.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 7) == 0) {
+        splitk_sum_store4_k<<<static_cast<int>(grid), 256, 0, stream>>>(a.splitk_ws, best, total / 4, a.N / 4,
+                                                                        static_cast<__nv_bfloat16*>(a.D), a.ldd);
+      } else {
+        splitk_finish_k<<<static_cast<int>(grid), 256, 0, stream>>>(
+            a.splitk_ws, best, a.M, a.N, EPI_STORE, static_cast<__nv_bfloat16*>(a.D), a.ldd, nullptr, 0, nullptr, nullptr,
+            0, nullptr, 1, 0);
+      }
+      count_launch();
+      return 0;
+    }
+  }
 
   const int nz0 = (a.batch_inner > 0) ? a.batch_inner : a.batch;
   if (a.batch % nz0 != 0) {

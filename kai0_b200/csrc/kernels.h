@@ -105,6 +105,14 @@ void advantage_loss_bwd(const float* u, const float* v, const float* value, cons
 // g[b, 0, :] = bf(g[b, 0, :] + bf(dx[b, :]))  for g bf16 [B, A, E]
 void add_row0_grad(bf16* g, const float* dx, int B, int A, int E, cudaStream_t st);
 
+// ---------------- observation preprocessing (preprocess_kernels.cu; preprocessing_pytorch.py:35-148) ----------------
+// One image key: fp32 [-1,1] input [B,3,h,w] (channels_last = 0) or [B,h,w,3] (1) -> out fp32 [B,3,S,S].
+// Resize-with-pad when (h,w) != (S,S); with train != 0 the augmentation with the 6 device-resident parameters
+// {start_h, start_w, angle_deg, brightness, contrast, saturation}; geometric = 0 for wrist cameras.
+size_t preprocess_scratch_floats(int batch, int out_size);
+void preprocess_image(const float* data, int height, int width, int channels_last, int batch, int out_size, int train,
+                      int geometric, const float* params, float* scratch, float* out, cudaStream_t st);
+
 // ---------------- fp32 SIMT linears (sgemm_f32.cu) ----------------
 // Y[M,N] = X[M,K] W[N,K]^T + bias   (nn.Linear in fp32: action_in/out_proj, time MLP, adaRMS dense)
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st);

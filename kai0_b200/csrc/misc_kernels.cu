@@ -73,26 +73,45 @@ __global__ void embed_write_k(const int64_t* __restrict__ tok, const int* __rest
   }
 }
 
-__global__ void geglu_bwd_k(const bf16* __restrict__ dh, const bf16* __restrict__ gu, bf16* __restrict__ dgu,
-                            int64_t rows, int n) {
-  const int chunks = n / 8;
-  const int64_t total = rows * chunks;
-  GRID_STRIDE(idx, total) {
-    const int ch = static_cast<int>(idx % chunks);
-    const int64_t r = idx / chunks;
-    float d[8], g[8], u[8], dg[8], du[8];
-    load8(dh + r * n + ch * 8, d);
-    load8(gu + r * 2 * n + ch * 8, g);
-    load8(gu + r * 2 * n + n + ch * 8, u);
+// One block row-strides over the tensor; each thread owns two 8-wide chunks per row (all six 16-byte loads issued
+// before any math) so that enough bytes are in flight per SM to cover HBM latency.
+__global__ void __launch_bounds__(256) geglu_bwd_k(const bf16* __restrict__ dh, const bf16* __restrict__ gu,
+                                                   bf16* __restrict__ dgu, int64_t rows, int n) {
+  const int chunks = n >> 3;
+  const int half = (chunks + 1) >> 1;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const bf16* dhr = dh + r * n;
+    const bf16* gr = gu + r * 2 * n;
+    bf16* dr = dgu + r * 2 * n;
+    for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < half; c0 += gridDim.x * blockDim.x) {
+      const int c1 = c0 + half;
+      const bool two = c1 < chunks;
+      float d[2][8], g[2][8], u[2][8];
+      load8(dhr + c0 * 8, d[0]);
+      load8(gr + c0 * 8, g[0]);
+      load8(gr + n + c0 * 8, u[0]);
+      if (two) {
+        load8(dhr + c1 * 8, d[1]);
+        load8(gr + c1 * 8, g[1]);
+        load8(gr + n + c1 * 8, u[1]);
+      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float a = bfr(gelu_tanh_fw(g[i]));
-      du[i] = d[i] * a;                   // d(a*u)/du
-      const float da = bfr(d[i] * u[i]);  // d(a*u)/da, a bf16 tensor in the reference graph
-      dg[i] = da * gelu_tanh_bw(g[i]);
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
+        const int c = k == 0 ? c0 : c1;
+        float dg[8], du[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float fw, bw;
+          gelu_tanh_fw_bw(g[k][i], fw, bw);
+          du[i] = d[k][i] * bfr(fw);                // d(a*u)/du
+          const float da = bfr(d[k][i] * u[k][i]);  // d(a*u)/da, a bf16 tensor in the reference graph
+          dg[i] = da * bw;
+        }
+        store8(dr + c * 8, dg);
+        store8(dr + n + c * 8, du);
+      }
     }
-    store8(dgu + r * 2 * n + ch * 8, dg);
-    store8(dgu + r * 2 * n + n + ch * 8, du);
   }
 }
 
@@ -289,7 +308,11 @@ void embed_tokens_bwd(const int64_t* tok, const bf16* dout, int64_t dout_bstride
 }
 
 void geglu_bwd(const bf16* dh, const bf16* gu, bf16* dgu, int64_t rows, int n, cudaStream_t st) {
-  geglu_bwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(dh, gu, dgu, rows, n); count_launch();
+  const int half = (n / 8 + 1) / 2;
+  const int gx = ceil_div(half, 256);
+  int64_t gy = (148 * 8 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  geglu_bwd_k<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, st>>>(dh, gu, dgu, rows, n); count_launch();
 }
 void geglu_fwd(const bf16* gu, bf16* h, int64_t rows, int n, cudaStream_t st) {
   geglu_fwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(gu, h, rows, n); count_launch();

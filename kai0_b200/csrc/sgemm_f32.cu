@@ -184,7 +184,36 @@ __global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ 
 
 }  // namespace
 
+// Few outputs, long K (decode: action_out_proj is [50,1024] x [32,1024]^T): one warp per output element, 16-byte
+// loads along K, shuffle reduction in a fixed order.  The tiled kernel would run this as ONE block with 64 k-steps.
+__global__ void __launch_bounds__(256) linear_f32_small_k(const float* __restrict__ X, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ Y, int M,
+                                                          int N, int K) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= M * N) return;
+  const int m = o / N, n = o % N;
+  const float4* x = reinterpret_cast<const float4*>(X + static_cast<int64_t>(m) * K);
+  const float4* w = reinterpret_cast<const float4*>(W + static_cast<int64_t>(n) * K);
+  float acc = 0.f;
+  for (int k = lane; k < K / 4; k += 32) {
+    const float4 a = x[k], b = w[k];
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    acc = fmaf(a.w, b.w, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) Y[o] = acc + (bias ? bias[n] : 0.f);
+}
+
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st) {
+  if (static_cast<int64_t>(M) * N <= 4096 && K >= 256 && K % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    linear_f32_small_k<<<(M * N + 7) / 8, 256, 0, st>>>(X, W, bias, Y, M, N, K);
+    count_launch();
+    return;
+  }
   run(LinearF32{X, K, 1}, LinearF32{W, K, 1}, EpiF32{Y, N, bias, 0}, M, N, K, 1, st);
 }
 

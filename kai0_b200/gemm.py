@@ -30,6 +30,7 @@ def gemm(
     accumulate: bool = False,
     block_n: int = 0,
     n_out: int | None = None,
+    workspace: torch.Tensor | None = None,
 ):
     """D[z] = A[z] @ B[z]^T with the fused epilogues of csrc/gemm.h.
 
@@ -80,6 +81,8 @@ def gemm(
     d.scale = scale
     d.accumulate = 1 if accumulate else 0
     d.block_n = block_n
+    if workspace is not None:  # fp32 scratch: lets the library pick a split-K schedule (see include/pi05.h)
+        d.workspace, d.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
     stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
     _lib.check(_lib.lib().pi05_gemm_bf16(C.byref(d), stream), "pi05_gemm_bf16")
     if a.dim() == 2 and b.dim() == 2:

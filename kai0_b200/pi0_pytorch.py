@@ -278,7 +278,12 @@ class PI0Pytorch(nn.Module):
         self.ex = get_gemma_config(self.ecfg.action_expert_variant)
         self._max_batch_hint = max_batch
         self.gradient_checkpointing_enabled = False
-        self.augment = False  # train-time image augmentation (preprocessing_pytorch.py:52-142): see DESIGN.md
+        # train-time image augmentation (preprocessing_pytorch.py:52-142).  The reference's forward() always calls its
+        # preprocessing with train=True (pi0_pytorch.py:318), so this is on by default; parity tests that compare
+        # against un-augmented oracles switch it off or inject the drawn parameters (_augment_params_override).
+        self.augment = True
+        self._augment_params_override = None
+        self._pre_scratch = None
 
         # ---- flat arenas + parameter views
         table = parameter_table(self.ecfg, self.pg, self.ex, self._value_head)
@@ -521,30 +526,76 @@ class PI0Pytorch(nn.Module):
         return out
 
     # ------------------------------------------------------------------ inputs
+    _apply_aug = True  # AdvantageEstimator never augments (pi0_pytorch.py:488-489)
+
+    def _draw_augment_params(self, keys, S, dev):
+        """The random numbers of preprocessing_pytorch.py:60-137, drawn with the same torch calls in the same order
+        (one draw per batch and key, on the images' device) and kept on the device: fp32 [len(keys), 6] =
+        {start_h, start_w, angle_deg, brightness, contrast, saturation}."""
+        if self._augment_params_override is not None:
+            return self._augment_params_override.to(dev, torch.float32).contiguous()
+        p = torch.zeros(len(keys), 6, dtype=torch.float32, device=dev)
+        mx = S - int(S * 0.95)
+        for i, key in enumerate(keys):
+            if "wrist" not in key:
+                if mx > 0:
+                    p[i, 0:1] = torch.randint(0, mx + 1, (1,), device=dev)
+                    p[i, 1:2] = torch.randint(0, mx + 1, (1,), device=dev)
+                p[i, 2:3] = torch.rand(1, device=dev) * 10 - 5
+            p[i, 3:4] = 0.7 + torch.rand(1, device=dev) * 0.6
+            p[i, 4:5] = 0.6 + torch.rand(1, device=dev) * 0.8
+            p[i, 5:6] = 0.5 + torch.rand(1, device=dev) * 1.0
+        return p
+
     def _preprocess_observation(self, observation, *, train=True):
-        """preprocessing_pytorch.py:20-173 for inputs already at 224x224 (resize/augmentation: DESIGN.md 'next')."""
+        """preprocessing_pytorch.py:20-173 on the device (pi05_preprocess_image per key): layout sniffing, resize-with-pad
+        to image_size, train-time augmentation, default masks.  Returns the images already stacked in the engine's
+        layout, fp32 [num_images, B, 3, S, S]."""
         images = getattr(observation, "images")
         keys = self._image_keys(images)
         state = observation.state
         batch_shape = state.shape[:-1]
         S = self.ecfg.image_size
-        out_images, out_masks = [], []
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "PI0Pytorch (B200 engine) has no CPU path: move the module to an sm_100 CUDA device first"
+            )
+        B = int(state.shape[0])
+        aug = bool(train and self.augment and self._apply_aug)
+        l = _lib.lib()
+        out = torch.empty((len(keys), B, 3, S, S), dtype=torch.float32, device=dev)
+        need = l.pi05_preprocess_scratch_floats(B, S)
+        if self._pre_scratch is None or self._pre_scratch.numel() < need or self._pre_scratch.device != dev:
+            self._pre_scratch = torch.empty(need, dtype=torch.float32, device=dev)
+        params = self._draw_augment_params(keys, S, dev) if aug else None
+        out_masks = []
         masks = getattr(observation, "image_masks", {}) or {}
-        for key in keys:
+        stream = self._stream()
+        for i, key in enumerate(keys):
             img = images[key]
-            if img.shape[1] != 3 and img.shape[-1] == 3:
-                img = img.permute(0, 3, 1, 2)  # the tower needs NCHW (SURVEY §8b note on layout sniffing)
-            if tuple(img.shape[-2:]) != (S, S):
-                raise ValueError(
-                    f"image {key} has resolution {tuple(img.shape[-2:])}; this round's engine takes {S}x{S} inputs "
-                    "(resize_with_pad is a 'next' row in DESIGN.md)"
-                )
-            out_images.append(img.to(torch.float32))
+            if img.dim() != 4 or img.shape[0] != B:
+                raise ValueError(f"image {key} must be [B,3,H,W] or [B,H,W,3] with B={B}, got {tuple(img.shape)}")
+            channels_first = img.shape[1] == 3  # preprocessing_pytorch.py:42 (same sniffing rule)
+            if not channels_first and img.shape[-1] != 3:
+                raise ValueError(f"image {key} has neither 3 channels first nor last: {tuple(img.shape)}")
+            h, w = (img.shape[2], img.shape[3]) if channels_first else (img.shape[1], img.shape[2])
+            if img.dtype != torch.float32:
+                raise ValueError(f"image {key} must be float32 in [-1, 1] (Observation.from_dict converts uint8), got {img.dtype}")
+            img = img.to(dev).contiguous()
+            _lib.check(
+                l.pi05_preprocess_image(
+                    C.c_void_p(img.data_ptr()), int(h), int(w), 0 if channels_first else 1, B, S, 1 if aug else 0,
+                    0 if "wrist" in key else 1, C.c_void_p(params[i].data_ptr()) if aug else None,
+                    C.c_void_p(self._pre_scratch.data_ptr()), C.c_void_p(out[i].data_ptr()), stream,
+                ),
+                "pi05_preprocess_image",
+            )
             if key in masks:
                 out_masks.append(masks[key])
             else:
                 out_masks.append(torch.ones(batch_shape, dtype=torch.bool, device=state.device))
-        return out_images, out_masks, observation.tokenized_prompt, observation.tokenized_prompt_mask, state
+        return out, out_masks, observation.tokenized_prompt, observation.tokenized_prompt_mask, state
 
     def _image_keys(self, images):
         if not set(IMAGE_KEYS).issubset(images):
@@ -555,7 +606,10 @@ class PI0Pytorch(nn.Module):
         dev = self._device()
         if len(images) != self._engine_key[3]:
             raise ValueError(f"expected {self._engine_key[3]} images, got {len(images)}")
-        imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
+        if isinstance(images, torch.Tensor):
+            imgs = images  # already [num_images, B, 3, S, S] fp32 from _preprocess_observation
+        else:
+            imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
         masks = torch.stack([m.to(dev) for m in img_masks], dim=0).to(torch.uint8).contiguous()
         toks = lang_tokens.to(dev, torch.int64).contiguous()
         tmask = lang_masks.to(dev).to(torch.uint8).contiguous()
@@ -736,6 +790,7 @@ class AdvantageEstimator(PI0Pytorch):
     camera/timestep images plus a 3-layer tanh value head on suffix_out[:, 0].  Same engine, `cfg.value_head = 1`."""
 
     _value_head = True
+    _apply_aug = False  # "Not applying aug for policy and reward model training" (pi0_pytorch.py:488-489)
 
     def __init__(self, config, **kw):
         super().__init__(config, **kw)
@@ -781,10 +836,10 @@ class AdvantageEstimator(PI0Pytorch):
     def forward(self, observation, actions, noise=None, time=None, return_loss_dict=False):
         """pi0_pytorch.py:499-592: loss [B, horizon] = w_action * mean_d (u_t - v_t)^2 + w_value * (value - progress)^2
         (and the reference's loss_aux_dict when asked).  Augmentation is never applied here (:488-489)."""
-        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=self.training)
         progress = getattr(observation, "progress", None)
         if progress is None:
             raise ValueError("AdvantageEstimator.forward needs observation.progress (pi0_pytorch.py:574)")
+        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=self.training)
         dev = self._device()
         actions = actions.to(dev, torch.float32).contiguous()
         if noise is None:

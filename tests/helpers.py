@@ -65,6 +65,9 @@ def build_pair(oc: O.OracleConfig, seed: int = 0, device="cuda", cls=None):
     assert all("lm_head" in m for m in missing), missing
     if device is not None:
         model = model.to(device)
+    # the oracle's forward_loss restates the network on un-augmented images; the train-time augmentation
+    # (on by default like the reference, pi0_pytorch.py:318) has its own parity tests (tests/test_preprocess_gpu.py)
+    model.augment = False
     return model, params
 
 

@@ -170,6 +170,7 @@ def test_reference_call_sequence_train_step_and_checkpoint_roundtrip(tmp_path):
         model.gradient_checkpointing_enable()
     optim = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
     model.train()
+    model.augment = True  # the reference's forward always augments (pi0_pytorch.py:318)
     batch = O.synthetic_batch(oc, 2)
     obs = H.Obs(batch, "cuda")
     torch.manual_seed(0)
@@ -194,10 +195,16 @@ def test_reference_call_sequence_train_step_and_checkpoint_roundtrip(tmp_path):
     # deterministic given explicit noise/time
     model.eval()
     model2.eval()
+    model2.augment = True
     with torch.no_grad():
+        torch.manual_seed(5)  # same augmentation draws for both replicas
         l1 = model(obs, batch["actions"].cuda(), batch["noise"].cuda(), batch["time"].cuda())
+        torch.manual_seed(5)
         l2 = model2(obs, batch["actions"].cuda(), batch["noise"].cuda(), batch["time"].cuda())
+        torch.manual_seed(6)
+        l3 = model2(obs, batch["actions"].cuda(), batch["noise"].cuda(), batch["time"].cuda())
     assert torch.equal(l1, l2)
+    assert not torch.equal(l1, l3)  # different draws -> different augmented images
 
 
 def test_full_size_decode_cache_path_agrees_with_joint_path():
@@ -208,6 +215,7 @@ def test_full_size_decode_cache_path_agrees_with_joint_path():
 
     torch.manual_seed(0)
     model = PI0Pytorch(Pi05EngineConfig(), init_weights=False).to("cuda")
+    model.augment = False  # the decode path never augments; compare like with like
     model.reset_parameters(seed=7)
     # give the zero-initialised adaRMS / RMSNorm weights some signal so the paths are exercised
     with torch.no_grad():

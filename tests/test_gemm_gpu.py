@@ -170,3 +170,27 @@ def test_gemm_rejects_bad_arguments():
     a, b = _mk((64, 60), 1), _mk((64, 60), 2)  # K = 60 -> row pitch not 16-byte aligned
     with pytest.raises(RuntimeError, match="16B aligned"):
         G.gemm(a, b)
+
+
+@pytest.mark.parametrize("M,N,K,a_major,b_major", [
+    (1152, 4304, 24576, 1, 1),   # SigLIP fc1 weight gradient: 85 pair-tiles on 74 clusters -> K split
+    (2560, 2048, 15488, 1, 1),   # Gemma qkv weight gradient shape (half the bench's token count)
+    (1152, 1152, 12288, 1, 1),   # under-filled 128-wide grid
+    (50, 2048, 16384, 0, 0),     # decode down-projection: small-M split-K
+])
+def test_gemm_split_k_paths_match_unsplit(M, N, K, a_major, b_major):
+    """With a workspace the library may split K (fp32 partials summed in a fixed order).  The result must agree with
+    the un-split kernel to fp32-summation-order noise and be bit-identical run to run."""
+    from kai0_b200 import gemm as G
+
+    sa = (M, K) if a_major == 0 else (K, M)
+    sb = (N, K) if b_major == 0 else (K, N)
+    a, b = _mk(sa, 11, 0.5), _mk(sb, 12, 0.05)
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    plain = G.gemm(a, b, a_major=a_major, b_major=b_major)
+    split = G.gemm(a, b, a_major=a_major, b_major=b_major, workspace=ws)
+    again = G.gemm(a, b, a_major=a_major, b_major=b_major, workspace=ws)
+    torch.cuda.synchronize()
+    assert torch.equal(split, again)
+    assert H.rel_err(split, plain) < 1e-3  # both are bf16 roundings of the same fp32 sum up to summation order
+    assert H.rel_err(split, _ref(a, b, a_major, b_major)) < 2.5e-3

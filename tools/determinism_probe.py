@@ -16,6 +16,7 @@ def main():
         from kai0_b200.pi0_pytorch import PI0Pytorch, Pi05EngineConfig
         oc = O.OracleConfig()
         model = PI0Pytorch(Pi05EngineConfig(), init_weights=False).to("cuda")
+        model.augment = False
         model.reset_parameters(seed=7)
         with torch.no_grad():
             for n, p in model.named_parameters():
