@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -19,6 +20,7 @@ constexpr float kMaskValue = -2.3819763e38f;  // pi0_pytorch.py:159
 __global__ void prefix_meta_k(const uint8_t* __restrict__ image_masks, const uint8_t* __restrict__ token_mask, int batch,
                               int num_images, int tpi, int L, uint8_t* __restrict__ pad, int* __restrict__ pos,
                               int* __restrict__ nvalid) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   const int P = num_images * tpi + L;
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(256) rope_pack_fwd_k(const bf16* __restrict__ 
                                                        const bf16* __restrict__ sin_t, bf16* __restrict__ Q,
                                                        bf16* __restrict__ K, bf16* __restrict__ V, int key_off,
                                                        int kv_len, int batch) {
+  pdl_enter();
   const int half = hd / 2;
   const int chunks = half / 8;
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * chunks;
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(256) rope_pack_bwd_k(const bf16* __restrict__ 
                                                        int pos_mode, const bf16* __restrict__ cos_t,
                                                        const bf16* __restrict__ sin_t, bf16* __restrict__ dqkv,
                                                        int key_off, int kv_len, int batch) {
+  pdl_enter();
   const int half = hd / 2;
   const int chunks = half / 8;
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * chunks;
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(256) rope_pack_bwd_k(const bf16* __restrict__ 
 __global__ void __launch_bounds__(256) softmax_fwd_k(bf16* __restrict__ s, int64_t ld, int rows_per_batch, int batch,
                                                      int n_keys, int n_prefix, const uint8_t* __restrict__ pad,
                                                      const uint8_t* __restrict__ qpad, int q_per_token) {
+  pdl_enter();
   const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= static_cast<int64_t>(batch) * rows_per_batch) return;
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_k(bf16* __restrict__ s, int64
 
 __global__ void __launch_bounds__(256) softmax_bwd_k(const bf16* __restrict__ p, bf16* __restrict__ dp, int64_t ld,
                                                      int64_t rows, int n_keys, float scale) {
+  pdl_enter();
   const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_k(const bf16* __restrict__ p,
 
 void prefix_meta(const uint8_t* image_masks, const uint8_t* token_mask, int batch, int num_images, int tokens_per_image,
                  int max_token_len, uint8_t* pad, int* pos, int* nvalid, cudaStream_t st) {
-  prefix_meta_k<<<ceil_div(batch, 32), 32, 0, st>>>(image_masks, token_mask, batch, num_images, tokens_per_image,
+  launch_pdl(prefix_meta_k, dim3(ceil_div(batch, 32)), dim3(32), 0, st, image_masks, token_mask, batch, num_images, tokens_per_image,
                                                     max_token_len, pad, pos, nvalid); count_launch();
 }
 
@@ -196,7 +202,7 @@ void rope_pack_fwd(const bf16* qkv, int T, int H, int hd, const int* pos, const 
                    cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * (hd / 16);
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
-  rope_pack_fwd_k<<<blocks, 256, 0, st>>>(qkv, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, Q, K, V, key_off, kv_len,
+  launch_pdl(rope_pack_fwd_k, dim3(blocks), dim3(256), 0, st, qkv, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, Q, K, V, key_off, kv_len,
                                           batch); count_launch();
 }
 
@@ -205,7 +211,7 @@ void rope_pack_bwd(const bf16* dQ, const float* dK, const float* dV, int T, int 
                    int kv_len, int batch, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(batch) * T * (H + 2) * (hd / 16);
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
-  rope_pack_bwd_k<<<blocks, 256, 0, st>>>(dQ, dK, dV, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, dqkv, key_off,
+  launch_pdl(rope_pack_bwd_k, dim3(blocks), dim3(256), 0, st, dQ, dK, dV, T, H, hd, pos, nvalid, pos_mode, cos_t, sin_t, dqkv, key_off,
                                           kv_len, batch); count_launch();
 }
 
@@ -214,13 +220,13 @@ void softmax_fwd(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_keys,
   if (softmax_fwd_vec(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad, q_per_token > 0 ? q_per_token : 1, st))
     return;
   const int64_t rows = static_cast<int64_t>(batch) * rows_per_batch;
-  softmax_fwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad,
+  launch_pdl(softmax_fwd_k, dim3(ceil_div(rows, 8)), dim3(256), 0, st, s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad,
                                                    q_per_token > 0 ? q_per_token : 1); count_launch();
 }
 
 void softmax_bwd(const bf16* p, bf16* dp, int64_t ld, int rows, int n_keys, float scale, cudaStream_t st) {
   if (softmax_bwd_vec(p, dp, ld, rows, n_keys, scale, st)) return;
-  softmax_bwd_k<<<ceil_div(rows, 8), 256, 0, st>>>(p, dp, ld, rows, n_keys, scale); count_launch();
+  launch_pdl(softmax_bwd_k, dim3(ceil_div(rows, 8)), dim3(256), 0, st, p, dp, ld, rows, n_keys, scale); count_launch();
 }
 
 }  // namespace pi05

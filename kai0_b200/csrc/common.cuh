@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pdl.cuh"
+
 namespace pi05 {
 
 typedef __nv_bfloat16 bf16;

@@ -22,6 +22,7 @@
 #include "gemm.h"
 #include "gemm_device.cuh"
 #include "gemm_host.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace pi05 {
@@ -78,6 +79,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched only shared memory / TMEM / the kernel parameters: it overlaps the previous kernel's tail
+  pdl_enter();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -316,7 +319,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cuda
   }
   const int total = kp.num_m * kp.num_n * kp.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, kp); count_launch();
+  launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ta, tb, kp); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) snprintf(err, err_len, "gemm launch: %s", cudaGetErrorString(e));
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__
                                                        const __nv_bfloat16* __restrict__ res, long long ldres,
                                                        const __nv_bfloat16* __restrict__ gate, int gate_rows,
                                                        long long ldgate) {
+  pdl_enter();
   const long long total = static_cast<long long>(M) * N;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__
 // STORE-only finish of the wave-quantisation path: 4 outputs per thread, 16-byte partial loads, fixed summation order.
 __global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restrict__ ws, int splits, long long total4,
                                                            int n4, __nv_bfloat16* __restrict__ D, long long ldd) {
+  pdl_enter();
   const long long total = total4 * 4;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total4;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -430,7 +435,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
       if (rc != 0) return rc;
       const long long total = static_cast<long long>(a.M) * a.N;
       const int grid = static_cast<int>((total + 255) / 256);
-      splitk_finish_k<<<grid, 256, 0, stream>>>(a.splitk_ws, s, a.M, a.N, a.epilogue, static_cast<__nv_bfloat16*>(a.D), a.ldd,
+      launch_pdl(splitk_finish_k, dim3(grid), dim3(256), 0, stream, a.splitk_ws, s, a.M, a.N, a.epilogue, static_cast<__nv_bfloat16*>(a.D), a.ldd,
                                                 static_cast<__nv_bfloat16*>(a.D2), a.ldd2,
                                                 static_cast<const __nv_bfloat16*>(a.bias),
                                                 static_cast<const __nv_bfloat16*>(a.res), a.ldres,
@@ -513,10 +518,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
       long long grid = (total / 4 + 255) / 256;
       if (grid > num_sms() * 16) grid = num_sms() * 16;
       if (a.N % 4 == 0 && a.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 7) == 0) {
-        splitk_sum_store4_k<<<static_cast<int>(grid), 256, 0, stream>>>(a.splitk_ws, best, total / 4, a.N / 4,
+        launch_pdl(splitk_sum_store4_k, dim3(static_cast<int>(grid)), dim3(256), 0, stream, a.splitk_ws, best, total / 4, a.N / 4,
                                                                         static_cast<__nv_bfloat16*>(a.D), a.ldd);
       } else {
-        splitk_finish_k<<<static_cast<int>(grid), 256, 0, stream>>>(
+        launch_pdl(splitk_finish_k, dim3(static_cast<int>(grid)), dim3(256), 0, stream,
             a.splitk_ws, best, a.M, a.N, EPI_STORE, static_cast<__nv_bfloat16*>(a.D), a.ldd, nullptr, 0, nullptr, nullptr,
             0, nullptr, 1, 0);
       }

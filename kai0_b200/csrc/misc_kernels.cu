@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -21,6 +22,7 @@ inline int grid_for(int64_t n, int per_block = 256, int cap = 148 * 16) {
 __global__ void embed_tokens_fwd_k(const int64_t* __restrict__ tok, const bf16* __restrict__ table,
                                    bf16* __restrict__ out, int batch, int L, int width, int64_t out_bstride, int row_off,
                                    float scale) {
+  pdl_enter();
   const int chunks = width / 8;
   const int64_t total = static_cast<int64_t>(batch) * L * chunks;
   GRID_STRIDE(idx, total) {
@@ -37,6 +39,7 @@ __global__ void embed_tokens_fwd_k(const int64_t* __restrict__ tok, const bf16* 
 
 // first[i] = smallest j with tok[j] == tok[i]
 __global__ void first_occurrence_k(const int64_t* __restrict__ tok, int* __restrict__ first, int n) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t t = tok[i];
@@ -51,6 +54,7 @@ __global__ void first_occurrence_k(const int64_t* __restrict__ tok, int* __restr
 __global__ void embed_accum_k(const int64_t* __restrict__ tok, const int* __restrict__ first,
                               const bf16* __restrict__ dout, int64_t dout_bstride, int row_off,
                               float* __restrict__ scratch, int batch, int L, int width, float scale) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(batch) * L * width;
   GRID_STRIDE(idx, total) {
     const int c = static_cast<int>(idx % width);
@@ -64,6 +68,7 @@ __global__ void embed_accum_k(const int64_t* __restrict__ tok, const int* __rest
 }
 __global__ void embed_write_k(const int64_t* __restrict__ tok, const int* __restrict__ first,
                               const float* __restrict__ scratch, bf16* __restrict__ dtable, int n, int width) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(n) * width;
   GRID_STRIDE(idx, total) {
     const int c = static_cast<int>(idx % width);
@@ -77,6 +82,7 @@ __global__ void embed_write_k(const int64_t* __restrict__ tok, const int* __rest
 // before any math) so that enough bytes are in flight per SM to cover HBM latency.
 __global__ void __launch_bounds__(256) geglu_bwd_k(const bf16* __restrict__ dh, const bf16* __restrict__ gu,
                                                    bf16* __restrict__ dgu, int64_t rows, int n) {
+  pdl_enter();
   const int chunks = n >> 3;
   const int half = (chunks + 1) >> 1;
   for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(256) geglu_bwd_k(const bf16* __restrict__ dh, 
 }
 
 __global__ void geglu_fwd_k(const bf16* __restrict__ gu, bf16* __restrict__ h, int64_t rows, int n) {
+  pdl_enter();
   const int chunks = n / 8;
   const int64_t total = rows * chunks;
   GRID_STRIDE(idx, total) {
@@ -132,6 +139,7 @@ __global__ void geglu_fwd_k(const bf16* __restrict__ gu, bf16* __restrict__ h, i
 
 __global__ void gelu_bwd_k(const bf16* __restrict__ dact, const bf16* __restrict__ pre, bf16* __restrict__ dpre,
                            int64_t n8) {
+  pdl_enter();
   GRID_STRIDE(idx, n8) {
     float d[8], x[8], o[8];
     load8(dact + idx * 8, d);
@@ -145,6 +153,7 @@ __global__ void gelu_bwd_k(const bf16* __restrict__ dact, const bf16* __restrict
 // block: 256 threads = 32 column-groups(8 cols) x 8 row lanes; rows slab of 256 per block.
 __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x, int64_t ld, int64_t rows, int cols,
                                                      float* __restrict__ acc32) {
+  pdl_enter();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 32 + cg) * 8;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 256;
@@ -177,12 +186,15 @@ __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x,
 }
 
 __global__ void cast_f32_to_bf16_k(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) out[i] = __float2bfloat16_rn(in[i]);
 }
 __global__ void cast_bf16_to_f32_k(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) out[i] = __bfloat162float(in[i]);
 }
 __global__ void add_bf16_k(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n8) {
+  pdl_enter();
   GRID_STRIDE(idx, n8) {
     float x[8], y[8];
     load8(a + idx * 8, x);
@@ -193,13 +205,16 @@ __global__ void add_bf16_k(const bf16* __restrict__ a, const bf16* __restrict__ 
   }
 }
 __global__ void add_f32_k(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) a[i] += b[i];
 }
 
 __global__ void fill_f32_k(float* __restrict__ p, float v, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) p[i] = v;
 }
 __global__ void decode_times_k(float* __restrict__ out, int n, float dt) {
+  pdl_enter();
   float t = 1.0f;
   for (int s = 0; s < n; ++s) {
     out[s] = t;
@@ -208,6 +223,7 @@ __global__ void decode_times_k(float* __restrict__ out, int n, float dt) {
 }
 __global__ void time_embedding_k(const float* __restrict__ time, const double* __restrict__ scaling,
                                  float* __restrict__ out, int batch, int half) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(batch) * half;
   GRID_STRIDE(idx, total) {
     const int i = static_cast<int>(idx % half);
@@ -218,12 +234,14 @@ __global__ void time_embedding_k(const float* __restrict__ time, const double* _
   }
 }
 __global__ void silu_fwd_k(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float v = x[i];
     y[i] = v / (1.0f + expf(-v));
   }
 }
 __global__ void silu_bwd_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float v = x[i];
     const float s = 1.0f / (1.0f + expf(-v));
@@ -233,6 +251,7 @@ __global__ void silu_bwd_k(const float* __restrict__ dy, const float* __restrict
 __global__ void flow_inputs_k(const float* __restrict__ actions, const float* __restrict__ noise,
                               const float* __restrict__ time, float* __restrict__ x_t, float* __restrict__ u_t,
                               int batch, int per) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(batch) * per;
   GRID_STRIDE(i, total) {
     const float t = time[i / per];
@@ -243,6 +262,7 @@ __global__ void flow_inputs_k(const float* __restrict__ actions, const float* __
 }
 __global__ void flow_loss_k(const float* __restrict__ u_t, const float* __restrict__ v_t, float* __restrict__ loss,
                             int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) {
     const float d = __fsub_rn(u_t[i], v_t[i]);
     loss[i] = __fmul_rn(d, d);
@@ -250,13 +270,16 @@ __global__ void flow_loss_k(const float* __restrict__ u_t, const float* __restri
 }
 __global__ void flow_loss_bwd_k(const float* __restrict__ u_t, const float* __restrict__ v_t,
                                 const float* __restrict__ dloss, float* __restrict__ dv, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) dv[i] = -2.0f * (u_t[i] - v_t[i]) * dloss[i];
 }
 __global__ void euler_step_k(float* __restrict__ x, const float* __restrict__ v, float dt, int64_t n) {
+  pdl_enter();
   GRID_STRIDE(i, n) x[i] = __fadd_rn(x[i], __fmul_rn(dt, v[i]));
 }
 __global__ void gather_rows_f32_k(const bf16* __restrict__ in, int64_t in_bstride, int row_off, int T, int width,
                                   float* __restrict__ out, int batch) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(batch) * T * width;
   GRID_STRIDE(idx, total) {
     const int c = static_cast<int>(idx % width);
@@ -267,6 +290,7 @@ __global__ void gather_rows_f32_k(const bf16* __restrict__ in, int64_t in_bstrid
 }
 __global__ void copy_rows_bf16_k(const bf16* __restrict__ in, int64_t in_bstride, int row_off, int T, int width,
                                  bf16* __restrict__ out, int batch) {
+  pdl_enter();
   const int chunks = width / 8;
   const int64_t total = static_cast<int64_t>(batch) * T * chunks;
   GRID_STRIDE(idx, total) {
@@ -279,6 +303,7 @@ __global__ void copy_rows_bf16_k(const bf16* __restrict__ in, int64_t in_bstride
 }
 __global__ void scatter_rows_bf16_k(const float* __restrict__ in, bf16* __restrict__ out, int64_t out_bstride,
                                     int row_off, int T, int width, int batch) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(batch) * T * width;
   GRID_STRIDE(idx, total) {
     const int c = static_cast<int>(idx % width);
@@ -293,18 +318,18 @@ __global__ void scatter_rows_bf16_k(const float* __restrict__ in, bf16* __restri
 void embed_tokens_fwd(const int64_t* tok, const bf16* table, bf16* out, int batch, int L, int width, int64_t out_bstride,
                       int row_off, float scale, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(batch) * L * (width / 8);
-  embed_tokens_fwd_k<<<grid_for(total), 256, 0, st>>>(tok, table, out, batch, L, width, out_bstride, row_off, scale); count_launch();
+  launch_pdl(embed_tokens_fwd_k, dim3(grid_for(total)), dim3(256), 0, st, tok, table, out, batch, L, width, out_bstride, row_off, scale); count_launch();
 }
 
 void embed_tokens_bwd(const int64_t* tok, const bf16* dout, int64_t dout_bstride, int row_off, bf16* dtable,
                       float* scratch, int* first, int batch, int L, int width, float scale, cudaStream_t st) {
   const int n = batch * L;
   cudaMemsetAsync(scratch, 0, static_cast<size_t>(n) * width * sizeof(float), st);
-  first_occurrence_k<<<ceil_div(n, 128), 128, 0, st>>>(tok, first, n); count_launch();
+  launch_pdl(first_occurrence_k, dim3(ceil_div(n, 128)), dim3(128), 0, st, tok, first, n); count_launch();
   const int64_t total = static_cast<int64_t>(n) * width;
-  embed_accum_k<<<grid_for(total), 256, 0, st>>>(tok, first, dout, dout_bstride, row_off, scratch, batch, L, width,
+  launch_pdl(embed_accum_k, dim3(grid_for(total)), dim3(256), 0, st, tok, first, dout, dout_bstride, row_off, scratch, batch, L, width,
                                                  scale); count_launch();
-  embed_write_k<<<grid_for(total), 256, 0, st>>>(tok, first, scratch, dtable, n, width); count_launch();
+  launch_pdl(embed_write_k, dim3(grid_for(total)), dim3(256), 0, st, tok, first, scratch, dtable, n, width); count_launch();
 }
 
 void geglu_bwd(const bf16* dh, const bf16* gu, bf16* dgu, int64_t rows, int n, cudaStream_t st) {
@@ -312,66 +337,66 @@ void geglu_bwd(const bf16* dh, const bf16* gu, bf16* dgu, int64_t rows, int n, c
   const int gx = ceil_div(half, 256);
   int64_t gy = (148 * 8 + gx - 1) / gx;
   if (gy > rows) gy = rows;
-  geglu_bwd_k<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, st>>>(dh, gu, dgu, rows, n); count_launch();
+  launch_pdl(geglu_bwd_k, dim3(dim3(gx, static_cast<unsigned>(gy))), dim3(256), 0, st, dh, gu, dgu, rows, n); count_launch();
 }
 void geglu_fwd(const bf16* gu, bf16* h, int64_t rows, int n, cudaStream_t st) {
-  geglu_fwd_k<<<grid_for(rows * (n / 8)), 256, 0, st>>>(gu, h, rows, n); count_launch();
+  launch_pdl(geglu_fwd_k, dim3(grid_for(rows * (n / 8))), dim3(256), 0, st, gu, h, rows, n); count_launch();
 }
 void gelu_bwd(const bf16* dact, const bf16* pre, bf16* dpre, int64_t n, cudaStream_t st) {
-  gelu_bwd_k<<<grid_for(n / 8), 256, 0, st>>>(dact, pre, dpre, n / 8); count_launch();
+  launch_pdl(gelu_bwd_k, dim3(grid_for(n / 8)), dim3(256), 0, st, dact, pre, dpre, n / 8); count_launch();
 }
 void colsum_bf16(const bf16* x, int64_t ld, int64_t rows, int cols, float* acc32, cudaStream_t st) {
   dim3 grid(ceil_div(cols, 256), ceil_div(rows, 256));
-  colsum_bf16_k<<<grid, 256, 0, st>>>(x, ld, rows, cols, acc32); count_launch();
+  launch_pdl(colsum_bf16_k, dim3(grid), dim3(256), 0, st, x, ld, rows, cols, acc32); count_launch();
 }
 void cast_f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st) {
-  cast_f32_to_bf16_k<<<grid_for(n), 256, 0, st>>>(in, out, n); count_launch();
+  launch_pdl(cast_f32_to_bf16_k, dim3(grid_for(n)), dim3(256), 0, st, in, out, n); count_launch();
 }
 void cast_bf16_to_f32(const bf16* in, float* out, int64_t n, cudaStream_t st) {
-  cast_bf16_to_f32_k<<<grid_for(n), 256, 0, st>>>(in, out, n); count_launch();
+  launch_pdl(cast_bf16_to_f32_k, dim3(grid_for(n)), dim3(256), 0, st, in, out, n); count_launch();
 }
 void add_bf16(const bf16* a, const bf16* b, bf16* out, int64_t n, cudaStream_t st) {
-  add_bf16_k<<<grid_for(n / 8), 256, 0, st>>>(a, b, out, n / 8); count_launch();
+  launch_pdl(add_bf16_k, dim3(grid_for(n / 8)), dim3(256), 0, st, a, b, out, n / 8); count_launch();
 }
-void add_f32(float* a, const float* b, int64_t n, cudaStream_t st) { add_f32_k<<<grid_for(n), 256, 0, st>>>(a, b, n); count_launch(); }
+void add_f32(float* a, const float* b, int64_t n, cudaStream_t st) { launch_pdl(add_f32_k, dim3(grid_for(n)), dim3(256), 0, st, a, b, n); count_launch(); }
 void fill_zero(void* p, size_t bytes, cudaStream_t st) { cudaMemsetAsync(p, 0, bytes, st); }
-void fill_f32(float* p, float v, int64_t n, cudaStream_t st) { fill_f32_k<<<grid_for(n), 256, 0, st>>>(p, v, n); count_launch(); }
+void fill_f32(float* p, float v, int64_t n, cudaStream_t st) { launch_pdl(fill_f32_k, dim3(grid_for(n)), dim3(256), 0, st, p, v, n); count_launch(); }
 void decode_times(float* out, int n, float dt, cudaStream_t st) {
-  decode_times_k<<<1, 1, 0, st>>>(out, n, dt); count_launch();
+  launch_pdl(decode_times_k, dim3(1), dim3(1), 0, st, out, n, dt); count_launch();
 }
 void time_embedding(const float* time, const double* scaling, float* out, int batch, int half, cudaStream_t st) {
-  time_embedding_k<<<grid_for(static_cast<int64_t>(batch) * half), 256, 0, st>>>(time, scaling, out, batch, half); count_launch();
+  launch_pdl(time_embedding_k, dim3(grid_for(static_cast<int64_t>(batch) * half)), dim3(256), 0, st, time, scaling, out, batch, half); count_launch();
 }
-void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st) { silu_fwd_k<<<grid_for(n), 256, 0, st>>>(x, y, n); count_launch(); }
+void silu_fwd(const float* x, float* y, int64_t n, cudaStream_t st) { launch_pdl(silu_fwd_k, dim3(grid_for(n)), dim3(256), 0, st, x, y, n); count_launch(); }
 void silu_bwd(const float* dy, const float* x, float* dx, int64_t n, cudaStream_t st) {
-  silu_bwd_k<<<grid_for(n), 256, 0, st>>>(dy, x, dx, n); count_launch();
+  launch_pdl(silu_bwd_k, dim3(grid_for(n)), dim3(256), 0, st, dy, x, dx, n); count_launch();
 }
 void flow_inputs(const float* actions, const float* noise, const float* time, float* x_t, float* u_t, int batch, int per,
                  cudaStream_t st) {
-  flow_inputs_k<<<grid_for(static_cast<int64_t>(batch) * per), 256, 0, st>>>(actions, noise, time, x_t, u_t, batch, per); count_launch();
+  launch_pdl(flow_inputs_k, dim3(grid_for(static_cast<int64_t>(batch) * per)), dim3(256), 0, st, actions, noise, time, x_t, u_t, batch, per); count_launch();
 }
 void flow_loss(const float* u_t, const float* v_t, float* loss, int64_t n, cudaStream_t st) {
-  flow_loss_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, loss, n); count_launch();
+  launch_pdl(flow_loss_k, dim3(grid_for(n)), dim3(256), 0, st, u_t, v_t, loss, n); count_launch();
 }
 void flow_loss_bwd(const float* u_t, const float* v_t, const float* dloss, float* dv, int64_t n, cudaStream_t st) {
-  flow_loss_bwd_k<<<grid_for(n), 256, 0, st>>>(u_t, v_t, dloss, dv, n); count_launch();
+  launch_pdl(flow_loss_bwd_k, dim3(grid_for(n)), dim3(256), 0, st, u_t, v_t, dloss, dv, n); count_launch();
 }
 void euler_step(float* x, const float* v, float dt, int64_t n, cudaStream_t st) {
-  euler_step_k<<<grid_for(n), 256, 0, st>>>(x, v, dt, n); count_launch();
+  launch_pdl(euler_step_k, dim3(grid_for(n)), dim3(256), 0, st, x, v, dt, n); count_launch();
 }
 void gather_rows_f32(const bf16* in, int64_t in_bstride, int row_off, int T, int width, float* out, int batch,
                      cudaStream_t st) {
-  gather_rows_f32_k<<<grid_for(static_cast<int64_t>(batch) * T * width), 256, 0, st>>>(in, in_bstride, row_off, T, width,
+  launch_pdl(gather_rows_f32_k, dim3(grid_for(static_cast<int64_t>(batch) * T * width)), dim3(256), 0, st, in, in_bstride, row_off, T, width,
                                                                                        out, batch); count_launch();
 }
 void copy_rows_bf16(const bf16* in, int64_t in_bstride, int row_off, int T, int width, bf16* out, int batch,
                     cudaStream_t st) {
-  copy_rows_bf16_k<<<grid_for(static_cast<int64_t>(batch) * T * (width / 8)), 256, 0, st>>>(in, in_bstride, row_off, T,
+  launch_pdl(copy_rows_bf16_k, dim3(grid_for(static_cast<int64_t>(batch) * T * (width / 8))), dim3(256), 0, st, in, in_bstride, row_off, T,
                                                                                             width, out, batch); count_launch();
 }
 void scatter_rows_bf16(const float* in, bf16* out, int64_t out_bstride, int row_off, int T, int width, int batch,
                        cudaStream_t st) {
-  scatter_rows_bf16_k<<<grid_for(static_cast<int64_t>(batch) * T * width), 256, 0, st>>>(in, out, out_bstride, row_off,
+  launch_pdl(scatter_rows_bf16_k, dim3(grid_for(static_cast<int64_t>(batch) * T * width)), dim3(256), 0, st, in, out, out_bstride, row_off,
                                                                                          T, width, batch); count_launch();
 }
 

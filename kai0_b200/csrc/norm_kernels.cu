@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -16,6 +17,7 @@ __global__ void __launch_bounds__(WARPS * 32) layernorm_fwd_k(const bf16* __rest
                                                               const bf16* __restrict__ b, bf16* __restrict__ y,
                                                               float* __restrict__ mean_o, float* __restrict__ rstd_o,
                                                               int rows, int width, float eps) {
+  pdl_enter();
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(WARPS * 32) layernorm_bwd_dx_k(const bf16* __r
                                                                  const float* __restrict__ rstd_i,
                                                                  const bf16* __restrict__ dres, bf16* __restrict__ dx,
                                                                  int rows, int width) {
+  pdl_enter();
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) norm_bwd_dwdb_k(const bf16* __restrict__ 
                                                        const float* __restrict__ mean_i,
                                                        const float* __restrict__ rstd_i, float* __restrict__ dw32,
                                                        float* __restrict__ db32, int rows, int width) {
+  pdl_enter();
   const int r0 = blockIdx.x * SLAB;
   const int r1 = min(rows, r0 + SLAB);
   for (int c = threadIdx.x * 8; c < width; c += 256 * 8) {
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_fwd_k(const bf16* __restri
                                                             bf16* __restrict__ y, float* __restrict__ rstd_o,
                                                             bf16* __restrict__ gate_out, int rows, int width,
                                                             float eps) {
+  pdl_enter();
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_dx_k(const bf16* __res
                                                                const float* __restrict__ rstd_i,
                                                                const bf16* __restrict__ dres, bf16* __restrict__ dx,
                                                                int rows, int width) {
+  pdl_enter();
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -231,6 +237,7 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_dx_k(const bf16* __res
 __global__ void __launch_bounds__(256) adarms_bwd_dmod_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                          const float* __restrict__ rstd_i, int rows_per_batch,
                                                          float* __restrict__ dmod, int width) {
+  pdl_enter();
   const int b = blockIdx.x;
   for (int c = threadIdx.x * 8; c < width; c += 256 * 8) {
     float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -261,6 +268,7 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
                                                             const bf16* __restrict__ gate, int rows_per_batch,
                                                             bf16* __restrict__ d_o, float* __restrict__ dmod,
                                                             int width) {
+  pdl_enter();
   const int b = blockIdx.x;
   for (int c = threadIdx.x * 8; c < width; c += 256 * 8) {
     float g[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -287,18 +295,18 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
 
 void layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int rows, int width,
                    float eps, cudaStream_t st) {
-  layernorm_fwd_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(x, w, b, y, mean, rstd, rows, width, eps); count_launch();
+  launch_pdl(layernorm_fwd_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, x, w, b, y, mean, rstd, rows, width, eps); count_launch();
 }
 
 void layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd,
                    const bf16* dres, bf16* dx, float* dw32, float* db32, int rows, int width, cudaStream_t st) {
-  layernorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mean, rstd, dres, dx, rows, width); count_launch();
-  norm_bwd_dwdb_k<true><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, mean, rstd, dw32, db32, rows, width); count_launch();
+  launch_pdl(layernorm_bwd_dx_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, dy, x, w, mean, rstd, dres, dx, rows, width); count_launch();
+  launch_pdl(norm_bwd_dwdb_k<true>, dim3(ceil_div(rows, SLAB)), dim3(256), 0, st, dy, x, mean, rstd, dw32, db32, rows, width); count_launch();
 }
 
 void rmsnorm_fwd(const bf16* x, const float* w, const float* mod, int rows_per_batch, bf16* y, float* rstd,
                  bf16* gate_out, int rows, int width, float eps, cudaStream_t st) {
-  rmsnorm_fwd_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(x, w, mod, rows_per_batch > 0 ? rows_per_batch : rows,
+  launch_pdl(rmsnorm_fwd_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, x, w, mod, rows_per_batch > 0 ? rows_per_batch : rows,
                                                               y, rstd, gate_out, rows, width, eps); count_launch();
 }
 
@@ -306,17 +314,17 @@ void rmsnorm_bwd(const bf16* dy, const bf16* x, const float* w, const float* mod
                  const float* rstd, const bf16* dres, bf16* dx, float* dw32, float* dmod, int rows, int width,
                  cudaStream_t st) {
   const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
-  rmsnorm_bwd_dx_k<<<ceil_div(rows, WARPS), WARPS * 32, 0, st>>>(dy, x, w, mod, rpb, rstd, dres, dx, rows, width); count_launch();
+  launch_pdl(rmsnorm_bwd_dx_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, dy, x, w, mod, rpb, rstd, dres, dx, rows, width); count_launch();
   if (mod == nullptr) {
-    norm_bwd_dwdb_k<false><<<ceil_div(rows, SLAB), 256, 0, st>>>(dy, x, nullptr, rstd, dw32, nullptr, rows, width); count_launch();
+    launch_pdl(norm_bwd_dwdb_k<false>, dim3(ceil_div(rows, SLAB)), dim3(256), 0, st, dy, x, nullptr, rstd, dw32, nullptr, rows, width); count_launch();
   } else {
-    adarms_bwd_dmod_k<<<rows / rpb, 256, 0, st>>>(dy, x, rstd, rpb, dmod, width); count_launch();
+    launch_pdl(adarms_bwd_dmod_k, dim3(rows / rpb), dim3(256), 0, st, dy, x, rstd, rpb, dmod, width); count_launch();
   }
 }
 
 void gated_residual_bwd(const bf16* dy, const bf16* o, const bf16* gate, int rows_per_batch, bf16* d_o, float* dmod,
                         int rows, int width, cudaStream_t st) {
-  gated_residual_bwd_k<<<rows / rows_per_batch, 256, 0, st>>>(dy, o, gate, rows_per_batch, d_o, dmod, width); count_launch();
+  launch_pdl(gated_residual_bwd_k, dim3(rows / rows_per_batch), dim3(256), 0, st, dy, o, gate, rows_per_batch, d_o, dmod, width); count_launch();
 }
 
 }  // namespace pi05

@@ -9,6 +9,7 @@
 #include "../../include/pi05.h"
 #include "common.cuh"
 #include "errors.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -18,6 +19,7 @@ constexpr int NORM_BLOCKS = 1184;  // 8 per SM
 
 __global__ void __launch_bounds__(256) sumsq_k(const bf16* __restrict__ gb, int64_t nb, const float* __restrict__ gf,
                                                int64_t nf, float* __restrict__ partial) {
+  pdl_enter();
   float acc = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(256) sumsq_k(const bf16* __restrict__ gb, int6
 // partial[0..n) -> out[0] = total norm, out[1] = clip coefficient
 __global__ void __launch_bounds__(256) finish_norm_k(const float* __restrict__ partial, int n, float max_norm,
                                                      float* __restrict__ out) {
+  pdl_enter();
   __shared__ double sm[256];
   double t = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) t += static_cast<double>(partial[i]);
@@ -86,6 +89,7 @@ __device__ __forceinline__ void adam_math(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m,
                                                     bf16* __restrict__ v, int64_t n, AdamArgs a,
                                                     const float* __restrict__ coef_ptr) {
+  pdl_enter();
   const float coef = coef_ptr[1];
   const int64_t n8 = n / 8;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const 
 __global__ void __launch_bounds__(256) adamw_f32_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamArgs a,
                                                    const float* __restrict__ coef_ptr) {
+  pdl_enter();
   const float coef = coef_ptr[1];
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -145,9 +150,9 @@ extern "C" int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_b
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = scratch + 8;  // scratch[0] = norm, scratch[1] = clip coefficient, [8, 8+NORM_BLOCKS) partial sums
-  sumsq_k<<<NORM_BLOCKS, 256, 0, st>>>(static_cast<const bf16*>(g_bf16), n_bf16, g_f32, n_f32, partial);
+  launch_pdl(sumsq_k, dim3(NORM_BLOCKS), dim3(256), 0, st, static_cast<const bf16*>(g_bf16), n_bf16, g_f32, n_f32, partial);
   count_launch();
-  finish_norm_k<<<1, 256, 0, st>>>(partial, NORM_BLOCKS, max_norm, scratch);
+  launch_pdl(finish_norm_k, dim3(1), dim3(256), 0, st, partial, NORM_BLOCKS, max_norm, scratch);
   count_launch();
   AdamArgs a;
   a.lr = lr;
@@ -160,12 +165,12 @@ extern "C" int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_b
   a.step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   a.bc2_sqrt = static_cast<float>(sqrt(bc2));
   if (n_bf16 > 0) {
-    adamw_bf16_k<<<148 * 16, 256, 0, st>>>(static_cast<bf16*>(p_bf16), static_cast<const bf16*>(g_bf16),
+    launch_pdl(adamw_bf16_k, dim3(148 * 16), dim3(256), 0, st, static_cast<bf16*>(p_bf16), static_cast<const bf16*>(g_bf16),
                                           static_cast<bf16*>(m_bf16), static_cast<bf16*>(v_bf16), n_bf16, a, scratch);
     count_launch();
   }
   if (n_f32 > 0) {
-    adamw_f32_k<<<148 * 8, 256, 0, st>>>(p_f32, g_f32, m_f32, v_f32, n_f32, a, scratch);
+    launch_pdl(adamw_f32_k, dim3(148 * 8), dim3(256), 0, st, p_f32, g_f32, m_f32, v_f32, n_f32, a, scratch);
     count_launch();
   }
   cudaError_t e = cudaGetLastError();

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 namespace {
@@ -36,6 +37,7 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 
 // image_tools.py:55-126 for fp32 input: out NCHW [B,3,S,S]
 __global__ void resize_pad_k(Img src, int S, int rh, int rw, int ph0, int pw0, float* __restrict__ out, int B) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(B) * 3 * S * S;
   const float sh = static_cast<float>(src.h) / rh, sw = static_cast<float>(src.w) / rw;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -59,6 +61,7 @@ __global__ void resize_pad_k(Img src, int S, int rh, int rw, int ph0, int pw0, f
 
 // plain layout change to NCHW (no resize, no augmentation)
 __global__ void to_nchw_k(Img src, float* __restrict__ out, int B) {
+  pdl_enter();
   const int S = src.h;
   const int64_t total = static_cast<int64_t>(B) * 3 * S * S;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -97,6 +100,7 @@ constexpr int kGeoBlocks = 32;  // blocks per sample in pass 1 (= partial sums p
 // pass 1.  geometric = 1: crop/resize + rotation (non-wrist cameras); 0: just x/2 + 0.5.
 __global__ void __launch_bounds__(256) augment_geo_k(Img im, const float* __restrict__ params, int geometric,
                                                      float* __restrict__ tmp, float* __restrict__ partial) {
+  pdl_enter();
   const int S = im.h, b = blockIdx.y;
   const float bright = params[3];
   Geo g;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(256) augment_geo_k(Img im, const float* __rest
 // pass 2: colour (preprocessing_pytorch.py:122-146)
 __global__ void __launch_bounds__(256) augment_colour_k(const float* __restrict__ tmp, const float* __restrict__ partial,
                                                         const float* __restrict__ params, int S, float* __restrict__ out) {
+  pdl_enter();
   const int b = blockIdx.y, npix = S * S;
   const float bright = params[3], contrast = params[4], satur = params[5];
   float tot = 0.f;
@@ -222,19 +227,19 @@ void preprocess_image(const float* data, int height, int width, int channels_las
     const int rh = static_cast<int>(height / ratio), rw = static_cast<int>(width / ratio);
     const int ph0 = (S - rh) / 2, pw0 = (S - rw) / 2;
     float* dst = train ? resized : out;
-    resize_pad_k<<<blocks_for(n), 256, 0, st>>>(src, S, rh, rw, ph0, pw0, dst, batch);
+    launch_pdl(resize_pad_k, dim3(blocks_for(n)), dim3(256), 0, st, src, S, rh, rw, ph0, pw0, dst, batch);
     count_launch();
     if (!train) return;
     cur = Img{resized, S, S, 0};
   } else if (!train) {
-    to_nchw_k<<<blocks_for(n), 256, 0, st>>>(src, out, batch);
+    launch_pdl(to_nchw_k, dim3(blocks_for(n)), dim3(256), 0, st, src, out, batch);
     count_launch();
     return;
   }
   dim3 grid(kGeoBlocks, batch);
-  augment_geo_k<<<grid, 256, 0, st>>>(cur, params, geometric, tmp, partial);
+  launch_pdl(augment_geo_k, dim3(grid), dim3(256), 0, st, cur, params, geometric, tmp, partial);
   count_launch();
-  augment_colour_k<<<grid, 256, 0, st>>>(tmp, partial, params, S, out);
+  launch_pdl(augment_colour_k, dim3(grid), dim3(256), 0, st, tmp, partial, params, S, out);
   count_launch();
 }
 

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include "pdl.cuh"
+
 namespace pi05 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

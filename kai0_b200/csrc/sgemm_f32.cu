@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -81,6 +82,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 template <class LA, class LB, class EPI>
 __global__ void __launch_bounds__(256) sgemm_k(LA la_, LB lb_, EPI epi_, int M, int N, int K, int k_per_split,
                                                int batched) {
+  pdl_enter();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   // blockIdx.z is either a split-K slice (atomic epilogue) or, in batched mode, an independent problem
@@ -145,16 +147,17 @@ void run(LA la, LB lb, EPI epi, int M, int N, int K, int splits, cudaStream_t st
   kps = ((kps + TK - 1) / TK) * TK;
   splits = (K + kps - 1) / kps;
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
-  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, kps, 0); count_launch();
+  launch_pdl(sgemm_k<LA, LB, EPI>, dim3(grid), dim3(256), 0, st, la, lb, epi, M, N, K, kps, 0); count_launch();
 }
 
 template <class LA, class LB, class EPI>
 void run_batched(LA la, LB lb, EPI epi, int M, int N, int K, int batch, cudaStream_t st) {
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, batch);
-  sgemm_k<<<grid, 256, 0, st>>>(la, lb, epi, M, N, K, K, 1); count_launch();
+  launch_pdl(sgemm_k<LA, LB, EPI>, dim3(grid), dim3(256), 0, st, la, lb, epi, M, N, K, K, 1); count_launch();
 }
 
 __global__ void reduce_batches_k(const float* __restrict__ part, float* __restrict__ out, int64_t n, int batch) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float s = 0.f;
@@ -164,6 +167,7 @@ __global__ void reduce_batches_k(const float* __restrict__ part, float* __restri
 }
 
 __global__ void colsum_f32_k(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+  pdl_enter();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   float s = 0.f;
@@ -173,6 +177,7 @@ __global__ void colsum_f32_k(const float* __restrict__ x, int M, int N, float* _
 
 // dpos[patch, c] = sum_img dout[img, patch, c]; dbias[c] = sum_{img,patch} dout
 __global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ dpos, int n_img, int patches, int width) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(patches) * width;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -189,6 +194,7 @@ __global__ void patch_dpos_k(const bf16* __restrict__ dout, float* __restrict__ 
 __global__ void __launch_bounds__(256) linear_f32_small_k(const float* __restrict__ X, const float* __restrict__ W,
                                                           const float* __restrict__ bias, float* __restrict__ Y, int M,
                                                           int N, int K) {
+  pdl_enter();
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= M * N) return;
   const int m = o / N, n = o % N;
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(256) linear_f32_small_k(const float* __restric
 void linear_f32(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, cudaStream_t st) {
   if (static_cast<int64_t>(M) * N <= 4096 && K >= 256 && K % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
-    linear_f32_small_k<<<(M * N + 7) / 8, 256, 0, st>>>(X, W, bias, Y, M, N, K);
+    launch_pdl(linear_f32_small_k, dim3((M * N + 7) / 8), dim3(256), 0, st, X, W, bias, Y, M, N, K);
     count_launch();
     return;
   }
@@ -225,7 +231,7 @@ void linear_f32_dgrad(const float* dY, const float* W, float* dX, int M, int N, 
 void linear_f32_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
   // dW[n, k] = sum_i dY[i, n] X[i, k] -> A(n, i) = dY[i*N + n], B(k, i) = X[i*K + k]
   run(LinearF32{dY, 1, N}, LinearF32{X, 1, K}, EpiF32{dW, K, nullptr, 0}, N, K, M, 1, st);
-  if (db) colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY, M, N, db); count_launch();
+  if (db) launch_pdl(colsum_f32_k, dim3((N + 127) / 128), dim3(128), 0, st, dY, M, N, db); count_launch();
 }
 
 // `batch` independent linears that share X: Y[z] = X W[z]^T + bias[z]  (all 37 adaRMS modulation layers in one launch)
@@ -240,7 +246,7 @@ void linear_f32_wgrad_batched(const float* dY, const float* X, float* dW, float*
   run_batched(LinearF32{dY, 1, N, dy_stride}, LinearF32{X, 1, K, 0}, EpiF32{dW, K, nullptr, 0, w_stride, 0}, N, K, M,
               batch, st);
   for (int z = 0; z < batch; ++z) {
-    colsum_f32_k<<<(N + 127) / 128, 128, 0, st>>>(dY + z * dy_stride, M, N, db + z * b_stride);
+    launch_pdl(colsum_f32_k, dim3((N + 127) / 128), dim3(128), 0, st, dY + z * dy_stride, M, N, db + z * b_stride);
     count_launch();
   }
 }
@@ -250,7 +256,7 @@ void linear_f32_dgrad_batched_sum(const float* dY, const float* W, float* dX, fl
   run_batched(LinearF32{dY, N, 1, dy_stride}, LinearF32{W, 1, K, w_stride},
               EpiF32{scratch, K, nullptr, 0, static_cast<int64_t>(M) * K, 0}, M, K, N, batch, st);
   const int64_t n = static_cast<int64_t>(M) * K;
-  reduce_batches_k<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(scratch, dX, n, batch);
+  launch_pdl(reduce_batches_k, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, st, scratch, dX, n, batch);
   count_launch();
 }
 
@@ -274,9 +280,9 @@ void patch_embed_bwd(const float* images, const bf16* dout, float* dW, float* db
   run(LinearBF16{dout, 1, width}, Im2colT{Im2col{images, image_size, patch, P}}, EpiF32{dW, K, nullptr, 2}, width, K,
       rows, splits, st);
   const int64_t total = static_cast<int64_t>(P) * P * width;
-  patch_dpos_k<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(dout, dpos, n_img, P * P, width); count_launch();
+  launch_pdl(patch_dpos_k, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, dout, dpos, n_img, P * P, width); count_launch();
   // dbias = column sum of dpos
-  colsum_f32_k<<<(width + 127) / 128, 128, 0, st>>>(dpos, P * P, width, dbias); count_launch();
+  launch_pdl(colsum_f32_k, dim3((width + 127) / 128), dim3(128), 0, st, dpos, P * P, width, dbias); count_launch();
 }
 
 }  // namespace pi05

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 
@@ -18,6 +19,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, int64_t ld, int rows_per_batch, int batch,
                                                          int n_keys, int n_prefix, const uint8_t* __restrict__ pad,
                                                          const uint8_t* __restrict__ qpad, int q_per_token) {
+  pdl_enter();
   const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= static_cast<int64_t>(batch) * rows_per_batch) return;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
 template <int CH>
 __global__ void __launch_bounds__(256) softmax_bwd_vec_k(const bf16* __restrict__ p, bf16* __restrict__ dp, int64_t ld,
                                                          int64_t rows, int n_keys, float scale) {
+  pdl_enter();
   const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -139,7 +142,7 @@ bool softmax_fwd_vec(bf16* s, int64_t ld, int rows_per_batch, int batch, int n_k
   const int grid = ceil_div(rows, 8);
   const int ch = static_cast<int>((ld + 255) / 256);
 #define LAUNCH_F(C)                                                                                                   \
-  softmax_fwd_vec_k<C><<<grid, 256, 0, st>>>(s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad, q_per_token); \
+  launch_pdl(softmax_fwd_vec_k<C>, dim3(grid), dim3(256), 0, st, s, ld, rows_per_batch, batch, n_keys, n_prefix, pad, qpad, q_per_token); \
   count_launch();                                                                                                     \
   break;
   switch (ch) {
@@ -162,7 +165,7 @@ bool softmax_bwd_vec(const bf16* p, bf16* dp, int64_t ld, int64_t rows, int n_ke
   const int grid = ceil_div(rows, 8);
   const int ch = static_cast<int>((ld + 255) / 256);
 #define LAUNCH_B(C)                                                               \
-  softmax_bwd_vec_k<C><<<grid, 256, 0, st>>>(p, dp, ld, rows, n_keys, scale);    \
+  launch_pdl(softmax_bwd_vec_k<C>, dim3(grid), dim3(256), 0, st, p, dp, ld, rows, n_keys, scale);    \
   count_launch();                                                                 \
   break;
   switch (ch) {

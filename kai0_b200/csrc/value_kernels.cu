@@ -3,11 +3,13 @@
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace pi05 {
 namespace {
 
 __global__ void tanh_fwd_k(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) y[i] = tanhf(x[i]);
 }
@@ -16,6 +18,7 @@ __global__ void tanh_fwd_k(const float* __restrict__ x, float* __restrict__ y, i
 __global__ void advantage_loss_k(const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ value,
                                  const float* __restrict__ progress, float w_a, float w_v, float* __restrict__ loss,
                                  float* __restrict__ la, float* __restrict__ lv, int B, int A, int ad) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * A) return;
   const int b = i / A;
@@ -38,6 +41,7 @@ __global__ void advantage_loss_k(const float* __restrict__ u, const float* __res
 // deterministic single-block means: out[0] = mean(la[0..n1)), out[1] = mean(lv[0..n2))
 __global__ void advantage_aux_k(const float* __restrict__ la, int n1, const float* __restrict__ lv, int n2,
                                 float* __restrict__ out) {
+  pdl_enter();
   __shared__ float sh[2][32];
   float a = 0.0f, b = 0.0f;
   for (int i = threadIdx.x; i < n1; i += blockDim.x) a += la[i];
@@ -68,6 +72,7 @@ __global__ void advantage_loss_bwd_k(const float* __restrict__ u, const float* _
                                      const float* __restrict__ value, const float* __restrict__ progress,
                                      const float* __restrict__ dloss, float w_a, float w_v, float* __restrict__ dv,
                                      float* __restrict__ dpre, int B, int A, int ad) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * A * ad;
   if (i < total) {
@@ -87,6 +92,7 @@ __global__ void advantage_loss_bwd_k(const float* __restrict__ u, const float* _
 
 // g[b*A + 0, :] = bf( g + bf(dx[b, :]) ): autograd sums the two bf16 gradients of suffix_out (slice + select)
 __global__ void add_row0_grad_k(bf16* __restrict__ g, const float* __restrict__ dx, int B, int A, int E) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(B) * E) return;
   const int b = static_cast<int>(i / E), c = static_cast<int>(i % E);
@@ -97,27 +103,27 @@ __global__ void add_row0_grad_k(bf16* __restrict__ g, const float* __restrict__ 
 }  // namespace
 
 void tanh_fwd(const float* x, float* y, int64_t n, cudaStream_t st) {
-  tanh_fwd_k<<<ceil_div(n, 256), 256, 0, st>>>(x, y, n);
+  launch_pdl(tanh_fwd_k, dim3(ceil_div(n, 256)), dim3(256), 0, st, x, y, n);
   count_launch();
 }
 void advantage_loss(const float* u, const float* v, const float* value, const float* progress, float w_a, float w_v,
                     float* loss, float* la, float* lv, float* aux, int B, int A, int ad, cudaStream_t st) {
-  advantage_loss_k<<<ceil_div(static_cast<int64_t>(B) * A, 128), 128, 0, st>>>(u, v, value, progress, w_a, w_v, loss, la,
+  launch_pdl(advantage_loss_k, dim3(ceil_div(static_cast<int64_t>(B) * A, 128)), dim3(128), 0, st, u, v, value, progress, w_a, w_v, loss, la,
                                                                              lv, B, A, ad);
   count_launch();
   if (aux != nullptr) {
-    advantage_aux_k<<<1, 256, 0, st>>>(la, B * A, lv, B, aux);
+    launch_pdl(advantage_aux_k, dim3(1), dim3(256), 0, st, la, B * A, lv, B, aux);
     count_launch();
   }
 }
 void advantage_loss_bwd(const float* u, const float* v, const float* value, const float* progress, const float* dloss,
                         float w_a, float w_v, float* dv, float* dpre, int B, int A, int ad, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(B) * A * ad;
-  advantage_loss_bwd_k<<<ceil_div(total, 256), 256, 0, st>>>(u, v, value, progress, dloss, w_a, w_v, dv, dpre, B, A, ad);
+  launch_pdl(advantage_loss_bwd_k, dim3(ceil_div(total, 256)), dim3(256), 0, st, u, v, value, progress, dloss, w_a, w_v, dv, dpre, B, A, ad);
   count_launch();
 }
 void add_row0_grad(bf16* g, const float* dx, int B, int A, int E, cudaStream_t st) {
-  add_row0_grad_k<<<ceil_div(static_cast<int64_t>(B) * E, 256), 256, 0, st>>>(g, dx, B, A, E);
+  launch_pdl(add_row0_grad_k, dim3(ceil_div(static_cast<int64_t>(B) * E, 256)), dim3(256), 0, st, g, dx, B, A, E);
   count_launch();
 }
 

@@ -29,7 +29,10 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us"
 def main():
     rep = sys.argv[1]
     peak = float(sys.argv[2]) if len(sys.argv) > 2 else 6571.0
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported: ncu -i X.ncu-rep --page raw --csv > X.csv
+        out = "".join(ln for ln in open(rep) if ln.startswith('"'))
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
 
