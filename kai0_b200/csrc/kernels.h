@@ -24,6 +24,11 @@ void rmsnorm_fwd(const bf16* x, const float* w, const float* mod, int rows_per_b
 void rmsnorm_bwd(const bf16* dy, const bf16* x, const float* w, const float* mod, int rows_per_batch,
                  const float* rstd, const bf16* dres, bf16* dx, float* dw32, float* dmod, int rows, int width,
                  cudaStream_t st);
+// One-pass variants (norm_bwd_fused.cu): dx and dw (db) from a single read of dy and x; false = shape not supported.
+bool layernorm_bwd_fused(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd,
+                         const bf16* dres, bf16* dx, float* dw32, float* db32, int rows, int width, cudaStream_t st);
+bool rmsnorm_bwd_fused(const bf16* dy, const bf16* x, const float* w, const float* rstd, const bf16* dres, bf16* dx,
+                       float* dw32, int rows, int width, cudaStream_t st);
 // y = x + o*gate backward pieces for the adaptive stream: d_o = bf(dy*gate[b]); dmod[b].gate += sum_rows dy*o.
 void gated_residual_bwd(const bf16* dy, const bf16* o, const bf16* gate, int rows_per_batch, bf16* d_o, float* dmod,
                         int rows, int width, cudaStream_t st);

@@ -233,15 +233,19 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_dx_k(const bf16* __res
   }
 }
 
-// adaptive: dmod[b].scale += sum_rows dy*xhat ; dmod[b].shift += sum_rows dy.  One block per batch element.
+// adaptive: dmod[b].scale += sum_rows dy*xhat ; dmod[b].shift += sum_rows dy.
+// grid (width / 256, batch): lane = 8-column group, warp = row lane (rows t = warp, warp + 8, ...); the 8 row-lane
+// partials are summed in a fixed order through shared memory (deterministic, no atomics).
 __global__ void __launch_bounds__(256) adarms_bwd_dmod_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                          const float* __restrict__ rstd_i, int rows_per_batch,
                                                          float* __restrict__ dmod, int width) {
   pdl_enter();
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x * 8; c < width; c += 256 * 8) {
-    float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < rows_per_batch; ++t) {
+  __shared__ float red[2][8][256];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < width) {
+    for (int t = warp; t < rows_per_batch; t += 8) {
       const int r = b * rows_per_batch + t;
       const int64_t off = static_cast<int64_t>(r) * width + c;
       float d[8], v[8];
@@ -254,12 +258,24 @@ __global__ void __launch_bounds__(256) adarms_bwd_dmod_k(const bf16* __restrict_
         a2[i] += d[i];
       }
     }
-    float* dm = dmod + static_cast<int64_t>(b) * 3 * width;
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dm[c + i] += a1[i];
-      dm[width + c + i] += a2[i];
+  for (int i = 0; i < 8; ++i) {
+    red[0][warp][lane * 8 + i] = a1[i];
+    red[1][warp][lane * 8 + i] = a2[i];
+  }
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < width) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      t1 += red[0][w][threadIdx.x];
+      t2 += red[1][w][threadIdx.x];
     }
+    float* dm = dmod + static_cast<int64_t>(b) * 3 * width;
+    dm[cc] += t1;
+    dm[width + cc] += t2;
   }
 }
 
@@ -269,11 +285,14 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
                                                             bf16* __restrict__ d_o, float* __restrict__ dmod,
                                                             int width) {
   pdl_enter();
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x * 8; c < width; c += 256 * 8) {
-    float g[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  __shared__ float red[8][256];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < width) {
+    float g[8];
     load8(gate + static_cast<int64_t>(b) * width + c, g);
-    for (int t = 0; t < rows_per_batch; ++t) {
+    for (int t = warp; t < rows_per_batch; t += 8) {
       const int64_t off = (static_cast<int64_t>(b) * rows_per_batch + t) * width + c;
       float d[8], ov[8], r[8];
       load8(dy + off, d);
@@ -285,9 +304,16 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
       }
       store8(d_o + off, r);
     }
-    float* dm = dmod + static_cast<int64_t>(b) * 3 * width + 2 * width;
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dm[c + i] += acc[i];
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    dmod[static_cast<int64_t>(b) * 3 * width + 2 * width + cc] += t;
   }
 }
 
@@ -300,6 +326,9 @@ void layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* 
 
 void layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd,
                    const bf16* dres, bf16* dx, float* dw32, float* db32, int rows, int width, cudaStream_t st) {
+  if (dw32 != nullptr && db32 != nullptr &&
+      layernorm_bwd_fused(dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width, st))
+    return;
   launch_pdl(layernorm_bwd_dx_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, dy, x, w, mean, rstd, dres, dx, rows, width); count_launch();
   launch_pdl(norm_bwd_dwdb_k<true>, dim3(ceil_div(rows, SLAB)), dim3(256), 0, st, dy, x, mean, rstd, dw32, db32, rows, width); count_launch();
 }
@@ -314,17 +343,18 @@ void rmsnorm_bwd(const bf16* dy, const bf16* x, const float* w, const float* mod
                  const float* rstd, const bf16* dres, bf16* dx, float* dw32, float* dmod, int rows, int width,
                  cudaStream_t st) {
   const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
+  if (mod == nullptr && dw32 != nullptr && rmsnorm_bwd_fused(dy, x, w, rstd, dres, dx, dw32, rows, width, st)) return;
   launch_pdl(rmsnorm_bwd_dx_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, dy, x, w, mod, rpb, rstd, dres, dx, rows, width); count_launch();
   if (mod == nullptr) {
     launch_pdl(norm_bwd_dwdb_k<false>, dim3(ceil_div(rows, SLAB)), dim3(256), 0, st, dy, x, nullptr, rstd, dw32, nullptr, rows, width); count_launch();
   } else {
-    launch_pdl(adarms_bwd_dmod_k, dim3(rows / rpb), dim3(256), 0, st, dy, x, rstd, rpb, dmod, width); count_launch();
+    launch_pdl(adarms_bwd_dmod_k, dim3(ceil_div(width, 256), rows / rpb), dim3(256), 0, st, dy, x, rstd, rpb, dmod, width); count_launch();
   }
 }
 
 void gated_residual_bwd(const bf16* dy, const bf16* o, const bf16* gate, int rows_per_batch, bf16* d_o, float* dmod,
                         int rows, int width, cudaStream_t st) {
-  launch_pdl(gated_residual_bwd_k, dim3(rows / rows_per_batch), dim3(256), 0, st, dy, o, gate, rows_per_batch, d_o, dmod, width); count_launch();
+  launch_pdl(gated_residual_bwd_k, dim3(ceil_div(width, 256), rows / rows_per_batch), dim3(256), 0, st, dy, o, gate, rows_per_batch, d_o, dmod, width); count_launch();
 }
 
 }  // namespace pi05
