@@ -381,9 +381,11 @@ def main():
         # low-overhead per-kernel breakdown of ONE step (CUPTI via torch.profiler): where the non-GEMM time goes
         from torch.profiler import ProfilerActivity, profile
 
+        lib.pi05_debug_set_pdl(0)  # a PDL-staged kernel's duration would include the wait for its predecessor
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(False)
             torch.cuda.synchronize()
+        lib.pi05_debug_set_pdl(1)
         agg = {}
         for ev in prof.events():
             if ev.device_type is not None and str(ev.device_type).endswith("CUDA"):

@@ -118,6 +118,9 @@ int pi05_get_tap(pi05_engine* e, const char* name, void* dst, int64_t* numel, in
 /* Profiling hook (ncu --profile-from-start off): bracket joint layer `layer` (and ViT layer `layer` when it exists)
  * of every following forward / backward with cudaProfilerStart/Stop; layer < 0 disables.  Instrumentation only. */
 int pi05_debug_profile_layer(pi05_engine* e, int layer);
+/* Programmatic dependent launch on (1, default; PI05_PDL=0 in the environment also disables) / off (0) for all
+ * following launches of the library.  Per-kernel timings from profilers are only meaningful with it off. */
+int pi05_debug_set_pdl(int enabled);
 
 /* ---- stand-alone operator: observation preprocessing of ONE image key on the device --------------------------
  * Replaces the per-image body of preprocess_observation_pytorch (src/openpi/models_pytorch/preprocessing_pytorch.py:

@@ -126,6 +126,7 @@ EXPORTS = (
     "pi05_preprocess_scratch_floats",
     "pi05_preprocess_image",
     "pi05_debug_profile_layer",
+    "pi05_debug_set_pdl",
     "pi05_gemm_bf16",
     "pi05_fused_clip_adamw",
     "pi05_launch_count",

@@ -6,6 +6,7 @@
 #include "../../include/pi05.h"
 #include "engine.h"
 #include "errors.h"
+#include "launch.h"
 
 using pi05::Engine;
 
@@ -180,6 +181,11 @@ int pi05_forward_value(pi05_engine* pe, const pi05_batch* b, const float* noise,
     return 1;
   }
   return pi05::engine_value(*E(pe), b, noise, time, value_out, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_debug_set_pdl(int enabled) {
+  pi05::pdl_state() = enabled ? 1 : 0;
+  return 0;
 }
 
 int pi05_debug_profile_layer(pi05_engine* pe, int layer) {

@@ -12,12 +12,16 @@
 
 namespace pi05 {
 
+// -1: not decided yet (read PI05_PDL on first use); 0 / 1: forced (pi05_debug_set_pdl, used by profiling runs because a
+// staged kernel's measured duration includes the time it waits for its predecessor)
+int& pdl_state();
 inline bool pdl_enabled() {
-  static const bool on = [] {
+  int& s = pdl_state();
+  if (s < 0) {
     const char* v = getenv("PI05_PDL");
-    return !(v != nullptr && v[0] == '0');
-  }();
-  return on;
+    s = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return s != 0;
 }
 
 template <class... P, class... A>

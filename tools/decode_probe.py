@@ -42,6 +42,11 @@ def main():
     print(f"host enqueue time {1e3 * (t1 - t0):.2f} ms")
     from torch.profiler import ProfilerActivity, profile
 
+    from kai0_b200 import _lib
+
+    _lib.lib().pi05_debug_set_pdl(0)  # per-kernel times are only meaningful without PDL staging
+    model._graphs = {}  # re-capture without programmatic edges
+    model.sample_actions("cuda", obs, noise=noise)
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         model.sample_actions("cuda", obs, noise=noise)
         torch.cuda.synchronize()
