@@ -80,7 +80,11 @@ static int prefix_layer(Engine& e, int l, int B, bool kv_only) {
 }
 
 // Expert-only layer reading the cache: K,V = cat(cache, new) (modeling_gemma.py:308-310).
-static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const float* mod_post, int rpb) {
+// The adaptive norms are fused behind the split-K finish of the GEMM that produces their input (gemm.h norm_*):
+// this layer's post-attention norm rides on o_proj, and the NEXT consumer's norm (layer l+1's input norm, or the final
+// norm after the last layer) rides on down_proj.  Only layer 0 runs its input norm as a separate kernel.
+static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const float* mod_post, int rpb,
+                        bool input_norm_done, const float* next_mod, bf16* next_out, bf16* next_gate) {
   cudaStream_t st = e.stream;
   const pi05_config& c = e.cfg;
   const int P = e.P, A = e.A, S = e.S, E = e.E, H = e.H, hd = e.hd;
@@ -88,7 +92,7 @@ static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const floa
   GemmaLayerA& p2 = e.a2[l];
   const GemmaLayerP& w2 = e.ex[l];
   bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
-  rmsnorm_fwd(p2.x_in, nullptr, mod_in, rpb, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
+  if (!input_norm_done) rmsnorm_fwd(p2.x_in, nullptr, mod_in, rpb, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
   CHECK_RC(engine_gemm(e, mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE)));
   rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
   {
@@ -117,9 +121,12 @@ static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const floa
     g.gate = p2.gate1;
     g.gate_rows = rpb;
     g.ldgate = E;
+    g.norm_mod = mod_post;  // post-attention adaRMS norm of x_mid -> n2, gate2
+    g.norm_rows_per_batch = rpb;
+    g.norm_out = p2.n2;
+    g.norm_gate_out = p2.gate2;
     CHECK_RC(engine_gemm(e, g));
   }
-  rmsnorm_fwd(p2.x_mid, nullptr, mod_post, rpb, p2.n2, p2.rstd2, p2.gate2, M2, E, 1e-6f, st);
   {
     GemmArgs g = mk_gemm(M2, c.expert.mlp_dim, E, p2.n2, E, w2.gate_w.data, E, p2.GU, 2 * c.expert.mlp_dim, EPI_GEGLU);
     g.D2 = p2.Hh;
@@ -134,6 +141,10 @@ static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const floa
     g.gate = p2.gate2;
     g.gate_rows = rpb;
     g.ldgate = E;
+    g.norm_mod = next_mod;  // the next consumer's adaRMS norm of x_out
+    g.norm_rows_per_batch = rpb;
+    g.norm_out = next_out;
+    g.norm_gate_out = next_gate;
     CHECK_RC(engine_gemm(e, g));
   }
   return 0;
@@ -207,9 +218,14 @@ int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_
     // embed_suffix (pi05): action_in_proj of the current x_t, cast to bf16 (pi0_pytorch.py:270-273,332-337)
     linear_f32(actions_out, e.ain_w.d<float>(), e.ain_b.d<float>(), e.aemb32, M2, E, ad, st);
     cast_f32_to_bf16(e.aemb32, e.a2[0].x_in, static_cast<int64_t>(M2) * E, st);
-    for (int l = 0; l < depth; ++l) CHECK_RC(suffix_layer(e, l, B, mod_at(2 * l, step), mod_at(2 * l + 1, step), M2));
-    const bf16* x2f = depth > 0 ? e.a2[depth - 1].x_out : e.a2[0].x_in;
-    rmsnorm_fwd(x2f, nullptr, mod_at(2 * depth, step), M2, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
+    for (int l = 0; l < depth; ++l) {
+      const bool last = l == depth - 1;
+      CHECK_RC(suffix_layer(e, l, B, mod_at(2 * l, step), mod_at(2 * l + 1, step), M2, /*input_norm_done=*/l > 0,
+                            mod_at(last ? 2 * depth : 2 * (l + 1), step), last ? e.suffix_out : e.a2[l + 1].n1,
+                            last ? nullptr : e.a2[l + 1].gate1));
+    }
+    if (depth == 0)
+      rmsnorm_fwd(e.a2[0].x_in, nullptr, mod_at(0, step), M2, e.suffix_out, e.rstd_f2, nullptr, M2, E, 1e-6f, st);
     cast_bf16_to_f32(e.suffix_out, e.so32, static_cast<int64_t>(M2) * E, st);
     linear_f32(e.so32, e.aout_w.d<float>(), e.aout_b.d<float>(), e.v_t, M2, ad, E, st);
     if (e.taps_enabled && step == 0) {  // keep a copy: v_t is overwritten by the following steps (u_t is free in decode)

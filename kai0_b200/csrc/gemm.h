@@ -56,6 +56,13 @@ struct GemmArgs {
   float* splitk_ws = nullptr;
   size_t splitk_ws_bytes = 0;
   int block_n = 0;     // 0 = auto (256 when N >= 256 else 128)
+  // Optional (EPI_RES, decode): the adaptive RMSNorm that consumes D (modeling_gemma.py:84-104) fused behind the
+  // epilogue.  norm_mod: fp32 [*, 3*N] = [scale | shift | gate] rows, one per norm_rows_per_batch output rows;
+  // norm_out = bf16 [M, N]; norm_gate_out (optional) = bf16 gate per batch row.  Same arithmetic as rmsnorm_fwd.
+  const float* norm_mod = nullptr;
+  int norm_rows_per_batch = 0;
+  void* norm_out = nullptr;
+  void* norm_gate_out = nullptr;
 };
 
 // Enqueue on `stream`.  Returns 0 on success; on failure returns non-zero and fills `err` (if given).

@@ -22,6 +22,7 @@
 #include "gemm.h"
 #include "gemm_device.cuh"
 #include "gemm_host.h"
+#include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
 
@@ -375,6 +376,99 @@ __global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__
     D[m * ldd + n] = __float2bfloat16_rn(acc);
   }
 }
+// Decode: split-K finish + EPI_RES epilogue + the adaptive RMSNorm of the result in ONE kernel (one warp per row, the
+// row stays in registers between the residual add and the normalisation).  Replaces splitk_finish_k + rmsnorm_fwd_k.
+template <int CH>
+__global__ void __launch_bounds__(256) splitk_finish_norm_k(const float* __restrict__ ws, int splits, int M, int N,
+                                                            __nv_bfloat16* __restrict__ D, long long ldd,
+                                                            const __nv_bfloat16* __restrict__ res, long long ldres,
+                                                            const __nv_bfloat16* __restrict__ gate, int gate_rows,
+                                                            long long ldgate, const float* __restrict__ mod,
+                                                            int norm_rpb, __nv_bfloat16* __restrict__ y,
+                                                            __nv_bfloat16* __restrict__ gate_out) {
+  pdl_enter();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long total = static_cast<long long>(M) * N;
+  float v[CH][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < N) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int z = 0; z < splits; ++z) {
+        const float4* p = reinterpret_cast<const float4*>(ws + z * total + static_cast<long long>(row) * N + c);
+        const float4 a = p[0], b = p[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+      const uint4 rv = *reinterpret_cast<const uint4*>(res + row * ldres + c);
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      float g[8];
+      if (gate) {
+        const uint4 gv = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(row / gate_rows) * ldgate + c);
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          g[2 * j] = __uint_as_float(gw[j] << 16);
+          g[2 * j + 1] = __uint_as_float(gw[j] & 0xFFFF0000u);
+        }
+      }
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * j + h;
+          float t = bf16_round(acc[i]);
+          if (gate) t = bf16_round(t * g[i]);
+          const float r = h == 0 ? __uint_as_float(rw[j] << 16) : __uint_as_float(rw[j] & 0xFFFF0000u);
+          o2[h] = bf16_round(t + r);  // the bf16 value the next layer sees
+          v[k][i] = o2[h];
+          ss += o2[h] * o2[h];
+        }
+        __nv_bfloat162 pk = __floats2bfloat162_rn(o2[0], o2[1]);
+        ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(D + row * ldd + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / N + 1e-6f);  // modeling_gemma.py:68-70
+  const int b = row / norm_rpb;
+  const float* m = mod + static_cast<long long>(b) * 3 * N;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < N) {
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 sc = *reinterpret_cast<const float2*>(m + c + 2 * j);
+        const float2 sh = *reinterpret_cast<const float2*>(m + N + c + 2 * j);
+        const float a0 = __fadd_rn(__fmul_rn(__fmul_rn(v[k][2 * j], rstd), __fadd_rn(1.0f, sc.x)), sh.x);  // :102
+        const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(v[k][2 * j + 1], rstd), __fadd_rn(1.0f, sc.y)), sh.y);
+        __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
+        ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(y + static_cast<long long>(row) * N + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (gate_out != nullptr && (row % norm_rpb) == 0) {
+        uint32_t gw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 gg = *reinterpret_cast<const float2*>(m + 2 * N + c + 2 * j);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(gg.x, gg.y);
+          gw[j] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(gate_out + static_cast<long long>(b) * N + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+      }
+    }
+  }
+}
+
 // STORE-only finish of the wave-quantisation path: 4 outputs per thread, 16-byte partial loads, fixed summation order.
 __global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restrict__ ws, int splits, long long total4,
                                                            int n4, __nv_bfloat16* __restrict__ D, long long ldd) {
@@ -401,7 +495,20 @@ __global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restri
 }
 }  // namespace
 
+static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int err_len, bool* norm_done);
+
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
+  bool norm_done = false;
+  const int rc = gemm_bf16_impl(a, stream, err, err_len, &norm_done);
+  if (rc == 0 && a.norm_mod != nullptr && !norm_done) {
+    // the fused finish+norm kernel was not applicable: plain kernel, same arithmetic
+    rmsnorm_fwd(static_cast<const bf16*>(a.D), nullptr, a.norm_mod, a.norm_rows_per_batch, static_cast<bf16*>(a.norm_out),
+                nullptr, static_cast<bf16*>(a.norm_gate_out), a.M, a.N, 1e-6f, stream);
+  }
+  return rc;
+}
+
+static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int err_len, bool* norm_done) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) {
     if (err) snprintf(err, err_len, "gemm: empty problem M=%d N=%d K=%d batch=%d", a.M, a.N, a.K, a.batch);
     return 1;
@@ -431,10 +538,32 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
       part.res = nullptr;
       part.gate = nullptr;
       part.D2 = nullptr;
+      part.norm_mod = nullptr;
       int rc = gemm_bf16(part, stream, err, err_len);
       if (rc != 0) return rc;
       const long long total = static_cast<long long>(a.M) * a.N;
       const int grid = static_cast<int>((total + 255) / 256);
+      const bool fuse_norm = a.norm_mod != nullptr && a.epilogue == EPI_RES && a.bias == nullptr && a.D2 == nullptr &&
+                             a.N % 8 == 0 && a.N <= 1024 && a.ldd % 8 == 0 && a.ldres % 8 == 0 &&
+                             (a.gate == nullptr || a.ldgate % 8 == 0);
+      if (fuse_norm) {
+        const int ch = (a.N + 255) / 256;
+        const dim3 g2((a.M + 7) / 8);
+#define PI05_FN(C)                                                                                                     \
+  launch_pdl(splitk_finish_norm_k<C>, g2, dim3(256), 0, stream, a.splitk_ws, s, a.M, a.N,                             \
+             static_cast<__nv_bfloat16*>(a.D), a.ldd, static_cast<const __nv_bfloat16*>(a.res), a.ldres,             \
+             static_cast<const __nv_bfloat16*>(a.gate), a.gate_rows > 0 ? a.gate_rows : 1, a.ldgate, a.norm_mod,    \
+             a.norm_rows_per_batch > 0 ? a.norm_rows_per_batch : a.M, static_cast<__nv_bfloat16*>(a.norm_out),       \
+             static_cast<__nv_bfloat16*>(a.norm_gate_out))
+        if (ch == 1) PI05_FN(1);
+        else if (ch == 2) PI05_FN(2);
+        else if (ch == 3) PI05_FN(3);
+        else PI05_FN(4);
+#undef PI05_FN
+        count_launch();
+        *norm_done = true;
+        return 0;
+      }
       launch_pdl(splitk_finish_k, dim3(grid), dim3(256), 0, stream, a.splitk_ws, s, a.M, a.N, a.epilogue, static_cast<__nv_bfloat16*>(a.D), a.ldd,
                                                 static_cast<__nv_bfloat16*>(a.D2), a.ldd2,
                                                 static_cast<const __nv_bfloat16*>(a.bias),
@@ -512,6 +641,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
       part.ldd = a.N;
       part.d_batch_stride = static_cast<int64_t>(a.M) * a.N;
       part.block_n = bn;
+      part.norm_mod = nullptr;
       int rc = gemm_bf16(part, stream, err, err_len);
       if (rc != 0) return rc;
       const long long total = static_cast<long long>(a.M) * a.N;
