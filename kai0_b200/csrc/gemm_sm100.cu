@@ -379,92 +379,107 @@ __global__ void __launch_bounds__(256) splitk_finish_k(const float* __restrict__
 // Decode: split-K finish + EPI_RES epilogue + the adaptive RMSNorm of the result in ONE kernel (one warp per row, the
 // row stays in registers between the residual add and the normalisation).  Replaces splitk_finish_k + rmsnorm_fwd_k.
 template <int CH>
-__global__ void __launch_bounds__(256) splitk_finish_norm_k(const float* __restrict__ ws, int splits, int M, int N,
-                                                            __nv_bfloat16* __restrict__ D, long long ldd,
-                                                            const __nv_bfloat16* __restrict__ res, long long ldres,
-                                                            const __nv_bfloat16* __restrict__ gate, int gate_rows,
-                                                            long long ldgate, const float* __restrict__ mod,
-                                                            int norm_rpb, __nv_bfloat16* __restrict__ y,
-                                                            __nv_bfloat16* __restrict__ gate_out) {
+__global__ void __launch_bounds__(CH * 32) splitk_finish_norm_k(const float* __restrict__ ws, int splits, int M, int N,
+                                                                __nv_bfloat16* __restrict__ D, long long ldd,
+                                                                const __nv_bfloat16* __restrict__ res, long long ldres,
+                                                                const __nv_bfloat16* __restrict__ gate, int gate_rows,
+                                                                long long ldgate, const float* __restrict__ mod,
+                                                                int norm_rpb, __nv_bfloat16* __restrict__ y,
+                                                                __nv_bfloat16* __restrict__ gate_out) {
+  // one block per output row, warp k owns columns [256k, 256k + 256): every load of the row is in flight at once
   pdl_enter();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
+  __shared__ float ssum[CH];
+  const int row = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(M) * N;
-  float v[CH][8];
+  const int c = lane * 8 + k * 256;
+  const bool live = c < N;
+  float v[8];
   float ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    const int c = lane * 8 + k * 256;
-    if (c < N) {
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int z = 0; z < splits; ++z) {
-        const float4* p = reinterpret_cast<const float4*>(ws + z * total + static_cast<long long>(row) * N + c);
-        const float4 a = p[0], b = p[1];
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-      }
-      const uint4 rv = *reinterpret_cast<const uint4*>(res + row * ldres + c);
-      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-      float g[8];
-      if (gate) {
-        const uint4 gv = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(row / gate_rows) * ldgate + c);
-        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          g[2 * j] = __uint_as_float(gw[j] << 16);
-          g[2 * j + 1] = __uint_as_float(gw[j] & 0xFFFF0000u);
-        }
-      }
-      uint32_t ow[4];
+  const int b = row / norm_rpb;
+  const float* m = mod + static_cast<long long>(b) * 3 * N;
+  float sc[8], sh[8];
+  if (live) {
+    // issue the (independent) modulation / residual / gate loads before the partial-sum chain
+    {
+      const float4 s0 = *reinterpret_cast<const float4*>(m + c), s1 = *reinterpret_cast<const float4*>(m + c + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(m + N + c), h1 = *reinterpret_cast<const float4*>(m + N + c + 4);
+      sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+      sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+    }
+    const uint4 rv = *reinterpret_cast<const uint4*>(res + row * ldres + c);
+    uint4 gv = make_uint4(0, 0, 0, 0);
+    if (gate) gv = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(row / gate_rows) * ldgate + c);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float* p0 = ws + static_cast<long long>(row) * N + c;
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {  // four splits (8 x 16-byte loads) in flight per step, summed in z order
+      float4 a[4], bq[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float o2[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int i = 2 * j + h;
-          float t = bf16_round(acc[i]);
-          if (gate) t = bf16_round(t * g[i]);
-          const float r = h == 0 ? __uint_as_float(rw[j] << 16) : __uint_as_float(rw[j] & 0xFFFF0000u);
-          o2[h] = bf16_round(t + r);  // the bf16 value the next layer sees
-          v[k][i] = o2[h];
-          ss += o2[h] * o2[h];
-        }
-        __nv_bfloat162 pk = __floats2bfloat162_rn(o2[0], o2[1]);
-        ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+        const float4* p = reinterpret_cast<const float4*>(p0 + (z + j) * total);
+        a[j] = p[0];
+        bq[j] = p[1];
       }
-      *reinterpret_cast<uint4*>(D + row * ldd + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[0] += a[j].x; acc[1] += a[j].y; acc[2] += a[j].z; acc[3] += a[j].w;
+        acc[4] += bq[j].x; acc[5] += bq[j].y; acc[6] += bq[j].z; acc[7] += bq[j].w;
+      }
     }
+    for (; z < splits; ++z) {
+      const float4* p = reinterpret_cast<const float4*>(p0 + z * total);
+      const float4 a = p[0], bq = p[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += bq.x; acc[5] += bq.y; acc[6] += bq.z; acc[7] += bq.w;
+    }
+    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * j + h;
+        float t = bf16_round(acc[i]);
+        if (gate) t = bf16_round(t * (h == 0 ? __uint_as_float(gw[j] << 16) : __uint_as_float(gw[j] & 0xFFFF0000u)));
+        const float r = h == 0 ? __uint_as_float(rw[j] << 16) : __uint_as_float(rw[j] & 0xFFFF0000u);
+        o2[h] = bf16_round(t + r);  // the bf16 value the next layer sees
+        v[i] = o2[h];
+        ss += o2[h] * o2[h];
+      }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(o2[0], o2[1]);
+      ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    *reinterpret_cast<uint4*>(D + row * ldd + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / N + 1e-6f);  // modeling_gemma.py:68-70
-  const int b = row / norm_rpb;
-  const float* m = mod + static_cast<long long>(b) * 3 * N;
+  if (lane == 0) ssum[k] = ss;
+  __syncthreads();
+  float tot = 0.f;
 #pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    const int c = lane * 8 + k * 256;
-    if (c < N) {
-      uint32_t ow[4];
+  for (int j = 0; j < CH; ++j) tot += ssum[j];
+  const float rstd = rsqrtf(tot / N + 1e-6f);  // modeling_gemma.py:68-70
+  if (live) {
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = __fadd_rn(__fmul_rn(__fmul_rn(v[2 * j], rstd), __fadd_rn(1.0f, sc[2 * j])), sh[2 * j]);  // :102
+      const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(v[2 * j + 1], rstd), __fadd_rn(1.0f, sc[2 * j + 1])), sh[2 * j + 1]);
+      __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
+      ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    *reinterpret_cast<uint4*>(y + static_cast<long long>(row) * N + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (gate_out != nullptr && (row % norm_rpb) == 0) {
+      uint32_t gw2[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 sc = *reinterpret_cast<const float2*>(m + c + 2 * j);
-        const float2 sh = *reinterpret_cast<const float2*>(m + N + c + 2 * j);
-        const float a0 = __fadd_rn(__fmul_rn(__fmul_rn(v[k][2 * j], rstd), __fadd_rn(1.0f, sc.x)), sh.x);  // :102
-        const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(v[k][2 * j + 1], rstd), __fadd_rn(1.0f, sc.y)), sh.y);
-        __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
-        ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+        const float2 gg = *reinterpret_cast<const float2*>(m + 2 * N + c + 2 * j);
+        __nv_bfloat162 pk = __floats2bfloat162_rn(gg.x, gg.y);
+        gw2[j] = *reinterpret_cast<uint32_t*>(&pk);
       }
-      *reinterpret_cast<uint4*>(y + static_cast<long long>(row) * N + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      if (gate_out != nullptr && (row % norm_rpb) == 0) {
-        uint32_t gw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 gg = *reinterpret_cast<const float2*>(m + 2 * N + c + 2 * j);
-          __nv_bfloat162 pk = __floats2bfloat162_rn(gg.x, gg.y);
-          gw[j] = *reinterpret_cast<uint32_t*>(&pk);
-        }
-        *reinterpret_cast<uint4*>(gate_out + static_cast<long long>(b) * N + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
-      }
+      *reinterpret_cast<uint4*>(gate_out + static_cast<long long>(b) * N + c) = make_uint4(gw2[0], gw2[1], gw2[2], gw2[3]);
     }
   }
 }
@@ -548,9 +563,9 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
                              (a.gate == nullptr || a.ldgate % 8 == 0);
       if (fuse_norm) {
         const int ch = (a.N + 255) / 256;
-        const dim3 g2((a.M + 7) / 8);
+        const dim3 g2(a.M);
 #define PI05_FN(C)                                                                                                     \
-  launch_pdl(splitk_finish_norm_k<C>, g2, dim3(256), 0, stream, a.splitk_ws, s, a.M, a.N,                             \
+  launch_pdl(splitk_finish_norm_k<C>, g2, dim3(C * 32), 0, stream, a.splitk_ws, s, a.M, a.N,                             \
              static_cast<__nv_bfloat16*>(a.D), a.ldd, static_cast<const __nv_bfloat16*>(a.res), a.ldres,             \
              static_cast<const __nv_bfloat16*>(a.gate), a.gate_rows > 0 ? a.gate_rows : 1, a.ldgate, a.norm_mod,    \
              a.norm_rows_per_batch > 0 ? a.norm_rows_per_batch : a.M, static_cast<__nv_bfloat16*>(a.norm_out),       \

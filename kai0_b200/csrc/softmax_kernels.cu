@@ -44,13 +44,20 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[i][e] = (j0 + e < n_keys) ? __bfloat162float(sr[j0 + e]) : 0.f;
       }
+      // the 8 pad flags of this chunk in one 8-byte load when the chunk lies inside the (8-aligned) prefix
+      uint64_t flags = ~0ull;
+      const bool vec_ok = padb != nullptr && j0 + 8 <= n_prefix && ((reinterpret_cast<uintptr_t>(padb) + j0) & 7) == 0;
+      if (vec_ok) flags = *reinterpret_cast<const uint64_t*>(padb + j0);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = j0 + e;
         if (j >= n_keys) {
           v[i][e] = -CUDART_INF_F;  // pitch padding: excluded from max / sum
         } else {
-          const bool valid = !qmasked && (j >= n_prefix || padb == nullptr || padb[j] != 0);
+          bool ok;
+          if (vec_ok) ok = ((flags >> (8 * e)) & 0xFFull) != 0;
+          else ok = (j >= n_prefix || padb == nullptr || padb[j] != 0);
+          const bool valid = !qmasked && ok;
           if (!valid) v[i][e] += kMaskValue;
           mx = fmaxf(mx, v[i][e]);
         }
