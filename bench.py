@@ -156,14 +156,34 @@ def to_device(d, actions, dev):
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference, timed on the host cores (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------------------
+# forward TFLOP per sample of the pieces of the path, used to scale the bounded CPU sample
+_TF_VIT_LAYER = 0.6605 / 27          # all three cameras, one SigLIP layer
+_TF_JOINT_LAYER = (3.8368 + 0.0311 + 0.1457) / 18   # one joint PaliGemma + expert layer incl. attention
+_TF_REST = 0.0003 + 3 * 0.0012       # adaRMS / heads / projector (not depth-scaled)
+
+
 def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
-    """Times forward + backward (torch.autograd through the oracle) of ONE sample per step on all host threads.
+    """Times the oracle port of the reference on all host threads on a BOUNDED sample of the workload: forward +
+    backward (torch.autograd) of ONE sample through the full-width architecture truncated to 1 of 27 SigLIP layers and
+    1 of 18 joint Gemma layers (same tensor shapes, same kernels per layer), scaled to a whole sample by the FLOP
+    ratio of SURVEY.md §8d.  A whole sample is ~14 TFLOP and takes minutes per pass on host cores.
     Returns (samples_per_sec, cores, sample_description, steps_done)."""
+    import dataclasses
+
     from oracle import pi05_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    oc = O.OracleConfig() if full else O.tiny_config()
+    if full:
+        base_cfg = O.OracleConfig()
+        dv, dg = 1, 1
+        oc = dataclasses.replace(base_cfg, vit_depth=dv,
+                                 paligemma=dataclasses.replace(base_cfg.paligemma, depth=dg),
+                                 expert=dataclasses.replace(base_cfg.expert, depth=dg))
+        frac = (dv * _TF_VIT_LAYER + dg * _TF_JOINT_LAYER + _TF_REST) / FWD_TFLOP_PER_SAMPLE
+    else:
+        oc = O.tiny_config()
+        frac = 1.0
     params = {}
     # values do not matter for timing: tile a 4M-element N(0, 0.02) pattern (bf16 normal_ on CPU is very slow)
     base = {torch.bfloat16: (torch.randn(1 << 22) * 0.02).to(torch.bfloat16), torch.float32: torch.randn(1 << 22) * 0.02}
@@ -183,7 +203,7 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
         loss.mean().backward()
 
     t0 = time.time()
-    one()  # first step doubles as the cost probe
+    one()  # first pass doubles as warm-up and cost probe
     t_first = time.time() - t0
     done_warm = 1
     while done_warm < warmup and (time.time() - t0) + t_first * (1 + steps) < budget_s:
@@ -193,10 +213,12 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
     t1 = time.time()
     for _ in range(k):
         one()
-    dt = time.time() - t1
-    desc = (f"B=1 forward+backward of the full pi0.5 oracle per step (14.0 TFLOP), {k} timed step(s) after {done_warm} "
-            f"warm-up, {cores} threads, bf16 weights as the reference")
-    return k / dt, cores, desc, k
+    dt = (time.time() - t1) / k
+    desc = (f"B=1 forward+backward of the oracle port, full widths, truncated to {oc.vit_depth}/27 SigLIP and "
+            f"{oc.paligemma.depth}/18 joint Gemma layers ({100 * frac:.1f} % of a sample's FLOPs: {dt:.1f} s per pass), "
+            f"scaled to a whole sample by that ratio; {k} timed pass(es) after {done_warm} warm-up, {cores} threads, "
+            "bf16 weights as the reference") if full else f"tiny debug architecture, {k} passes"
+    return frac / dt, cores, desc, k
 
 
 # ------------------------------------------------------------------------------------------------------------
