@@ -162,6 +162,26 @@ _TF_JOINT_LAYER = (3.8368 + 0.0311 + 0.1457) / 18   # one joint PaliGemma + expe
 _TF_REST = 0.0003 + 3 * 0.0012       # adaRMS / heads / projector (not depth-scaled)
 
 
+def _pick_cpu_threads() -> int:
+    """All the host threads the port can USE: torch's bf16 CPU GEMM gets slower when oversubscribed on many-thread hosts
+    (128 threads: 3.5x slower than 8 on the same pass), so a ~1 s probe picks the fastest of a few thread counts."""
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    a = (torch.randn(968, 2048) * 0.1).to(torch.bfloat16)
+    w = (torch.randn(4096, 2048) * 0.02).to(torch.bfloat16)
+    best, best_t = n, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(a, w)
+        t0 = time.time()
+        for _ in range(3):
+            torch.nn.functional.linear(a, w)
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
     """Times the oracle port of the reference on all host threads on a BOUNDED sample of the workload: forward +
     backward (torch.autograd) of ONE sample through the full-width architecture truncated to 1 of 27 SigLIP layers and
@@ -172,7 +192,7 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
 
     from oracle import pi05_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = _pick_cpu_threads()
     torch.set_num_threads(cores)
     if full:
         base_cfg = O.OracleConfig()
