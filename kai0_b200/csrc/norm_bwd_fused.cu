@@ -1,9 +1,9 @@
 // Fused LayerNorm / plain-RMSNorm backward: dx AND the weight (bias) gradient from ONE read of dy and x.
 // The two-kernel version (norm_kernels.cu: *_bwd_dx_k + norm_bwd_dwdb_k) reads dy and x twice and its column-sum kernel
-// ran at 9-19 % of the HBM peak (profiles/r01_ncu_layer.md).  Here a persistent block of 16 warps walks 16-row slabs:
+// ran at 9-19 % of the HBM peak (profiles/r01_ncu_layer.md).  Here persistent blocks of 8 warps walk 8-row slabs:
 //   phase A: warp w owns row w of the slab — loads dy / x (all 16-byte loads of the row in flight), keeps the packed
 //            values in registers for the statistics and the dx pass, and parks a bf16 copy of both in shared memory;
-//   phase B: thread t owns columns t, t+512, ... and adds the slab's 16 rows from shared memory into its dw (db)
+//   phase B: thread t owns columns t, t+256, ... and adds the slab's 8 rows from shared memory into its dw (db)
 //            accumulators, which live in registers for the whole kernel;
 // one atomicAdd per column per block at the end.  Arithmetic per element is identical to the two-kernel version.
 #include "common.cuh"
@@ -14,8 +14,8 @@
 namespace pi05 {
 namespace {
 
-constexpr int NW = 16;    // warps per block = rows per slab
-constexpr int MAXC = 4;   // columns per thread in phase B (width <= 512 * MAXC)
+constexpr int NW = 8;     // warps per block = rows per slab (three blocks per SM run out of phase: A overlaps B)
+constexpr int MAXC = 8;   // columns per thread in phase B (width <= 256 * MAXC)
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -29,7 +29,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // LN = true : y = (x - mean) * rstd * w + b   (w bf16; dw, db)
 // LN = false: y = x * rstd * (1 + w)          (w fp32; dw)
 template <bool LN, int CH>
-__global__ void __launch_bounds__(NW * 32) norm_bwd_slab_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(NW * 32, 3) norm_bwd_slab_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const void* __restrict__ w_, const float* __restrict__ mean_i,
                                                            const float* __restrict__ rstd_i,
                                                            const bf16* __restrict__ dres, bf16* __restrict__ dx,
@@ -162,7 +162,8 @@ bool launch_fused(const bf16* dy, const bf16* x, const void* w, const float* mea
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int nslab = (rows + NW - 1) / NW;
-  const int grid = nslab < sms ? nslab : sms;
+  const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+  const int grid = nslab < per_sm * sms ? nslab : per_sm * sms;
 #define PI05_NORM_CASE(C)                                                                                              \
   case C: {                                                                                                            \
     static bool attr_set = false;                                                                                      \
