@@ -14,8 +14,8 @@
 namespace pi05 {
 namespace {
 
-constexpr int NW = 8;     // warps per block = rows per slab (three blocks per SM run out of phase: A overlaps B)
-constexpr int MAXC = 8;   // columns per thread in phase B (width <= 256 * MAXC)
+// NW = warps per block = rows per slab.  Measured (B=32 bench shapes): width 2048 is fastest with one 16-warp block per
+// SM (128 KB of shared memory), width 1152 with three 8-warp blocks per SM running out of phase (A overlaps B).
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -28,8 +28,8 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 
 // LN = true : y = (x - mean) * rstd * w + b   (w bf16; dw, db)
 // LN = false: y = x * rstd * (1 + w)          (w fp32; dw)
-template <bool LN, int CH>
-__global__ void __launch_bounds__(NW * 32, 3) norm_bwd_slab_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+template <bool LN, int CH, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 1) norm_bwd_slab_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const void* __restrict__ w_, const float* __restrict__ mean_i,
                                                            const float* __restrict__ rstd_i,
                                                            const bf16* __restrict__ dres, bf16* __restrict__ dx,
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(NW * 32, 3) norm_bwd_slab_k(const bf16* __rest
   bf16* xS = dyS + static_cast<size_t>(NW) * width;            // [NW][width]
   __shared__ float meanS[NW], rstdS[NW];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MAXC = 2048 / (NW * 32);  // columns per thread in phase B (width <= 2048)
   float aw[MAXC], ab[MAXC];
 #pragma unroll
   for (int j = 0; j < MAXC; ++j) aw[j] = ab[j] = 0.f;
@@ -149,40 +150,46 @@ __global__ void __launch_bounds__(NW * 32, 3) norm_bwd_slab_k(const bf16* __rest
   }
 }
 
+template <bool LN, int CH, int NW>
+void launch_slab(const bf16* dy, const bf16* x, const void* w, const float* mean, const float* rstd, const bf16* dres,
+                 bf16* dx, float* dw32, float* db32, int rows, int width, int sms, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(2) * NW * width * sizeof(bf16);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(norm_bwd_slab_k<LN, CH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NW * 256 * CH * 2);
+    attr_set = true;
+  }
+  const int nslab = (rows + NW - 1) / NW;
+  const int per_sm = NW == 8 ? (smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1)) : 1;
+  const int grid = nslab < per_sm * sms ? nslab : per_sm * sms;
+  launch_pdl(norm_bwd_slab_k<LN, CH, NW>, dim3(grid), dim3(NW * 32), smem, st, dy, x, w, mean, rstd, dres, dx, dw32, db32,
+             rows, width);
+}
+
 template <bool LN>
 bool launch_fused(const bf16* dy, const bf16* x, const void* w, const float* mean, const float* rstd, const bf16* dres,
                   bf16* dx, float* dw32, float* db32, int rows, int width, cudaStream_t st) {
   if (width % 8 != 0 || width > 2048) return false;
   const int ch = (width + 255) / 256;
-  const size_t smem = static_cast<size_t>(2) * NW * width * sizeof(bf16);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int nslab = (rows + NW - 1) / NW;
-  const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
-  const int grid = nslab < per_sm * sms ? nslab : per_sm * sms;
-#define PI05_NORM_CASE(C)                                                                                              \
-  case C: {                                                                                                            \
-    static bool attr_set = false;                                                                                      \
-    if (!attr_set) {                                                                                                   \
-      cudaFuncSetAttribute(norm_bwd_slab_k<LN, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NW * 256 * C * 2); \
-      attr_set = true;                                                                                                 \
-    }                                                                                                                  \
-    launch_pdl(norm_bwd_slab_k<LN, C>, dim3(grid), dim3(NW * 32), smem, st, dy, x, w, mean, rstd, dres, dx, dw32, db32, \
-               rows, width);                                                                                           \
-  } break;
+#define PI05_NORM_CASE(C, W)                                                                               \
+  case C:                                                                                                  \
+    launch_slab<LN, C, W>(dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width, sms, st);               \
+    break;
   switch (ch) {
-    PI05_NORM_CASE(1)
-    PI05_NORM_CASE(2)
-    PI05_NORM_CASE(3)
-    PI05_NORM_CASE(4)
-    PI05_NORM_CASE(5)
-    PI05_NORM_CASE(6)
-    PI05_NORM_CASE(7)
-    PI05_NORM_CASE(8)
+    PI05_NORM_CASE(1, 8)
+    PI05_NORM_CASE(2, 8)
+    PI05_NORM_CASE(3, 8)
+    PI05_NORM_CASE(4, 8)
+    PI05_NORM_CASE(5, 8)
+    PI05_NORM_CASE(6, 16)
+    PI05_NORM_CASE(7, 16)
+    PI05_NORM_CASE(8, 16)
     default:
       return false;
   }
