@@ -36,6 +36,17 @@ METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four dominant GEMM classes at the bench's
+# shapes, from the committed `ncu --set full` captures (profiles/r01_ncu_gemm_{geglu,dgrad,wgrad,down}.md);
+# key = (M, N, K, epilogue, majors) as printed by pi05_gemm_profile_report
+NCU_TRAFFIC_BYTES = {
+    (30976, 32768, 2048, 5, 0): 5332.3e6,   # GeGLU forward (fused gate|up weight)
+    (30976, 2048, 32768, 0, 1): 5550.0e6,   # dgrad of gate|up
+    (32768, 2048, 30976, 0, 3): 5455.0e6,   # wgrad of gate|up
+    (30976, 2048, 16384, 4, 0): 2944.2e6,   # down projection + residual
+}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -415,6 +426,8 @@ def main():
         barrier()
         if rank == 0:
             nbytes = sum(g.numel() * g.element_size() for g in model._flat_grad.values() if g is not None)
+            nbytes -= 2 * (model._flat_grad[torch.bfloat16].numel() - model._offsets[
+                "paligemma_with_expert.gemma_expert.lm_head.weight"][1])  # the unused lm_head is not exchanged
             ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
             print(f"  [allreduce] {nbytes / 1e9:.2f} GB of gradients: {ts} ms -> "
                   f"{nbytes / 1e9 / (min(ts) / 1e3):.0f} GB/s algorithmic", file=sys.stderr)
@@ -489,7 +502,9 @@ def main():
             ach = top["flop"] / (top["ms"] / 1e3) / 1e12
             roofline = {
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC_BYTES.get((top["M"], top["N"], top["K"], top["epi"], top["majors"])),
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_gemm_*.md)",
+                "algorithmic_bytes": 2.0 * (top["M"] * top["K"] + top["N"] * top["K"] + top["M"] * top["N"]) * top["batch"],
                 "kernel": f"gemm_kernel<256,{top['epi']}> M={top['M']} N={top['N']} K={top['K']} "
                           f"majors={top['majors']} ({top['launches']} launches in the timed region)",
                 "peak_source": f"{peaks_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",

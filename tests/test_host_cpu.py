@@ -174,3 +174,29 @@ def test_advantage_estimator_surface():
     obs = H.Obs(batch)
     with pytest.raises(ValueError, match="progress"):
         model(obs, batch["actions"])
+
+
+def test_every_kernel_honours_the_pdl_contract():
+    """launch.h: a kernel launched with the programmatic-stream-serialization attribute must wait for its predecessor
+    (pdl_enter / pdl_wait) before touching global memory.  Static check of the sources: every __global__ kernel body
+    contains the call, and no launch bypasses launch_pdl with a raw <<<>>>."""
+    csrc = os.path.join(ROOT, "kai0_b200", "csrc")
+    missing, raw = [], []
+    for fn in sorted(os.listdir(csrc)):
+        if not fn.endswith((".cu", ".cuh")):
+            continue
+        src = open(os.path.join(csrc, fn)).read()
+        if "<<<" in re.sub(r"//[^\n]*", "", src):
+            raw.append(fn)
+        for m in re.finditer(r"__global__[^{;]*\{", src):
+            # body = up to the matching closing brace
+            depth, i = 1, m.end()
+            while depth and i < len(src):
+                depth += {"{": 1, "}": -1}.get(src[i], 0)
+                i += 1
+            body = src[m.end():i]
+            if "pdl_enter()" not in body and "pdl_wait()" not in body:
+                name = re.findall(r"(\w+)\s*\(", m.group(0))
+                missing.append(f"{fn}:{name[-1] if name else '?'}")
+    assert not missing, missing
+    assert not raw, raw
