@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
   for (int i = 0; i < CH; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      v[i][e] = expf(v[i][e] - mx);  // exp(-inf) = 0 for the padding
+      v[i][e] = __expf(v[i][e] - mx);  // ex2.approx form (rel. error ~1e-6, far below the bf16 rounding of P); exp(-inf) = 0
       sum += v[i][e];
     }
   sum = warp_sum(sum);
