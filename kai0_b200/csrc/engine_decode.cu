@@ -93,8 +93,12 @@ static int suffix_layer(Engine& e, int l, int B, const float* mod_in, const floa
   const GemmaLayerP& w2 = e.ex[l];
   bf16 *Kc = e.Kl[l], *Vc = e.Vl[l];
   if (!input_norm_done) rmsnorm_fwd(p2.x_in, nullptr, mod_in, rpb, p2.n1, p2.rstd1, p2.gate1, M2, E, 1e-6f, st);
-  CHECK_RC(engine_gemm(e, mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE)));
-  rope_pack_fwd(p2.qkv, A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B, st);
+  {  // fused qkv projection; RoPE + the q / K-cache / V-cache split ride on its split-K finish (gemm.h GemmRope)
+    GemmArgs g = mk_gemm(M2, QW, E, p2.n1, E, w2.q_w.data, E, p2.qkv, QW, EPI_STORE);
+    const GemmRope rope{A, H, hd, e.pos, e.nvalid, 1, e.rope_cos, e.rope_sin, p2.Q, Kc, Vc, P, S, B};
+    g.rope = &rope;
+    CHECK_RC(engine_gemm(e, g));
+  }
   {
     GemmArgs g = mk_gemm(A * H, S, hd, p2.Q, hd, Kc, hd, p2.P, e.Spad, EPI_SCALE);
     g.batch = B;

@@ -24,6 +24,19 @@ enum GemmEpilogue : int {
   EPI_COUNT = 9,
 };
 
+// Optional (EPI_STORE, decode): the RoPE + q/k/v split that consumes a fused qkv projection (rope_pack_fwd in kernels.h,
+// same arguments) fused behind the split-K finish: Q / K-cache / V-cache rows are written directly, D is not.
+struct GemmRope {
+  int T, H, hd;
+  const int* pos;
+  const int* nvalid;
+  int pos_mode;
+  const void* cos_t;
+  const void* sin_t;
+  void *Q, *K, *V;
+  int key_off, kv_len, batch;
+};
+
 struct GemmArgs {
   // Problem: for every batch index z: D[z][M,N] = A[z][M,K] * B[z][N,K]^T
   int M = 0, N = 0, K = 0, batch = 1;
@@ -63,6 +76,7 @@ struct GemmArgs {
   int norm_rows_per_batch = 0;
   void* norm_out = nullptr;
   void* norm_gate_out = nullptr;
+  const GemmRope* rope = nullptr;
 };
 
 // Enqueue on `stream`.  Returns 0 on success; on failure returns non-zero and fills `err` (if given).

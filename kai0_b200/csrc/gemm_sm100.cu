@@ -484,6 +484,81 @@ __global__ void __launch_bounds__(CH * 32) splitk_finish_norm_k(const float* __r
   }
 }
 
+// Decode: split-K finish of the fused qkv projection + RoPE + q/k/v split (rope_pack_fwd_k's arithmetic) in one kernel.
+// One block per token row, one warp per 256-wide head slot (H query heads, K, V); lanes 0-15 hold the first half of
+// the head, lanes 16-31 the second half (rotate_half pairs are exchanged with one shuffle).
+__global__ void __launch_bounds__(1024) splitk_finish_rope_k(const float* __restrict__ ws, int splits, int M, int N,
+                                                             GemmRope r) {
+  pdl_enter();
+  const int row = blockIdx.x, slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(M) * N;
+  const int c = lane * 8;
+  const float* p0 = ws + static_cast<long long>(row) * N + slot * r.hd + c;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int z = 0;
+  for (; z + 4 <= splits; z += 4) {
+    float4 a[4], bq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4* p = reinterpret_cast<const float4*>(p0 + (z + j) * total);
+      a[j] = p[0];
+      bq[j] = p[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[0] += a[j].x; acc[1] += a[j].y; acc[2] += a[j].z; acc[3] += a[j].w;
+      acc[4] += bq[j].x; acc[5] += bq[j].y; acc[6] += bq[j].z; acc[7] += bq[j].w;
+    }
+  }
+  for (; z < splits; ++z) {
+    const float4* p = reinterpret_cast<const float4*>(p0 + z * total);
+    const float4 a = p[0], bq = p[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += bq.x; acc[5] += bq.y; acc[6] += bq.z; acc[7] += bq.w;
+  }
+  float x[8], other[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = bf16_round(acc[i]);  // the projection's bf16 output
+    other[i] = __shfl_xor_sync(0xffffffffu, x[i], 16);
+  }
+  const int b = row / r.T, t = row % r.T;
+  float o[8];
+  if (slot == r.H + 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = x[i];
+  } else {
+    const int half = r.hd / 2;
+    const int pidx = (r.pos_mode == 0 ? r.pos[row] : r.nvalid[b] + t) + 1;
+    const int cc = c & (half - 1);
+    const uint4 cv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(r.cos_t) +
+                                                     static_cast<long long>(pidx) * half + cc);
+    const uint4 sv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(r.sin_t) +
+                                                     static_cast<long long>(pidx) * half + cc);
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw[4] = {sv.x, sv.y, sv.z, sv.w};
+    const bool first = lane < 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float cs = (i & 1) ? __uint_as_float(cw[i >> 1] & 0xFFFF0000u) : __uint_as_float(cw[i >> 1] << 16);
+      const float sn = (i & 1) ? __uint_as_float(sw[i >> 1] & 0xFFFF0000u) : __uint_as_float(sw[i >> 1] << 16);
+      // q*cos + rotate_half(q)*sin in bf16 ops (modeling_gemma.py:170-194): first half pairs with -second, second with +first
+      o[i] = first ? bf16_round(x[i] * cs) + bf16_round(-other[i] * sn) : bf16_round(x[i] * cs) + bf16_round(other[i] * sn);
+    }
+  }
+  __nv_bfloat16* dst;
+  if (slot < r.H) dst = static_cast<__nv_bfloat16*>(r.Q) + (static_cast<long long>(row) * r.H + slot) * r.hd + c;
+  else
+    dst = static_cast<__nv_bfloat16*>(slot == r.H ? r.K : r.V) +
+          (static_cast<long long>(b) * r.kv_len + r.key_off + t) * r.hd + c;
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 pk = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+    ow[j] = *reinterpret_cast<uint32_t*>(&pk);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
 // STORE-only finish of the wave-quantisation path: 4 outputs per thread, 16-byte partial loads, fixed summation order.
 __global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restrict__ ws, int splits, long long total4,
                                                            int n4, __nv_bfloat16* __restrict__ D, long long ldd) {
@@ -515,6 +590,12 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream, char* err, int err_len) {
   bool norm_done = false;
   const int rc = gemm_bf16_impl(a, stream, err, err_len, &norm_done);
+  if (rc == 0 && a.rope != nullptr && !norm_done) {
+    const GemmRope& r = *a.rope;  // the fused finish+RoPE kernel was not applicable: plain kernel on the stored qkv
+    rope_pack_fwd(static_cast<const bf16*>(a.D), r.T, r.H, r.hd, r.pos, r.nvalid, r.pos_mode,
+                  static_cast<const bf16*>(r.cos_t), static_cast<const bf16*>(r.sin_t), static_cast<bf16*>(r.Q),
+                  static_cast<bf16*>(r.K), static_cast<bf16*>(r.V), r.key_off, r.kv_len, r.batch, stream);
+  }
   if (rc == 0 && a.norm_mod != nullptr && !norm_done) {
     // the fused finish+norm kernel was not applicable: plain kernel, same arithmetic
     rmsnorm_fwd(static_cast<const bf16*>(a.D), nullptr, a.norm_mod, a.norm_rows_per_batch, static_cast<bf16*>(a.norm_out),
@@ -554,6 +635,7 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
       part.gate = nullptr;
       part.D2 = nullptr;
       part.norm_mod = nullptr;
+      part.rope = nullptr;
       int rc = gemm_bf16(part, stream, err, err_len);
       if (rc != 0) return rc;
       const long long total = static_cast<long long>(a.M) * a.N;
@@ -561,6 +643,14 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
       const bool fuse_norm = a.norm_mod != nullptr && a.epilogue == EPI_RES && a.bias == nullptr && a.D2 == nullptr &&
                              a.N % 8 == 0 && a.N <= 1024 && a.ldd % 8 == 0 && a.ldres % 8 == 0 &&
                              (a.gate == nullptr || a.ldgate % 8 == 0);
+      if (a.rope != nullptr && a.epilogue == EPI_STORE && a.rope->hd == 256 && a.N == (a.rope->H + 2) * a.rope->hd &&
+          a.rope->H + 2 <= 32 && a.bias == nullptr) {
+        launch_pdl(splitk_finish_rope_k, dim3(a.M), dim3(32 * (a.rope->H + 2)), 0, stream, a.splitk_ws, s, a.M, a.N,
+                   *a.rope);
+        count_launch();
+        *norm_done = true;
+        return 0;
+      }
       if (fuse_norm) {
         const int ch = (a.N + 255) / 256;
         const dim3 g2(a.M);
@@ -657,6 +747,7 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
       part.d_batch_stride = static_cast<int64_t>(a.M) * a.N;
       part.block_n = bn;
       part.norm_mod = nullptr;
+      part.rope = nullptr;
       int rc = gemm_bf16(part, stream, err, err_len);
       if (rc != 0) return rc;
       const long long total = static_cast<long long>(a.M) * a.N;
