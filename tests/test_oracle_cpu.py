@@ -189,3 +189,24 @@ def test_bf16_noise_floor_of_the_oracle_itself():
     floor_s = H.rel_err(t2["suffix_out"], t1["suffix_out"])
     print(f"oracle self-noise: v_t {floor_v:.2e} suffix_out {floor_s:.2e}")
     assert floor_v < 1e-2 and floor_s < 1e-2
+
+
+def test_advantage_loss_reduces_to_the_plain_loss_and_broadcasts_the_value_term():
+    """AdvantageEstimator.forward (pi0_pytorch.py:560-587): with w_value = 0, w_action = 1 the loss is the plain flow
+    loss averaged over the action dimension; the value term is one number per sample broadcast over the horizon, with
+    the progress target clamped to [-1, 1]."""
+    oc = O.tiny_config(value_head=True)
+    p = O.init_params(oc, seed=3)
+    b = O.synthetic_batch(oc, 2)
+    args = (b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"], b["noise"], b["time"])
+    with torch.no_grad():
+        plain = O.forward_loss(p, oc, *args).mean(dim=-1)
+        prog = torch.tensor([0.4, -3.0])
+        la = O.advantage_forward_loss(p, oc, *args, prog, loss_action_weight=1.0, loss_value_weight=0.0)
+        both = O.advantage_forward_loss(p, oc, *args, prog, loss_action_weight=1.0, loss_value_weight=2.0)
+        clamped = O.advantage_forward_loss(p, oc, *args, torch.tensor([0.4, -1.0]), loss_action_weight=1.0,
+                                           loss_value_weight=2.0)
+    assert la.shape == (2, oc.action_horizon) and torch.allclose(la, plain, rtol=0, atol=0)
+    extra = both - la
+    assert torch.allclose(extra, extra[:, :1].expand_as(extra)) and bool((extra > 0).all())
+    assert torch.equal(both, clamped)  # progress -3 is clamped to -1
