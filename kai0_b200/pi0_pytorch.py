@@ -885,3 +885,8 @@ class AdvantageEstimator(PI0Pytorch):
         )
         del keep
         return out.view(bsize, 1)
+
+
+# stage_advantage/annotation/evaluator.py:31 imports this name (its value model: sample_values over whole episodes);
+# the stock reference module does not define it, the evaluator's call sites are AdvantageEstimator's surface.
+PI0Pytorch_Custom = AdvantageEstimator
