@@ -173,6 +173,9 @@ _TF_JOINT_LAYER = (3.8368 + 0.0311 + 0.1457) / 18   # one joint PaliGemma + expe
 _TF_REST = 0.0003 + 3 * 0.0012       # adaRMS / heads / projector (not depth-scaled)
 
 
+_LAST_CPU_DECODE = None  # filled by cpu_reference: CPU timing of the decode metric (reported beside `decode`)
+
+
 def _pick_cpu_threads() -> int:
     """All the host threads the port can USE: torch's bf16 CPU GEMM gets slower when oversubscribed on many-thread hosts
     (128 threads: 3.5x slower than 8 on the same pass), so a ~1 s probe picks the fastest of a few thread counts."""
@@ -245,6 +248,20 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
     for _ in range(k):
         one()
     dt = (time.time() - t1) / k
+    # secondary metric beside it: the 10-step action decode on the same truncated architecture, scaled by decode FLOPs
+    # (prefix pass 4.635 TFLOP = SigLIP 0.6605 + PaliGemma 3.84 + rest, 10 steps x 0.0389 expert)
+    global _LAST_CPU_DECODE
+    _LAST_CPU_DECODE = None
+    if full and (time.time() - t0) < budget_s:
+        dfrac = (oc.vit_depth * 0.6605 / 27 + oc.paligemma.depth * (3.84 + 10 * 0.0389) / 18 + 0.13) / 5.024
+        with torch.no_grad():
+            td = time.time()
+            O.sample_actions({k: v.detach() for k, v in params.items()}, oc, b["images"], b["img_masks"], b["tokens"],
+                             b["token_mask"], b["noise"])
+            td = time.time() - td
+        _LAST_CPU_DECODE = {"decode_ms_scaled": 1e3 * td / dfrac, "measured_s": td, "flop_fraction": dfrac,
+                            "sample": "sample_actions (10 steps, B=1) of the same truncated oracle, one pass, scaled by "
+                                      "the decode FLOP ratio"}
     desc = (f"B=1 forward+backward of the oracle port, full widths, truncated to {oc.vit_depth}/27 SigLIP and "
             f"{oc.paligemma.depth}/18 joint Gemma layers ({100 * frac:.1f} % of a sample's FLOPs: {dt:.1f} s per pass), "
             f"scaled to a whole sample by that ratio; {k} timed pass(es) after {done_warm} warm-up, {cores} threads, "
@@ -299,6 +316,8 @@ def main():
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
+        if _LAST_CPU_DECODE is not None:
+            line["cpu_baseline"]["decode"] = _LAST_CPU_DECODE
         emit(line)
         return 0
 
@@ -536,6 +555,8 @@ def main():
             torch.cuda.empty_cache()
             sps, cores, desc, _ = cpu_reference(1, 0, args.cpu_budget, full=not args.small)
             line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            if _LAST_CPU_DECODE is not None:
+                line["cpu_baseline"]["decode"] = _LAST_CPU_DECODE
         emit(line)
     if world > 1:
         dist.barrier()
