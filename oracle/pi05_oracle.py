@@ -4,10 +4,17 @@ This file is a plain-torch restatement of the reference's PyTorch arithmetic, op
 rounding point.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference`
 legs may import it; the product path (kai0_b200/) never does.
 
-PARITY UNPINNED: the reference ships no test, golden vector or fixture for `models_pytorch` and
-its own code cannot be imported here (needs transformers==4.53.2 with patched files + jax/flax).  The oracle is
-therefore pinned two other ways (tests/test_oracle_cpu.py): against stock transformers-5.5 `SiglipVisionModel`
-and `GemmaModel` for the un-patched math, and through internal consistency (KV-cache decode == joint forward).
+PARITY PINNED to the reference itself: the reference ships no test, golden vector or fixture for `models_pytorch`
+(SURVEY.md §8c), but its own PI0Pytorch can be executed on the CPU of the build container — the patched transformers
+files are loaded in place over the installed transformers and jax is stubbed (tools/reference_loader.py).
+tools/make_golden_reference.py ran it in both of its precisions on a seeded configuration with the reference's
+geometry (tools/reference_pin.py) and committed the outputs (tests/golden/reference_pin.pt); this oracle reproduces
+them to 1.5e-7 relative (loss) / 9e-8 (action chunk) in float32 and to the bf16 noise floor (1.1e-3 / 3.7e-4) under the
+bfloat16 dtype map (tests/test_reference_pin_cpu.py, which also re-runs the reference bit-exactly when the checkout is
+present).  Additional pins (tests/test_oracle_cpu.py): stock transformers-5.5 `SiglipVisionModel` / `GemmaModel` for
+the un-patched math, internal consistency (KV-cache decode == joint forward), mask known-answers.
+The AdvantageEstimator head and the backward pass (torch.autograd through this file) are not covered by reference
+outputs: for those rows parity remains anchored on this restatement.
 
 Every function cites the reference lines it follows (paths relative to /root/reference/src/openpi/):
   P  = models_pytorch/pi0_pytorch.py
