@@ -13,8 +13,9 @@ them to 1.5e-7 relative (loss) / 9e-8 (action chunk) in float32 and to the bf16 
 bfloat16 dtype map (tests/test_reference_pin_cpu.py, which also re-runs the reference bit-exactly when the checkout is
 present).  Additional pins (tests/test_oracle_cpu.py): stock transformers-5.5 `SiglipVisionModel` / `GemmaModel` for
 the un-patched math, internal consistency (KV-cache decode == joint forward), mask known-answers.
-The AdvantageEstimator head and the backward pass (torch.autograd through this file) are not covered by reference
-outputs: for those rows parity remains anchored on this restatement.
+The same fixture pins the backward pass (gradient of loss.mean() w.r.t. every parameter, reference autograd vs
+torch.autograd through this file: 1.1e-6 in float32) and the AdvantageEstimator (6 images, value head, weighted loss,
+sample_values, gradients: 4.9e-8 / 5.6e-9 / 1.1e-6 in float32).
 
 Every function cites the reference lines it follows (paths relative to /root/reference/src/openpi/):
   P  = models_pytorch/pi0_pytorch.py

@@ -58,3 +58,52 @@ def test_committed_reference_outputs_are_reproducible_here():
     loss, acts = MG.run_reference(p0, m, params, PIN.pin_inputs())
     g = torch.load(GOLD)
     assert torch.equal(loss, g["loss_float32"]) and torch.equal(acts, g["actions_float32"])
+
+
+@pytest.mark.parametrize("precision,tol", [("float32", 1e-4), ("bfloat16", 0.12)])
+def test_oracle_autograd_matches_the_reference_models_gradients(precision, tol):
+    """`loss.mean().backward()` through the reference (train_pytorch.py:547-549) on the pin configuration: per parameter
+    the L2 norm and 256 strided elements of its gradient are committed.  torch.autograd through the oracle must give the
+    same gradients — to 1e-4 in float32 (measured 1.1e-6: identical semantics, incl. the tied / padded embedding and the
+    parameters that get no gradient), to bf16 noise under the bfloat16 dtype map (measured worst 6.5e-2, on the last
+    layer's key projection whose gradient is small)."""
+    import make_golden_reference as MG
+
+    g = torch.load(GOLD)
+    ref = g[f"grads_{precision}"]
+    oc = PIN.oracle_config()
+    params = PIN.pin_weights(O.param_specs(oc), dtype_map=precision == "bfloat16")
+    mine = MG.oracle_backward(params, oc, PIN.pin_inputs())
+    assert set(mine) == set(ref)  # the same parameters receive a gradient (e.g. not the dead last-layer prefix MLP)
+    worst = MG.compare_grads(mine, ref)
+    assert worst[0] < tol, worst
+    # padding_idx: row 0 of the embedding table gets no gradient in the reference either
+    emb = "paligemma_with_expert.paligemma.model.language_model.embed_tokens.weight"
+    assert float(ref[emb]["sample"][0]) == 0.0 and float(mine[emb]["sample"][0]) == 0.0
+
+
+@pytest.mark.parametrize("precision,tol,tol_grad", [("float32", 1e-5, 1e-4), ("bfloat16", 2e-3, 0.2)])
+def test_oracle_matches_the_reference_advantage_estimator(precision, tol, tol_grad):
+    """AdvantageEstimator (pi0_pytorch.py:464-644) run from the reference checkout: 6 image keys given in scrambled
+    order, weighted loss [B, 50] with a clamped progress target, `sample_values` (its noise / time injected), and the
+    gradients of loss.mean() incl. the value head.  Measured: float32 4.9e-8 (loss) / 5.6e-9 (value) / 1.1e-6
+    (gradients); bfloat16 2.5e-4 / 1.2e-5 / 0.12 (bf16 noise on a small last-layer gradient)."""
+    import make_golden_reference as MG
+
+    g = torch.load(GOLD)
+    oc, b, progress = MG.adv_config_and_inputs()
+    params = PIN.pin_weights(O.param_specs(oc), dtype_map=precision == "bfloat16")
+    loss, value, grads = MG.oracle_advantage(params, oc, b, progress)
+    assert loss.shape == (PIN.BATCH, 50) and value.shape == (PIN.BATCH, 1)
+    assert H.rel_err(loss, g[f"adv_loss_{precision}"]) < tol
+    assert H.max_err(value, g[f"adv_value_{precision}"]) < tol
+    assert set(grads) == set(g[f"adv_grads_{precision}"]) and any(k.startswith("value_head.") for k in grads)
+    worst = MG.compare_grads(grads, g[f"adv_grads_{precision}"])
+    assert worst[0] < tol_grad, worst
+    aux = g[f"adv_aux_{precision}"]  # the reference's loss_aux_dict (:582-583)
+    with torch.no_grad():
+        v_t, so = O.model_v_t(params, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"],
+                              b["time"][:, None, None] * b["noise"] + (1 - b["time"][:, None, None]) * b["actions"],
+                              b["time"])
+        la = torch.nn.functional.mse_loss(b["noise"] - b["actions"], v_t, reduction="none").mean(-1).mean()
+    assert abs(float(la) - aux["loss_action"]) < 5 * tol * aux["loss_action"]
