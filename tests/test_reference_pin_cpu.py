@@ -48,16 +48,24 @@ def test_oracle_matches_the_reference_model(precision, tol_loss, tol_actions):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/openpi"), reason="reference checkout not present (GPU box)")
 def test_committed_reference_outputs_are_reproducible_here():
-    """Build container only: run the reference again (float32 precision, the cheaper one) and compare bit-exactly."""
+    """Build container only: build the reference again (bfloat16 dtype map), check that its state_dict is exactly the
+    parameter contract the oracle and the engine expose (names, shapes, dtypes; plus the two lm_heads), run it and
+    compare with the committed outputs bit-exactly."""
     import make_golden_reference as MG
 
     torch.set_num_threads(2)
     oc = PIN.oracle_config()
-    params = PIN.pin_weights(O.param_specs(oc), dtype_map=False)
-    p0, m = MG.build_reference("float32")
+    specs = O.param_specs(oc)
+    params = PIN.pin_weights(specs, dtype_map=True)
+    p0, m = MG.build_reference("bfloat16")
+    sd = m.state_dict()
+    extra = set(sd) - set(specs)
+    assert extra == {"paligemma_with_expert.paligemma.lm_head.weight", "paligemma_with_expert.gemma_expert.lm_head.weight"}
+    for name, (shape, dt) in specs.items():
+        assert tuple(sd[name].shape) == tuple(shape) and sd[name].dtype == dt, name
     loss, acts = MG.run_reference(p0, m, params, PIN.pin_inputs())
     g = torch.load(GOLD)
-    assert torch.equal(loss, g["loss_float32"]) and torch.equal(acts, g["actions_float32"])
+    assert torch.equal(loss, g["loss_bfloat16"]) and torch.equal(acts, g["actions_bfloat16"])
 
 
 @pytest.mark.parametrize("precision,tol", [("float32", 1e-4), ("bfloat16", 0.12)])
