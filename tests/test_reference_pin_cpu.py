@@ -115,3 +115,31 @@ def test_oracle_matches_the_reference_advantage_estimator(precision, tol, tol_gr
                               b["time"])
         la = torch.nn.functional.mse_loss(b["noise"] - b["actions"], v_t, reduction="none").mean(-1).mean()
     assert abs(float(la) - aux["loss_action"]) < 5 * tol * aux["loss_action"]
+
+
+def test_default_forward_consumes_random_numbers_in_the_reference_order():
+    """`PI0Pytorch.forward(observation, actions)` with nothing injected: the reference augments the images (train=True),
+    then draws noise, then time, all from the global torch RNG (pi0_pytorch.py:318-324).  The committed loss comes from
+    the reference with a fixed seed.  Here the same seed feeds the PRODUCT's host-side draw functions
+    (`kai0_b200.pi0_pytorch.PI0Pytorch._draw_augment_params`, `sample_noise`, `sample_time` — pure torch, device =
+    cpu) in the order the product's forward() calls them; the oracle evaluated on what they return must reproduce the
+    reference's loss (float32: 1e-5).  A different draw order or distribution would change every number."""
+    from kai0_b200.pi0_pytorch import PI0Pytorch
+    from oracle import preprocess_oracle as PO
+
+    g = torch.load(GOLD)
+    oc = PIN.oracle_config()
+    params = PIN.pin_weights(O.param_specs(oc), dtype_map=False)
+    b = PIN.pin_inputs()
+    model = PI0Pytorch(H.engine_config(oc), init_weights=False)  # CPU module: only its torch-side helpers are used
+    cpu = torch.device("cpu")
+    torch.manual_seed(PIN.WEIGHT_SEED + 1)
+    aug = model._draw_augment_params(PIN.KEYS, oc.image_size, cpu)       # forward(): _preprocess_observation first,
+    noise = model.sample_noise(b["actions"].shape, cpu)                   # then sample_noise,
+    time = model.sample_time(b["actions"].shape[0], cpu)                  # then sample_time
+    imgs = PO.preprocess_images(dict(zip(PIN.KEYS, b["images"])), PIN.KEYS, train=True, params=aug,
+                                resolution=(oc.image_size, oc.image_size))
+    with torch.no_grad():
+        loss = O.forward_loss(params, oc, [imgs[k] for k in PIN.KEYS], b["img_masks"], b["tokens"], b["token_mask"],
+                              b["actions"], noise, time)
+    assert H.rel_err(loss, g["loss_default_float32"]) < 1e-5

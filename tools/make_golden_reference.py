@@ -213,6 +213,17 @@ def main():
               f"[{time.time() - t:.0f} s]")
         out[f"loss_{precision}"] = loss.to(torch.float32).contiguous()
         out[f"actions_{precision}"] = acts.to(torch.float32).contiguous()
+    # ---- the DEFAULT training forward: preprocessing with train=True (augmentation) and noise / time drawn inside, all
+    # from the global torch RNG (pi0_pytorch.py:318-324) -> pins the order in which random numbers are consumed
+    params = PIN.pin_weights(specs, dtype_map=False)
+    p0, m = build_reference("float32")
+    m.load_state_dict(params, strict=False)
+    torch.manual_seed(PIN.WEIGHT_SEED + 1)
+    with torch.no_grad():
+        out["loss_default_float32"] = m.forward(Obs(b), b["actions"]).to(torch.float32).contiguous()
+    del m
+    print(f"default forward (augmentation + internal noise/time, seed {PIN.WEIGHT_SEED + 1}): loss mean "
+          f"{float(out['loss_default_float32'].mean()):.6f}")
     # ---- AdvantageEstimator (pi0_pytorch.py:464-644): 6 images, value head, weighted loss, sample_values
     oc_a, b_a, progress = adv_config_and_inputs()
     for precision in ("bfloat16", "float32"):
