@@ -170,12 +170,16 @@ def run_reference_advantage(p0, precision, params, b, progress):
     return loss.detach(), {k: float(v) for k, v in aux.items()}, value, grads
 
 
-def oracle_advantage(params, oc, b, progress):
-    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    loss = O.advantage_forward_loss(pr, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"],
-                                    b["noise"], b["time"], progress, loss_action_weight=ADV_WA, loss_value_weight=ADV_WV)
-    loss.mean().backward()
-    grads = grad_summary((n, p.grad) for n, p in pr.items())
+def oracle_advantage(params, oc, b, progress, with_grads=True):
+    pr = {k: v.clone().requires_grad_(with_grads) for k, v in params.items()}
+    with torch.set_grad_enabled(with_grads):
+        loss = O.advantage_forward_loss(pr, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"],
+                                        b["noise"], b["time"], progress, loss_action_weight=ADV_WA,
+                                        loss_value_weight=ADV_WV)
+    grads = None
+    if with_grads:
+        loss.mean().backward()
+        grads = grad_summary((n, p.grad) for n, p in pr.items())
     with torch.no_grad():
         _, so = O.model_v_t(params, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["noise"], b["time"])
         value = O.value_head(params, so)
