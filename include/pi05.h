@@ -46,7 +46,7 @@ typedef struct pi05_config {
 } pi05_config;
 
 /* dtype codes used in tensor descriptors */
-enum { PI05_F32 = 0, PI05_BF16 = 1 };
+enum { PI05_F32 = 0, PI05_BF16 = 1, PI05_I32 = 2, PI05_U8 = 3 }; /* I32 / U8: index taps only (pi05_get_tap) */
 
 /* One named parameter (reference state_dict key), its data and (optionally) its gradient buffer.
  * The Python module owns both as torch tensors; the engine only keeps the pointers. */

@@ -236,7 +236,8 @@ int pi05_get_tap(pi05_engine* pe, const char* name, void* dst, int64_t* numel, i
   if (numel) *numel = it->second.numel;
   if (dtype) *dtype = it->second.dtype;
   if (dst) {
-    const size_t bytes = static_cast<size_t>(it->second.numel) * (it->second.dtype == PI05_BF16 ? 2 : 4);
+    const int dtc = it->second.dtype;
+    const size_t bytes = static_cast<size_t>(it->second.numel) * (dtc == PI05_BF16 ? 2 : (dtc == PI05_U8 ? 1 : 4));
     cudaError_t ce =
         cudaMemcpyAsync(dst, it->second.ptr, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
     if (ce != cudaSuccess) {

@@ -568,6 +568,10 @@ int vision_forward(Engine& e, const float* images, int B, bf16* prefix_embs) {
 int prefix_forward(Engine& e, const pi05_batch* b) {
   const int B = b->batch;
   prefix_meta(b->image_masks, b->token_mask, B, e.NI, e.T, e.L, e.pad, e.pos, e.nvalid, e.stream);
+  // index work of pi0_pytorch.py:219-235,342-343 (pad mask, cumsum(pad) - 1, valid-prefix count): bit-exact taps
+  add_tap(e, "prefix_pad", e.pad, static_cast<int64_t>(B) * e.P, PI05_U8);
+  add_tap(e, "prefix_pos", e.pos, static_cast<int64_t>(B) * e.P, PI05_I32);
+  add_tap(e, "prefix_nvalid", e.nvalid, B, PI05_I32);
   bf16* prefix_embs = e.a1[0].x_in;
   CHECK_RC(vision_forward(e, b->images, B, prefix_embs));
   embed_tokens_fwd(b->tokens, e.embed.d<bf16>(), prefix_embs, B, e.L, e.D, static_cast<int64_t>(e.P) * e.D, e.NI * e.T,

@@ -17,6 +17,10 @@ from . import _lib
 class FusedClipAdamW:
     def __init__(self, model, lr=2.5e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10, max_norm=1.0):
         self.model = model
+        frozen = [n for n, p in model.named_parameters() if not p.requires_grad and "lm_head" not in n]
+        if frozen:
+            raise ValueError("FusedClipAdamW updates every element of the flat arenas; frozen parameters are not supported "
+                             f"(requires_grad=False on {frozen[:3]}...): use torch.optim.AdamW over model.parameters()")
         model.direct_grads = True
         self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, max_norm=max_norm)]
         self.flat = model.flat_parameters()  # [bf16 (trainable prefix), fp32]
@@ -33,6 +37,10 @@ class FusedClipAdamW:
     def step(self):
         """Clips (global L2 norm over every trainable gradient) and applies AdamW. Returns the pre-clip gradient
         norm as a 0-dim device tensor (what clip_grad_norm_ returns)."""
+        live = self.model._flat_params
+        if live is None or live[0] is not self.flat[0] or live[1] is not self.flat[1]:
+            raise RuntimeError("FusedClipAdamW: the model's arenas were re-created (.to() / .cuda() after the optimiser was "
+                               "built); create the optimiser after moving the model, as train_pytorch.py:417,469 does")
         gb, gf = self.flat[0].grad, self.flat[1].grad
         if gb is None or gf is None:
             raise RuntimeError("FusedClipAdamW.step(): no gradients (run backward with model.direct_grads = True)")

@@ -220,28 +220,56 @@ def _attach(root: nn.Module, dotted: str, param: nn.Parameter, top_cls=_Node):
 
 
 class _EngineFunction(torch.autograd.Function):
-    """One autograd node for the whole network: forward = pi05_forward, backward = pi05_backward."""
+    """One autograd node for the whole network: forward = pi05_forward, backward = pi05_backward.
+
+    The engine keeps ONE activation stash per training engine, so a node's backward is only valid while its forward is
+    still the engine's most recent training forward: every training forward stamps a generation number, backward checks
+    it and raises instead of silently using another batch's stash (the reference's autograd graph would keep both)."""
 
     @staticmethod
     def forward(ctx, model, batch, actions, noise, time, *params):
         ctx.model = model
         loss = model._engine_forward(batch, actions, noise, time)
+        ctx.engine = model._engine
+        ctx.generation = model._train_generation
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         model = ctx.model
+        if ctx.engine is not model._train_engine_handle() or ctx.generation != model._train_generation:
+            raise RuntimeError(
+                "PI0Pytorch (B200 engine): backward() of a forward whose activation stash is gone - another training "
+                "forward ran on this model (or the engine was re-created by .to() / a different batch size) before this "
+                "backward.  The engine keeps one stash: call backward() before the next training forward "
+                "(no_grad / eval forwards, sample_actions and sample_values use a separate engine and are fine).")
+        params = [p for _, p in model._grad_params]
+        if not model.direct_grads:
+            # autograd path (DDP hooks, plain .grad): the engine OVERWRITES its flat gradient arena on every backward.
+            # A .grad that is still a view of the arena (autograd steals the tensor we return when .grad was None) would
+            # be overwritten in place and then doubled by AccumulateGrad: detach such gradients from the arena first,
+            # and hand out copies whenever something is already accumulated (zero_grad(set_to_none=False), gradient
+            # accumulation).  The reference loop (set_to_none=True, one backward per step) never takes this branch.
+            accumulating = False
+            for p in params:
+                if p.grad is not None:
+                    accumulating = True
+                    if model._aliases_grad_arena(p.grad):
+                        p.grad = p.grad.detach().clone()
         grads = model._engine_backward(dloss.contiguous())
+        dead = model._dead_grad_names
         if model.direct_grads:
             # engine-owned gradients: .grad of every parameter is (a view of) the flat gradient arena; autograd only
-            # sees the anchor.  Skips ~700 per-parameter AccumulateGrad copies per step.
+            # sees the anchor.  Skips ~700 per-parameter AccumulateGrad copies per step.  Overwrite semantics.
             if model._flat_params is not None:
                 model._sync_flat_param_grads()  # the caller optimises the two flat tensors
-            else:
-                for (_, p), g in zip(model._grad_params, grads):
-                    p.grad = g
+            for (n, p), g in zip(model._grad_params, grads):
+                p.grad = None if n in dead else g
             return (None, None, None, None, None, torch.zeros_like(model._grad_anchor))
-        return (None, None, None, None, None, *grads)
+        out = []
+        for (n, _), g in zip(model._grad_params, grads):
+            out.append(None if n in dead else (g.clone() if accumulating else g))
+        return (None, None, None, None, None, *out)
 
 
 class PI0Pytorch(nn.Module):
@@ -324,18 +352,32 @@ class PI0Pytorch(nn.Module):
         self.use_cuda_graph = True  # sample_actions replays one captured CUDA graph per (batch, num_steps)
         self._graphs = {}
 
-        self._engine = None
-        self._engine_key = None
+        self._engine = None        # the ACTIVE engine handle (one of self._engines)
+        self._engine_key = None    # (device index, train, max batch, num_images) of the active engine
         self._workspace = None
-        self._graphs = {}
+        self._engines = OrderedDict()  # (device index, train, num_images) -> dict(handle, workspace, max_batch, graphs); LRU order
+        self._train_generation = 0
         self._dp_group = None
         self._keep = None
+        # parameters the reference's autograd leaves WITHOUT a gradient (nothing on the loss path reads the last layer's
+        # prefix-stream output or the final prefix norm, pi0_pytorch.py:350-358): .grad stays None for them, so a stock
+        # optimiser creates no state and applies no weight decay, exactly as with the reference module
+        last = f"{_LM}layers.{self.pg.depth - 1}."
+        self._dead_grad_names = frozenset(
+            [last + "self_attn.o_proj.weight", last + "mlp.gate_proj.weight", last + "mlp.up_proj.weight",
+             last + "mlp.down_proj.weight", last + "post_attention_layernorm.weight", _LM + "norm.weight"]
+        ) if self.pg.depth > 0 else frozenset([_LM + "norm.weight"])
 
     # ------------------------------------------------------------------ init / housekeeping
     @torch.no_grad()
     def reset_parameters(self, seed: int | None = None):
-        """Reference init rules: Linear/Embedding N(0, 0.02) (HF initializer_range), LayerNorm ones/zeros, RMSNorm
-        weight and adaRMS dense weight zeros (modeling_gemma.py:59-63), nn.Linear default for the fp32 heads."""
+        """Seeded from-scratch initialisation in the reference's DISTRIBUTIONS (not its RNG stream: a checkpoint is what
+        makes two runs comparable, train_pytorch.py:450-460).  Transformer weights and embeddings N(0, 0.02) (HF
+        `initializer_range`), LayerNorm ones / zeros, RMSNorm weight and adaRMS dense zeros (modeling_gemma.py:59-63),
+        and for the fp32 heads outside the HF stack (`action_in/out_proj`, `time_mlp_*`, `value_head.*`: plain nn.Linear in
+        pi0_pytorch.py:100-109) torch's nn.Linear default: weight and bias U(-1/sqrt(fan_in), +1/sqrt(fan_in)).  The
+        SigLIP patch convolution / position embedding also get N(0, 0.02) (HF uses lecun-normal / width-scaled normal
+        there; immaterial once `safetensors.load_model` has run)."""
         dev = self._device()
         g = None
         if seed is not None:
@@ -343,14 +385,16 @@ class PI0Pytorch(nn.Module):
         params = dict(self.named_parameters())
         for name, shape, dt, kind in self._table:
             p = params[name]
-            if kind == "zeros":
+            if not name.startswith(_PWE):  # plain nn.Linear heads: kaiming_uniform_(a=sqrt(5)) + uniform bias
+                w_shape = shape if name.endswith(".weight") else params[name[: -len("bias")] + "weight"].shape
+                bound = 1.0 / math.sqrt(math.prod(w_shape[1:]))
+                p.uniform_(-bound, bound, generator=g)
+            elif kind == "zeros":
                 p.zero_()
             elif kind == "ones":
                 p.fill_(1.0)
             else:
-                fan_in = math.prod(shape[1:])
-                std = 0.02 if (kind == "embed" or name.startswith(_PWE)) else 1.0 / math.sqrt(3.0 * fan_in)
-                p.normal_(0.0, std, generator=g)  # drawn on the parameter's own device
+                p.normal_(0.0, 0.02, generator=g)  # drawn on the parameter's own device
 
     def _apply(self, fn, recurse=True):
         """Keep the parameters views of the flat arenas across .to()/.cuda(): move the arenas, re-point the views."""
@@ -438,11 +482,26 @@ class PI0Pytorch(nn.Module):
         return self._flat[torch.bfloat16].device
 
     def _destroy_engine(self):
-        if self._engine is not None:
-            _lib.lib().pi05_destroy(self._engine)
+        """Destroys EVERY cached engine (parameters moved / module deleted)."""
+        for ent in self._engines.values():
+            _lib.lib().pi05_destroy(ent["handle"])
+        self._engines.clear()
         self._engine = None
         self._engine_key = None
         self._workspace = None
+        self._graphs = {}
+
+    def _evict_engine(self, key):
+        ent = self._engines.pop(key)
+        if self._engine is ent["handle"]:
+            self._engine, self._engine_key, self._workspace, self._graphs = None, None, None, {}
+        _lib.lib().pi05_destroy(ent["handle"])
+        ent["workspace"] = None
+
+    def _train_engine_handle(self):
+        """Handle of the training engine whose stash the last training forward filled (None if it was evicted)."""
+        ent = self._engines.get(getattr(self, "_train_key", None))
+        return ent["handle"] if ent is not None else None
 
     def __del__(self):
         try:
@@ -451,19 +510,33 @@ class PI0Pytorch(nn.Module):
             pass
 
     def _ensure_engine(self, batch: int, train: bool, num_images: int | None = None):
+        """Makes the engine for (device, train, num_images) the active one, creating it on first use.  Engines are kept
+        (an AdvantageEstimator alternating 3- and 6-image calls, or a validation forward between training steps, does not
+        re-plan 100+ GB of workspace each time); when a new workspace does not fit in free device memory the least
+        recently used other engines are destroyed first."""
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError(
                 "PI0Pytorch (B200 engine) has no CPU path: move the module to an sm_100 CUDA device first"
             )
         ni = int(num_images or self.ecfg.num_images)
-        need_b = max(batch, self._max_batch_hint or 0)
-        key = (dev.index, train)
-        if (self._engine is not None and self._engine_key[:2] == key and self._engine_key[2] >= batch
-                and self._engine_key[3] == ni):
-            return
-        self._destroy_engine()
-        self._graphs = {}
+        key = (dev.index, bool(train), ni)
+        ent = self._engines.get(key)
+        if ent is not None and ent["max_batch"] < batch:
+            self._evict_engine(key)  # grown batch: re-plan this one
+            ent = None
+        if ent is None:
+            ent = self._create_engine(dev, key, max(batch, self._max_batch_hint or 0))
+            self._engines[key] = ent
+        self._engines.move_to_end(key)
+        self._engine = ent["handle"]
+        self._engine_ent = ent
+        self._workspace = ent["workspace"]
+        self._graphs = ent["graphs"]
+        self._engine_key = (dev.index, bool(train), ent["max_batch"], ni)
+
+    def _create_engine(self, dev, key, need_b):
+        _, train, ni = key
         l = _lib.lib()
         c = _lib.Config()
         for dst, src in ((c.paligemma, self.pg), (c.expert, self.ex)):
@@ -479,22 +552,41 @@ class PI0Pytorch(nn.Module):
         if nbytes == 0:
             raise RuntimeError(f"pi05_workspace_bytes: {_lib.last_error()}")
         with torch.cuda.device(dev):
-            self._workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-            base = (self._workspace.data_ptr() + 255) // 256 * 256
+            need = nbytes + 256
+            if train:
+                need += sum(t.numel() * t.element_size() for dt, t in self._flat.items() if self._flat_grad[dt] is None)
+            # LRU eviction until the new workspace fits (free memory incl. what torch's caching allocator can give back)
+            while self._engines:
+                free, _ = torch.cuda.mem_get_info(dev)
+                cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                if free + cached >= need + (1 << 30):
+                    break
+                self._evict_engine(next(iter(self._engines)))
+                torch.cuda.empty_cache()
+            workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (workspace.data_ptr() + 255) // 256 * 256
             handle = C.c_void_p()
             _lib.check(
                 l.pi05_create(C.byref(c), dev.index or 0, C.c_void_p(base), C.c_size_t(nbytes), C.byref(handle)),
                 "pi05_create",
             )
-        self._engine = handle
-        self._engine_key = (dev.index, train, need_b, ni)
         if train:
             for dt in (torch.bfloat16, torch.float32):
                 if self._flat_grad[dt] is None:
                     self._flat_grad[dt] = torch.zeros_like(self._flat[dt])
-        self._bind()
+        ent = {"handle": handle, "workspace": workspace, "max_batch": need_b, "graphs": {}}
+        self._bind(handle, with_grads=train)
+        return ent
 
-    def _bind(self):
+    def _aliases_grad_arena(self, t: Tensor) -> bool:
+        for g in self._flat_grad.values():
+            if g is not None and g.device == t.device:
+                lo = g.data_ptr()
+                if lo <= t.data_ptr() < lo + g.numel() * g.element_size():
+                    return True
+        return False
+
+    def _bind(self, handle, with_grads: bool):
         names, arr = [], (_lib.Param * len(self._offsets))()
         for i, (name, (dt, o, n, _)) in enumerate(self._offsets.items()):
             esz = 2 if dt == torch.bfloat16 else 4
@@ -504,10 +596,10 @@ class PI0Pytorch(nn.Module):
             arr[i].dtype = 1 if dt == torch.bfloat16 else 0
             arr[i].numel = n
             arr[i].data = self._flat[dt].data_ptr() + o * esz
-            g = self._flat_grad[dt]
+            g = self._flat_grad[dt] if with_grads else None
             arr[i].grad = (g.data_ptr() + o * esz) if g is not None else None
         self._keep = names
-        _lib.check(_lib.lib().pi05_bind_params(self._engine, arr, len(self._offsets)), "pi05_bind_params")
+        _lib.check(_lib.lib().pi05_bind_params(handle, arr, len(self._offsets)), "pi05_bind_params")
 
     def set_taps(self, enabled: bool):
         self._taps = bool(enabled)
@@ -517,7 +609,8 @@ class PI0Pytorch(nn.Module):
         n, dt = C.c_int64(), C.c_int32()
         l = _lib.lib()
         _lib.check(l.pi05_get_tap(self._engine, name.encode(), None, C.byref(n), C.byref(dt), None), "pi05_get_tap")
-        out = torch.empty(n.value, dtype=torch.bfloat16 if dt.value == 1 else torch.float32, device=self._device())
+        tdt = {0: torch.float32, 1: torch.bfloat16, 2: torch.int32, 3: torch.uint8}[dt.value]
+        out = torch.empty(n.value, dtype=tdt, device=self._device())
         stream = C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
         _lib.check(
             l.pi05_get_tap(self._engine, name.encode(), C.c_void_p(out.data_ptr()), C.byref(n), C.byref(dt), stream),
@@ -657,11 +750,12 @@ class PI0Pytorch(nn.Module):
             ),
             "pi05_forward",
         )
-        self._last_inputs = (keep, actions, noise, time)  # keep device buffers alive until backward
+        self._engine_ent["keep"] = (keep, actions, noise, time)  # device buffers stay alive until this engine's next call
         return loss
 
     def _engine_backward(self, dloss):
-        _lib.check(_lib.lib().pi05_backward(self._engine, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
+        handle = self._train_engine_handle()
+        _lib.check(_lib.lib().pi05_backward(handle, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
         if self._dp_group is not None:
             self._allreduce_flat_grads()
         grads = []
@@ -700,8 +794,7 @@ class PI0Pytorch(nn.Module):
         time = time.to(dev, torch.float32).contiguous()
         B = actions.shape[0]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]),
-                            num_images=len(images))
+        self._ensure_engine(B, train=need_grad, num_images=len(images))
         pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         return self._run_training_forward(pack, actions, noise, time, need_grad)
 
@@ -709,6 +802,8 @@ class PI0Pytorch(nn.Module):
         dev = self._device()
         if not need_grad:
             return self._engine_forward(pack, actions, noise, time)
+        self._train_generation += 1  # invalidates the stash any earlier, not yet back-propagated forward relied on
+        self._train_key = (dev.index, True, self._engine_key[3])
         named = dict(self.named_parameters())
         self._grad_params = [(n, named[n]) for n in self._offsets if n not in _UNUSED and named[n].requires_grad]
         if self.direct_grads:
@@ -726,8 +821,7 @@ class PI0Pytorch(nn.Module):
         if noise is None:
             noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev)
         noise = noise.to(dev, torch.float32).contiguous()
-        train_engine = self._engine_key is not None and self._engine_key[1]
-        self._ensure_engine(bsize, train=train_engine, num_images=len(images))
+        self._ensure_engine(bsize, train=False, num_images=len(images))
         b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         taps = bool(getattr(self, "_taps", False))
         if self.use_cuda_graph and not taps:
@@ -830,7 +924,7 @@ class AdvantageEstimator(PI0Pytorch):
             ),
             "pi05_forward_advantage",
         )
-        self._last_inputs = (keep, actions, noise, time, self._adv_progress)
+        self._engine_ent["keep"] = (keep, actions, noise, time, self._adv_progress)
         return loss
 
     def forward(self, observation, actions, noise=None, time=None, return_loss_dict=False):
@@ -851,8 +945,7 @@ class AdvantageEstimator(PI0Pytorch):
         B = actions.shape[0]
         self._adv_progress = progress.to(dev, torch.float32).reshape(B).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        self._ensure_engine(B, train=need_grad or (self._engine_key is not None and self._engine_key[1]),
-                            num_images=len(images))
+        self._ensure_engine(B, train=need_grad, num_images=len(images))
         pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         loss = self._run_training_forward(pack, actions, noise, time, need_grad)
         if return_loss_dict:
@@ -872,8 +965,7 @@ class AdvantageEstimator(PI0Pytorch):
 
     def _sample_values(self, images, img_masks, lang_tokens, lang_masks, noise, time):
         bsize = noise.shape[0]
-        train_engine = self._engine_key is not None and self._engine_key[1]
-        self._ensure_engine(bsize, train=train_engine, num_images=len(images))
+        self._ensure_engine(bsize, train=False, num_images=len(images))
         b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         out = torch.empty(bsize, dtype=torch.float32, device=self._device())
         l = _lib.lib()

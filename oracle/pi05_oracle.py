@@ -540,6 +540,10 @@ def model_v_t(p, cfg: OracleConfig, images, img_masks, lang_tokens, lang_masks, 
     att_2d = make_att_2d_masks(pad_masks, att_masks)  # P:342
     position_ids = torch.cumsum(pad_masks, dim=1) - 1  # P:343
     mask4d = prepare_attention_masks_4d(att_2d)  # P:346
+    if taps is not None:  # the index work of P:219-235,342-346, for bit-exact comparison
+        taps["pad_masks"] = pad_masks
+        taps["position_ids"] = position_ids
+        taps["att_2d_masks"] = att_2d
     prefix_out, suffix_out = joint_forward(p, cfg, prefix_embs, suffix_embs, mask4d, position_ids, cond, taps)
     if taps is not None:
         taps["prefix_out"] = prefix_out

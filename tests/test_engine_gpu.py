@@ -62,6 +62,22 @@ def test_forward_matches_oracle_and_golden(name):
 
     # index / integer work: bit exact
     assert torch.equal(tap("suffix_embs", taps["suffix_embs"]), taps["suffix_embs"].float())
+    # a12 (pi0_pytorch.py:52-81,219-235,342-343): pad mask, position ids and valid-prefix count, bit exact; the 2-D mask
+    # the engine applies analytically (prefix queries see valid prefix keys, suffix queries see valid prefix keys and
+    # every suffix key) must be the reference's make_att_2d_masks on every valid query row
+    Pn = oc.num_images * T + oc.max_token_len
+    e_pad = model.get_tap("prefix_pad").cpu().view(B, Pn).bool()
+    e_pos = model.get_tap("prefix_pos").cpu().view(B, Pn).long()
+    e_nv = model.get_tap("prefix_nvalid").cpu().long()
+    assert torch.equal(e_pad, taps["pad_masks"][:, :Pn])
+    assert torch.equal(e_pos, taps["position_ids"][:, :Pn])
+    assert torch.equal(e_nv, taps["pad_masks"][:, :Pn].sum(1))
+    assert torch.equal(e_nv[:, None] + torch.arange(A), taps["position_ids"][:, Pn:])  # suffix positions (pos_mode 1)
+    analytic = torch.zeros(B, Pn + A, Pn + A, dtype=torch.bool)
+    analytic[:, :Pn, :Pn] = e_pad[:, None, :] & e_pad[:, :, None]
+    analytic[:, Pn:, :Pn] = e_pad[:, None, :].expand(B, A, Pn)
+    analytic[:, Pn:, Pn:] = True
+    assert torch.equal(analytic, taps["att_2d_masks"])
     text_rows = slice(oc.num_images * T, None)
     assert torch.equal(tap("prefix_embs", taps["prefix_embs"])[:, text_rows], taps["prefix_embs"].float()[:, text_rows])
     # floating point
@@ -126,7 +142,12 @@ def test_backward_matches_oracle_autograd(name, B):
         if n not in pr:
             assert p.grad is None  # the unused expert lm_head never gets a gradient
             continue
-        gr = pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])
+        if pr[n].grad is None:
+            # autograd leaves parameters that cannot reach the loss WITHOUT a gradient (last layer's prefix o_proj / MLP /
+            # post-norm, final prefix norm): the engine does the same, so a stock optimiser creates no state for them
+            assert p.grad is None and n in model._dead_grad_names, n
+            continue
+        gr = pr[n].grad
         assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape, n
         ref_norm = float(gr.float().norm())
         if ref_norm < 1e-5:  # mathematically-zero gradients (final prefix norm, SigLIP k bias): absolute check
@@ -238,3 +259,96 @@ def test_full_size_decode_cache_path_agrees_with_joint_path():
     assert torch.isfinite(a1).all()
     assert torch.equal(a1, a2)
     assert H.rel_err(v_cache, v_joint) < TOL_VT
+
+
+def _named_grads(model):
+    return {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def test_autograd_semantics_accumulation_stale_backward_and_interleaved_eval():
+    """What `nn.Module` callers may do around the one-stash engine: gradient accumulation and
+    zero_grad(set_to_none=False) give g1 + g2 / g exactly as autograd would; a no_grad forward, sample_actions between a
+    forward and its backward do not disturb it; a second TRAINING forward before backward raises instead of silently
+    back-propagating through the wrong stash."""
+    oc = O.tiny_config()
+    model, _ = H.build_pair(oc, seed=5)
+    model.train()
+    b1, b2 = O.synthetic_batch(oc, 2, seed=11, ragged=True), O.synthetic_batch(oc, 2, seed=12)
+    args = lambda b: (H.Obs(b, "cuda"), b["actions"].cuda(), b["noise"].cuda(), b["time"].cuda())  # noqa: E731
+
+    def grads_of(b):
+        model.zero_grad(set_to_none=True)
+        model(*args(b)).mean().backward()
+        return _named_grads(model)
+
+    g1, g2 = grads_of(b1), grads_of(b2)
+    assert set(model._dead_grad_names).isdisjoint(g1)
+    # two micro-batches without zero_grad: .grad == g1 + g2 (bf16 accumulation of the two bf16 gradients)
+    model.zero_grad(set_to_none=True)
+    model(*args(b1)).mean().backward()
+    model(*args(b2)).mean().backward()
+    acc = _named_grads(model)
+    for n in g1:
+        p = dict(model.named_parameters())[n]
+        want = (g1[n].to(p.dtype) + g2[n].to(p.dtype)).float()
+        assert torch.equal(acc[n], want), n
+    # zero_grad(set_to_none=False) then one backward: .grad == g (not 2 g)
+    model.zero_grad(set_to_none=False)
+    model(*args(b1)).mean().backward()
+    again = _named_grads(model)
+    for n in g1:
+        assert torch.equal(again[n], g1[n]), n
+    # a validation forward and a decode between forward and backward leave the training stash alone
+    model.zero_grad(set_to_none=True)
+    loss = model(*args(b1))
+    with torch.no_grad():
+        model(*args(b2))
+    model.sample_actions("cuda", H.Obs(b2, "cuda"), noise=b2["noise"].cuda())
+    loss.mean().backward()
+    inter = _named_grads(model)
+    for n in g1:
+        assert torch.equal(inter[n], g1[n]), n
+    # two training forwards, then backward of the first: refused
+    model.zero_grad(set_to_none=True)
+    l1 = model(*args(b1))
+    l2 = model(*args(b2))
+    with pytest.raises(RuntimeError, match="activation stash"):
+        l1.mean().backward()
+    l2.mean().backward()  # the latest one is still valid
+    last = _named_grads(model)
+    for n in g2:
+        assert torch.equal(last[n], g2[n]), n
+
+
+def test_engines_are_kept_per_mode_and_image_count():
+    """An AdvantageEstimator alternating 3- and 6-image calls (and train / eval calls) must not re-plan its workspace
+    each time: engines are cached by (train, num_images)."""
+    import dataclasses
+
+    from kai0_b200.pi0_pytorch import AdvantageEstimator
+
+    oc3 = dataclasses.replace(O.tiny_config(), value_head=True)
+    oc6 = dataclasses.replace(oc3, num_images=6)
+    model, _ = H.build_pair(oc3, seed=3, cls=AdvantageEstimator)
+    b3, b6 = O.synthetic_batch(oc3, 2, seed=1), O.synthetic_batch(oc6, 2, seed=2)
+    keys6 = ("base_-1_rgb", "left_wrist_-1_rgb", "right_wrist_-1_rgb", "base_0_rgb", "left_wrist_0_rgb", "right_wrist_0_rgb")
+
+    def obs_of(b, keys):
+        o = H.Obs(b, "cuda")
+        o.images = {k: b["images"][i].cuda() for i, k in enumerate(keys)}
+        o.image_masks = {k: b["img_masks"][i].cuda() for i, k in enumerate(keys)}
+        return o
+
+    o3, o6 = obs_of(b3, keys6[3:]), obs_of(b6, keys6)
+    model.eval()
+    v3a = model.sample_values("cuda", o3)
+    h3 = model._engine
+    model.sample_values("cuda", o6)
+    h6 = model._engine
+    assert h3 is not h6 and len(model._engines) == 2
+    torch.manual_seed(0)
+    v3b = model.sample_values("cuda", o3)
+    assert model._engine is h3 and len(model._engines) == 2
+    model.sample_values("cuda", o6)
+    assert model._engine is h6
+    assert v3a.shape == v3b.shape == (2, 1)

@@ -25,12 +25,18 @@ import typing
 
 import torch
 
-REF = "/root/reference/src/openpi"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the reference's `openpi` package lies: the read-only checkout of the build container, else the offline install
+# of the UNMODIFIED package under baseline/_ref (git-ignored; made by tools/stage_reference.py, which is what
+# `pip install --target baseline/_ref /root/reference` would have produced had the `hatchling` build backend been in
+# the wheelhouse) -- that copy travels to the GPU box with the snapshot, /root/reference does not.
+_CANDIDATES = ("/root/reference/src/openpi", os.path.join(_ROOT, "baseline", "_ref", "openpi"))
+REF = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "models_pytorch"))), _CANDIDATES[0])
 TR = os.path.join(REF, "models_pytorch", "transformers_replace", "models")
 
 
 def available() -> bool:
-    return os.path.isdir(REF)
+    return os.path.isdir(os.path.join(REF, "models_pytorch"))
 
 
 @dataclasses.dataclass
