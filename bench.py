@@ -3,7 +3,7 @@
     python bench.py --gpus 1 --steps K --warmup W                 # N = 1
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                    # N > 1 (NCCL, one flat all-reduce per dtype arena)
-    python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU arm (oracle port of the reference)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the CPU arm: the reference's OWN PI0Pytorch on host cores
 
 A step = what scripts/train_pytorch.py:531-561 does per iteration for BASELINE.json configs[1]
 ("pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32, 1xB200"): uint8 batch -> Observation.from_dict ->
@@ -32,6 +32,11 @@ import torch  # noqa: E402
 # forward FLOPs per sample (SURVEY.md §8d, 2 flops/MAC, block-sparse attention) and the training multiplier
 FWD_TFLOP_PER_SAMPLE = 4.674
 TRAIN_TFLOP_PER_SAMPLE = 3 * FWD_TFLOP_PER_SAMPLE
+# FLOPs the engine does NOT execute: the last joint layer's prefix-stream o_proj, MLP and prefix-query attention feed
+# nothing on the loss path (pi0_pytorch.py:350-358 keeps suffix_out only), so forward and backward skip them
+# (engine.cu joint_layer_forward `prefix_live`): 2*968*2048*2048 + 3*2*968*2048*16384 + 2*2*(968*8)*968*256 flop forward
+SKIPPED_FWD_TFLOP_PER_SAMPLE = (2 * 968 * 2048 * 2048 + 3 * 2 * 968 * 2048 * 16384 + 2 * 2 * 968 * 8 * 968 * 256) / 1e12
+EXECUTED_TRAIN_TFLOP_PER_SAMPLE = TRAIN_TFLOP_PER_SAMPLE - 3 * SKIPPED_FWD_TFLOP_PER_SAMPLE
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 
@@ -165,108 +170,86 @@ def to_device(d, actions, dev):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference, timed on the host cores (cpu_baseline / --impl reference)
+# CPU arm: the reference's OWN PI0Pytorch training step timed on the host cores (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------------------
-# forward TFLOP per sample of the pieces of the path, used to scale the bounded CPU sample
-_TF_VIT_LAYER = 0.6605 / 27          # all three cameras, one SigLIP layer
-_TF_JOINT_LAYER = (3.8368 + 0.0311 + 0.1457) / 18   # one joint PaliGemma + expert layer incl. attention
-_TF_REST = 0.0003 + 3 * 0.0012       # adaRMS / heads / projector (not depth-scaled)
+def _reference_runner():
+    """tools/reference_runner.py when the reference package is reachable (/root/reference in the build container, the
+    offline install under baseline/_ref on the GPU box), else None."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import reference_runner as RR
+    except Exception:  # noqa: BLE001
+        return None
+    return RR if RR.available() else None
 
 
-_LAST_CPU_DECODE = None  # filled by cpu_reference: CPU timing of the decode metric (reported beside `decode`)
+def cpu_reference(host_d, host_a, steps: int, warmup: int, budget_s: float, whole_first: bool):
+    """The reference's own training step (train_pytorch.py:540-561: forward with its own augmentation and per-layer
+    gradient checkpointing, backward, clip_grad_norm_, torch.optim.AdamW) on the host cores, B = 1 per step.
+    whole_first: the first warm-up step is ONE WHOLE untruncated sample (measured and reported); if K + W whole samples
+    do not fit the budget, the timed steps run the same reference model truncated in depth and are scaled by the stated
+    FLOP ratio (tools/reference_runner.time_cpu).  Returns the runner's dict, or the oracle port's if the reference is
+    not reachable (kind "port")."""
+    RR = _reference_runner()
+    if RR is not None:
+        if whole_first:
+            info = RR.time_cpu(host_d, host_a, steps, warmup, budget_s)
+        else:
+            info = RR.time_cpu_bounded(host_d, host_a, steps, warmup, depth=1, vit=2)
+        info["kind"] = "reference"
+        return info
+    return _cpu_port(steps, warmup, budget_s)
 
 
-def _pick_cpu_threads() -> int:
-    """All the host threads the port can USE: torch's bf16 CPU GEMM gets slower when oversubscribed on many-thread hosts
-    (128 threads: 3.5x slower than 8 on the same pass), so a ~1 s probe picks the fastest of a few thread counts."""
-    n = os.cpu_count() or 1
-    cands = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
-    a = (torch.randn(968, 2048) * 0.1).to(torch.bfloat16)
-    w = (torch.randn(4096, 2048) * 0.02).to(torch.bfloat16)
-    best, best_t = n, float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        torch.nn.functional.linear(a, w)
-        t0 = time.time()
-        for _ in range(3):
-            torch.nn.functional.linear(a, w)
-        dt = time.time() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    return best
-
-
-def cpu_reference(steps: int, warmup: int, budget_s: float, full: bool = True):
-    """Times the oracle port of the reference on all host threads on a BOUNDED sample of the workload: forward +
-    backward (torch.autograd) of ONE sample through the full-width architecture truncated to 1 of 27 SigLIP layers and
-    1 of 18 joint Gemma layers (same tensor shapes, same kernels per layer), scaled to a whole sample by the FLOP
-    ratio of SURVEY.md §8d.  A whole sample is ~14 TFLOP and takes minutes per pass on host cores.
-    Returns (samples_per_sec, cores, sample_description, steps_done)."""
+def _cpu_port(steps: int, warmup: int, budget_s: float):
+    """Fallback when no reference package is reachable: forward + backward of the oracle port (oracle/pi05_oracle.py) at
+    full widths, truncated to 1 of 27 SigLIP and 1 of 18 joint layers, scaled by the FLOP ratio."""
     import dataclasses
 
     from oracle import pi05_oracle as O
 
-    cores = _pick_cpu_threads()
-    torch.set_num_threads(cores)
-    if full:
-        base_cfg = O.OracleConfig()
-        dv, dg = 1, 1
-        oc = dataclasses.replace(base_cfg, vit_depth=dv,
-                                 paligemma=dataclasses.replace(base_cfg.paligemma, depth=dg),
-                                 expert=dataclasses.replace(base_cfg.expert, depth=dg))
-        frac = (dv * _TF_VIT_LAYER + dg * _TF_JOINT_LAYER + _TF_REST) / FWD_TFLOP_PER_SAMPLE
-    else:
-        oc = O.tiny_config()
-        frac = 1.0
-    params = {}
-    # values do not matter for timing: tile a 4M-element N(0, 0.02) pattern (bf16 normal_ on CPU is very slow)
+    threads = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
+    base_cfg = O.OracleConfig()
+    oc = dataclasses.replace(base_cfg, vit_depth=1, paligemma=dataclasses.replace(base_cfg.paligemma, depth=1),
+                             expert=dataclasses.replace(base_cfg.expert, depth=1))
+    frac = (0.6605 / 27 + (3.8368 + 0.0311 + 0.1457) / 18 + 0.0039) / FWD_TFLOP_PER_SAMPLE
     base = {torch.bfloat16: (torch.randn(1 << 22) * 0.02).to(torch.bfloat16), torch.float32: torch.randn(1 << 22) * 0.02}
+    params = {}
     for name, (shape, dt) in O.param_specs(oc).items():
         n = 1
-        for s in shape:
-            n *= s
-        reps = (n + (1 << 22) - 1) >> 22
-        params[name] = base[dt].repeat(reps)[:n].view(shape).clone().requires_grad_(True)
+        for d in shape:
+            n *= d
+        params[name] = base[dt].repeat((n + (1 << 22) - 1) >> 22)[:n].view(shape).clone().requires_grad_(True)
     b = O.synthetic_batch(oc, 1)
 
     def one():
         for p in params.values():
             p.grad = None
-        loss = O.forward_loss(params, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"],
-                              b["noise"], b["time"])
-        loss.mean().backward()
+        O.forward_loss(params, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["actions"], b["noise"],
+                       b["time"]).mean().backward()
 
-    t0 = time.time()
-    one()  # first pass doubles as warm-up and cost probe
-    t_first = time.time() - t0
-    done_warm = 1
-    while done_warm < warmup and (time.time() - t0) + t_first * (1 + steps) < budget_s:
+    for _ in range(max(warmup, 1)):
         one()
-        done_warm += 1
-    k = max(1, min(steps, int((budget_s - (time.time() - t0)) / max(t_first, 1e-3))))
     t1 = time.time()
-    for _ in range(k):
+    for _ in range(steps):
         one()
-    dt = (time.time() - t1) / k
-    # secondary metric beside it: the 10-step action decode on the same truncated architecture, scaled by decode FLOPs
-    # (SURVEY §8d: prefix pass 4.635 TFLOP = SigLIP 0.6605 + PaliGemma 3.84 + rest, 10 steps x 0.0389 expert)
-    global _LAST_CPU_DECODE
-    _LAST_CPU_DECODE = None
-    if full and (time.time() - t0) < budget_s:
-        dfrac = (oc.vit_depth * 0.6605 / 27 + oc.paligemma.depth * (3.84 + 10 * 0.0389) / 18 + 0.13) / 5.024
-        with torch.no_grad():
-            td = time.time()
-            O.sample_actions({k: v.detach() for k, v in params.items()}, oc, b["images"], b["img_masks"], b["tokens"],
-                             b["token_mask"], b["noise"])
-            td = time.time() - td
-        _LAST_CPU_DECODE = {"decode_ms_scaled": 1e3 * td / dfrac, "measured_s": td, "flop_fraction": dfrac,
-                            "sample": "sample_actions (10 steps, B=1) of the same truncated oracle, one pass, scaled by "
-                                      "the decode FLOP ratio"}
-    desc = (f"B=1 forward+backward of the oracle port, full widths, truncated to {oc.vit_depth}/27 SigLIP and "
-            f"{oc.paligemma.depth}/18 joint Gemma layers ({100 * frac:.1f} % of a sample's FLOPs: {dt:.1f} s per pass), "
-            f"scaled to a whole sample by that ratio; {k} timed pass(es) after {done_warm} warm-up, {cores} threads, "
-            "bf16 weights as the reference") if full else f"tiny debug architecture, {k} passes"
-    return frac / dt, cores, desc, k
+    dt = (time.time() - t1) / max(steps, 1)
+    return {"kind": "port", "threads": threads, "mode": "bounded", "s_per_step": dt, "samples_per_s": frac / dt,
+            "scale": frac, "sample": f"oracle PORT (no reference package reachable): B=1 forward+backward truncated to 1/27 "
+                                     f"SigLIP + 1/18 joint layers = {100 * frac:.1f} % of a sample's FLOPs, scaled; "
+                                     f"{threads} threads"}
+
+
+def bench_config(world: int, B: int, small: bool):
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": ("pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32 per GPU (BASELINE.json configs[1]; configs[2] "
+                         "at N=8)") if not small else "DEBUG small architecture (invalid as a bench number)",
+            "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+            "step": "uint8 batch -> Observation.from_dict -> forward (train-time augmentation on) -> backward -> gradient "
+                    "all-reduce (N>1) -> clip_grad_norm_(1.0) -> AdamW(0.9, 0.95, eps 1e-8, wd 1e-10, state in the parameter "
+                    "dtype) -> zero_grad  (scripts/train_pytorch.py:531-561)",
+            "l2": "per-step activations (>100 GB) and weights (7 GB) far exceed the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -277,7 +260,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]/[2]: 32)")
-    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the CPU legs may take")
+    ap.add_argument("--ref-budget", type=float, default=420.0,
+                    help="--impl reference: seconds the whole run (build + warm-up + K steps) should stay within")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: exchange the gradients after backward (two torch.distributed all-reduces) instead of the "
+                         "engine's overlapped chunked exchange")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the reference_gpu anchor (the reference's own eager module timed on this GPU, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug: tiny architecture (not a valid bench number)")
     ap.add_argument("--per-param-optimizer", action="store_true",
@@ -299,26 +288,30 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = "pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32 per GPU (BASELINE.json configs[1]; configs[2] at N=8)"
 
     # ---------------------------------------------------------------- CPU arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sps, cores, desc, k = cpu_reference(args.steps, min(args.warmup, 1), max(60.0, args.cpu_budget * 1.5),
-                                            full=not args.small)
-        line = {
-            "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": "weak",
+        host_d, host_a = make_host_batch(args.batch, 0, pin=False)
+        info = cpu_reference(host_d, host_a, args.steps, args.warmup, args.ref_budget, whole_first=not args.small)
+        sps = info["samples_per_s"]
+        cb = {"value": sps, "unit": UNIT, "cores": info["threads"], "kind": info["kind"], "sample": info["sample"],
+              "mode": info["mode"], "flop_fraction_per_step": info["scale"], "measured_s_per_step": info["s_per_step"]}
+        for k in ("first_whole_sample_step_s", "measured_whole_sample_samples_per_s", "build_s"):
+            if k in info:
+                cb[k] = info[k]
+        emit({
+            "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * info["s_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "note": "reference's PyTorch path cannot be imported (needs patched "
-                       "transformers 4.53.2 + jax); this is its CPU oracle port (oracle/pi05_oracle.py)"},
-            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "config": bench_config(args.gpus, args.batch, args.small),
+            "implementation": "the reference's own PI0Pytorch (executed in place, unmodified) on the host CPU; each step = one "
+                              "sample (B = 1) of the B = 32 workload, see cpu_baseline.sample; ms_per_step is the measured "
+                              "time of that step, value = flop_fraction_per_step / measured_s_per_step",
+            "cpu_baseline": cb,
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }
-        if _LAST_CPU_DECODE is not None:
-            line["cpu_baseline"]["decode"] = _LAST_CPU_DECODE
-        emit(line)
+        })
         return 0
 
     # ---------------------------------------------------------------- B200 arm
@@ -347,12 +340,14 @@ def main():
     model.check_inputs = False
     model.direct_grads = True  # public knob: .grad = views of the flat gradient arena (no per-parameter autograd copies)
     model.train()
+    use_fused = not (args.per_param_optimizer or args.torch_optimizer)
     if world > 1:
-        model.enable_flat_allreduce()
+        # engine-owned exchange: chunked ncclAllReduce overlapped with backward; with the fused optimiser the 1/world
+        # average is folded into the update instead of a separate pass over the 7 GB of gradients
+        model.enable_flat_allreduce(overlap=not args.no_overlap, average="optimizer" if use_fused else "in_place")
     # optimiser over the two flat arenas (public opt-in): element-wise identical to the per-parameter
     # AdamW / global-norm clip of train_pytorch.py:469-475,557, in 2 tensors instead of ~700
     params = model.flat_parameters() if not args.per_param_optimizer else [p for p in model.parameters() if p.requires_grad]
-    use_fused = not (args.per_param_optimizer or args.torch_optimizer)
     if use_fused:
         from kai0_b200.optim import FusedClipAdamW
 
@@ -421,6 +416,8 @@ def main():
         step(False)
     step(True)
     barrier()
+    # each timed region gets its own clock samples: on a power-capped part the SM clock drifts between back-to-back
+    # regions, so `value` and `e2e` are only comparable together with the clocks they ran at
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -429,27 +426,44 @@ def main():
     ms_dev, _ = timed(args.steps, False)
     n1 = lib.pi05_launch_count()
     lib.pi05_gemm_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
     buf = C.create_string_buffer(1 << 16)
     lib.pi05_gemm_profile_report(buf, len(buf))
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
     ms_e2e, last_loss = timed(args.steps, True)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks_e2e = sampler2.stop() if rank == 0 else None
 
-    if world > 1 and os.environ.get("PI05_BENCH_VERBOSE"):
-        # cost of the exchange step alone (the two flat all-reduces + the 1/world scaling), all ranks in lock-step
+    exchange = None
+    if world > 1:
+        # the exchange step ALONE on an otherwise idle GPU (one-shot C-ABI entry, same communicator): its cost if it were
+        # not overlapped, and the NCCL bus bandwidth it reaches
         barrier()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        for i in range(3):
-            ev[i].record()
-            model._allreduce_flat_grads()
-        ev[3].record()
+        h = model._train_engine_handle()
+        comm = model._dp_comm
+        calls, nbytes = C.c_int64(), C.c_int64()
+        if comm is not None and h is not None:
+            lib.pi05_grad_exchange_stats(h, C.byref(calls), C.byref(nbytes))
+            overl_calls, payload = calls.value, nbytes.value
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.pi05_allreduce_grads(h, comm, world, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                           "pi05_allreduce_grads")
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = torch.tensor([min(ts)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            exchange = {"payload_gb": payload / 1e9, "collectives_per_backward": overl_calls, "max_ctas": model._dp_max_ctas,
+                        "standalone_ms": ms, "standalone_algbw_gbs": payload / 1e9 / (ms / 1e3),
+                        "standalone_busbw_gbs": 2.0 * (world - 1) / world * payload / 1e9 / (ms / 1e3),
+                        "note": "standalone = the same payload as ONE un-overlapped exchange on an idle GPU through this "
+                                "communicator (few CTAs by design); in the step it runs chunk by chunk under backward"}
         barrier()
-        if rank == 0:
-            nbytes = sum(g.numel() * g.element_size() for g in model._flat_grad.values() if g is not None)
-            nbytes -= 2 * (model._flat_grad[torch.bfloat16].numel() - model._offsets[
-                "paligemma_with_expert.gemma_expert.lm_head.weight"][1])  # the unused lm_head is not exchanged
-            ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
-            print(f"  [allreduce] {nbytes / 1e9:.2f} GB of gradients: {ts} ms -> "
-                  f"{nbytes / 1e9 / (min(ts) / 1e3):.0f} GB/s algorithmic", file=sys.stderr)
 
     if rank == 0 and os.environ.get("PI05_TORCH_PROFILE"):
         # low-overhead per-kernel breakdown of ONE step (CUPTI via torch.profiler): where the non-GEMM time goes
@@ -529,34 +543,54 @@ def main():
                 "peak_source": f"{peaks_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                 "all_tcgen05_gemms": {"tflops": gemm_flop / (gemm_ms / 1e3) / 1e12 if gemm_ms else None,
                                       "share_of_step": gemm_ms / ms_dev},
+                # model FLOPs (14.02 TFLOP per trained sample, dead last-layer prefix work included) and the
+                # FLOPs the engine actually executes (that work is skipped: 13.39 TFLOP), both against the same peak
                 "step_model_flops_utilisation": (value / world) * TRAIN_TFLOP_PER_SAMPLE / peak_tf,
+                "step_hardware_flops_utilisation": (value / world) * EXECUTED_TRAIN_TFLOP_PER_SAMPLE / peak_tf,
+                "tflop_per_sample": {"model": TRAIN_TFLOP_PER_SAMPLE, "executed": EXECUTED_TRAIN_TFLOP_PER_SAMPLE},
             }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload if not args.small else "DEBUG small architecture (invalid as a bench number)",
-                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "optimizer": ("kai0_b200.optim.FusedClipAdamW: clip_grad_norm_(1.0) + AdamW(0.9,0.95,1e-8,wd 1e-10) "
-                                     "over the 2 flat arenas in one engine pass" if use_fused else
-                                     "torch.optim.AdamW(fused) + clip_grad_norm_(1.0) as scripts/train_pytorch.py, over "
-                                     + ("model.parameters()" if args.per_param_optimizer
-                                        else "model.flat_parameters() (2 flat arenas)")),
-                       "l2": "per-step activations (>100 GB) and weights (7 GB) far exceed the 126 MB L2; no flush needed"},
+            "config": bench_config(world, B, args.small),
+            "implementation": {
+                "engine": "kai0_b200/libpi05.so (hand-written sm_100a kernels) behind kai0_b200.pi0_pytorch.PI0Pytorch",
+                "optimizer": ("kai0_b200.optim.FusedClipAdamW: the clip + AdamW of the step in one engine pass over the 2 "
+                              "flat arenas" if use_fused else
+                              "torch.optim.AdamW(fused) + clip_grad_norm_(1.0) over "
+                              + ("model.parameters()" if args.per_param_optimizer else "model.flat_parameters()")),
+                "gradient_exchange": None if world == 1 else model.exchange_description(), "exchange": exchange},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host_d, host_a),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss,
+                    "clocks": clocks_e2e},
             "gpu_launches": int(n1 - n0),
             "decode": decode,
             "clocks": clocks,
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1:
+            # free the engine (108 GB of workspace) before the reference legs
             del optim
+            model._destroy_engine()
+            del model
             torch.cuda.empty_cache()
-            sps, cores, desc, _ = cpu_reference(1, 0, args.cpu_budget, full=not args.small)
-            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-            if _LAST_CPU_DECODE is not None:
-                line["cpu_baseline"]["decode"] = _LAST_CPU_DECODE
+        if world == 1 and not args.no_cpu_baseline:
+            info = cpu_reference(host_d, host_a, 2, 1, 0.0, whole_first=False)
+            line["cpu_baseline"] = {"value": info["samples_per_s"], "unit": UNIT, "cores": info["threads"],
+                                    "kind": info["kind"], "sample": info["sample"],
+                                    "flop_fraction_per_step": info["scale"], "measured_s_per_step": info["s_per_step"],
+                                    "note": "`bench.py --impl reference` additionally times one WHOLE sample"}
+        if world == 1 and not args.no_reference_gpu and not args.small:
+            RR = _reference_runner()
+            if RR is None:
+                line["reference_gpu"] = {"unavailable": "no reference package reachable (/root/reference or baseline/_ref)"}
+            else:
+                try:
+                    line["reference_gpu"] = RR.time_gpu(host_d, host_a, dev, steps=3, warmup=2, batch=B)
+                    line["reference_gpu"]["speedup_of_this_engine"] = value / line["reference_gpu"]["value"]
+                except Exception as exc:  # noqa: BLE001
+                    line["reference_gpu"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         emit(line)
     if world > 1:
         dist.barrier()

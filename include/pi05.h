@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PI05_ABI_VERSION 1
+#define PI05_ABI_VERSION 2
 
 typedef struct pi05_engine pi05_engine; /* opaque */
 
@@ -177,6 +177,42 @@ int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_bf16, void* 
                           const float* g_f32, float* m_f32, float* v_f32, int64_t n_f32, float lr, float beta1,
                           float beta2, float eps, float weight_decay, int64_t step, float max_norm, float* scratch,
                           void* stream);
+
+/* Same, with a gradient pre-scale: the arenas hold SUMS over `1 / grad_scale` data-parallel ranks (pi05_set_grad_exchange
+ * with average_in_place = 0) and the averaged gradient DDP would have produced, bf(g * grad_scale), is taken on the fly
+ * (norm, clip and update all see the averaged value; scratch[0] = norm of the AVERAGED gradient). */
+int pi05_fused_clip_adamw_scaled(void* p_bf16, const void* g_bf16, void* m_bf16, void* v_bf16, int64_t n_bf16, float* p_f32,
+                                 const float* g_f32, float* m_f32, float* v_f32, int64_t n_f32, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int64_t step, float max_norm,
+                                 float grad_scale, float* scratch, void* stream);
+
+/* ---- data-parallel gradient exchange: replaces DistributedDataParallel's bucketed all-reduce
+ * (scripts/train_pytorch.py:440-447) ----------------------------------------------------------------------------
+ * `nccl_comm` is an ncclComm_t created by the caller over the data-parallel ranks (libnccl is resolved at run time with
+ * dlopen: the library has no link-time NCCL dependency).
+ *
+ * pi05_set_grad_exchange: from now on pi05_backward itself exchanges the gradients, OVERLAPPED with the rest of backward:
+ * as soon as the kernels producing one contiguous group of the gradient arena (an expert layer, a PaliGemma layer, the fp32
+ * norm / adaRMS / head block, the embedding table, groups of SigLIP layers) are enqueued, a ncclAllReduce(sum) of that range
+ * is enqueued on an engine-owned high-priority stream behind an event; at the end of pi05_backward the caller's stream
+ * waits for the exchange stream.  average_in_place != 0: every range is also multiplied by 1 / nranks on the exchange
+ * stream (what DDP's averaging leaves in .grad); 0: the arenas hold sums and the caller folds 1 / nranks into its
+ * optimiser (pi05_fused_clip_adamw_scaled).  nccl_comm = NULL switches the exchange off again.
+ * The tcgen05 GEMMs schedule tiles dynamically, so the few SMs the NCCL kernels occupy cost their share and no more.
+ *
+ * pi05_allreduce_grads: the same exchange as ONE blocking-order step on `stream` after pi05_backward (no overlap): sum
+ * all-reduce of both gradient arenas (the never-used expert lm_head excluded), then 1 / nranks when average != 0. */
+int pi05_set_grad_exchange(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_t average_in_place);
+int pi05_allreduce_grads(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_t average, void* stream);
+/* Communicator helpers for hosts without an NCCL binding of their own (the Python host uses them through ctypes):
+ * rank 0 calls pi05_nccl_unique_id (128 bytes out) and ships the id to every rank by its own means (torch.distributed's
+ * store here); every rank then calls pi05_nccl_comm_create (collective).  max_ctas > 0 bounds the SMs the communicator's
+ * kernels may occupy (ncclConfig_t.maxCTAs); 0 = NCCL's default. */
+int pi05_nccl_unique_id(void* out128);
+int pi05_nccl_comm_create(const void* unique_id128, int32_t nranks, int32_t rank, int32_t max_ctas, void** comm_out);
+int pi05_nccl_comm_destroy(void* comm);
+/* Statistics of the last pi05_backward's exchange: *calls = ncclAllReduce launches, *bytes = payload bytes. */
+int pi05_grad_exchange_stats(pi05_engine* e, int64_t* calls, int64_t* bytes);
 
 /* ---- instrumentation (bench.py): kernel-launch counter and per-launch CUDA-event timing of the GEMM -------- */
 unsigned long long pi05_launch_count(void);

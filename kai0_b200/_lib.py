@@ -129,6 +129,13 @@ EXPORTS = (
     "pi05_debug_set_pdl",
     "pi05_gemm_bf16",
     "pi05_fused_clip_adamw",
+    "pi05_fused_clip_adamw_scaled",
+    "pi05_set_grad_exchange",
+    "pi05_allreduce_grads",
+    "pi05_grad_exchange_stats",
+    "pi05_nccl_unique_id",
+    "pi05_nccl_comm_create",
+    "pi05_nccl_comm_destroy",
     "pi05_launch_count",
     "pi05_gemm_profile_enable",
     "pi05_gemm_profile_report",
@@ -206,6 +213,24 @@ def lib() -> C.CDLL:
                 [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5
                 + [C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
             )
+            l.pi05_fused_clip_adamw_scaled.restype = C.c_int
+            l.pi05_fused_clip_adamw_scaled.argtypes = (
+                [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5
+                + [C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+            )
+        if hasattr(l, "pi05_set_grad_exchange"):
+            l.pi05_set_grad_exchange.restype = C.c_int
+            l.pi05_set_grad_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+            l.pi05_allreduce_grads.restype = C.c_int
+            l.pi05_allreduce_grads.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+            l.pi05_grad_exchange_stats.restype = C.c_int
+            l.pi05_grad_exchange_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            l.pi05_nccl_unique_id.restype = C.c_int
+            l.pi05_nccl_unique_id.argtypes = [C.c_void_p]
+            l.pi05_nccl_comm_create.restype = C.c_int
+            l.pi05_nccl_comm_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+            l.pi05_nccl_comm_destroy.restype = C.c_int
+            l.pi05_nccl_comm_destroy.argtypes = [C.c_void_p]
         _lib = l
         return _lib
 

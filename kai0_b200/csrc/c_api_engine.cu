@@ -99,7 +99,39 @@ int pi05_create(const pi05_config* cfg, int device, void* workspace, size_t work
   return 0;
 }
 
-void pi05_destroy(pi05_engine* e) { delete E(e); }
+void pi05_destroy(pi05_engine* e) {
+  if (e) pi05::exchange_destroy(*E(e));
+  delete E(e);
+}
+
+int pi05_set_grad_exchange(pi05_engine* pe, void* nccl_comm, int32_t nranks, int32_t average_in_place) {
+  Engine* e = E(pe);
+  if (!e) {
+    pi05::set_error("pi05_set_grad_exchange: null engine");
+    return 1;
+  }
+  return pi05::exchange_setup(*e, nccl_comm, nranks, average_in_place);
+}
+
+int pi05_allreduce_grads(pi05_engine* pe, void* nccl_comm, int32_t nranks, int32_t average, void* stream) {
+  Engine* e = E(pe);
+  if (!e) {
+    pi05::set_error("pi05_allreduce_grads: null engine");
+    return 1;
+  }
+  return pi05::exchange_all(*e, nccl_comm, nranks, average, static_cast<cudaStream_t>(stream));
+}
+
+int pi05_grad_exchange_stats(pi05_engine* pe, int64_t* calls, int64_t* bytes) {
+  Engine* e = E(pe);
+  if (!e) {
+    pi05::set_error("pi05_grad_exchange_stats: null engine");
+    return 1;
+  }
+  if (calls) *calls = e->xch.calls;
+  if (bytes) *bytes = e->xch.bytes;
+  return 0;
+}
 
 int pi05_bind_params(pi05_engine* pe, const pi05_param* params, int n) {
   Engine* e = E(pe);

@@ -6,6 +6,7 @@
 //   transformers_replace/models/siglip/modeling_siglip.py:271-282,435-481,763-796 (vision tower),
 //   transformers_replace/models/paligemma/modeling_paligemma.py:91-99,232-247 (projector).
 // Every bf16 GEMM runs on the tcgen05 kernel of gemm_sm100.cu; everything else is in *_kernels.cu.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -459,6 +460,87 @@ int engine_resolve_params(Engine& e) {
                                    Bz(j).g<float>() != Bz(0).g<float>() + j * e.ada_bstride))
           e.ada_uniform_grad = false;
       }
+    }
+  }
+  // ---- contiguous gradient groups for the overlapped data-parallel exchange (exchange.h), in arena order; verified to
+  // tile [first trainable bf16 gradient, end of the last one) / the fp32 arena without overlap
+  {
+    GradExchange& x = e.xch;
+    auto span = [](std::initializer_list<const PRef*> ps, int dtype) {
+      GRange r;
+      r.dtype = dtype;
+      const int esz = dtype == PI05_BF16 ? 2 : 4;
+      for (const PRef* p : ps) {
+        if (p->grad == nullptr) return GRange{};
+        char* lo = static_cast<char*>(p->grad);
+        char* hi = lo + p->numel * esz;
+        if (r.lo == nullptr || lo < r.lo) r.lo = lo;
+        if (hi > r.hi) r.hi = hi;
+      }
+      return r;
+    };
+    x.pg.clear();
+    x.ex.clear();
+    x.vit.clear();
+    const int BFt = PI05_BF16, Ft = PI05_F32;
+    for (auto& p : e.pg) x.pg.push_back(span({&p.q_w, &p.k_w, &p.v_w, &p.o_w, &p.gate_w, &p.up_w, &p.down_w}, BFt));
+    for (auto& p : e.ex) x.ex.push_back(span({&p.q_w, &p.k_w, &p.v_w, &p.o_w, &p.gate_w, &p.up_w, &p.down_w}, BFt));
+    for (auto& p : e.vit)
+      x.vit.push_back(span({&p.ln1_w, &p.ln1_b, &p.ln2_w, &p.ln2_b, &p.q_w, &p.k_w, &p.v_w, &p.q_b, &p.k_b, &p.v_b, &p.out_w,
+                            &p.out_b, &p.fc1_w, &p.fc1_b, &p.fc2_w, &p.fc2_b}, BFt));
+    x.vtail = span({&e.post_ln_w, &e.post_ln_b, &e.proj_w, &e.proj_b}, BFt);
+    x.embed = span({&e.embed}, BFt);
+    x.f32_vis = span({&e.patch_w, &e.patch_b, &e.pos_emb}, Ft);
+    std::vector<const PRef*> f32;
+    for (auto& p : e.pg) { f32.push_back(&p.in_w); f32.push_back(&p.post_w); }
+    for (auto& p : e.ex) { f32.push_back(&p.in_dw); f32.push_back(&p.in_db); f32.push_back(&p.post_dw); f32.push_back(&p.post_db); }
+    for (const PRef* p : {&e.pg_norm_w, &e.ex_norm_dw, &e.ex_norm_db, &e.ain_w, &e.ain_b, &e.aout_w, &e.aout_b, &e.tin_w,
+                          &e.tin_b, &e.tout_w, &e.tout_b})
+      f32.push_back(p);
+    if (c.value_head)
+      for (const PRef* p : {&e.vh0_w, &e.vh0_b, &e.vh2_w, &e.vh2_b, &e.vh4_w, &e.vh4_b}) f32.push_back(p);
+    x.f32_main = GRange{};
+    x.f32_main.dtype = Ft;
+    bool f32_ok = true;
+    for (const PRef* p : f32) {
+      if (p->grad == nullptr) { f32_ok = false; break; }
+      char* lo = static_cast<char*>(p->grad);
+      char* hi = lo + p->numel * 4;
+      if (x.f32_main.lo == nullptr || lo < x.f32_main.lo) x.f32_main.lo = lo;
+      if (hi > x.f32_main.hi) x.f32_main.hi = hi;
+    }
+    if (!f32_ok) x.f32_main = GRange{};
+    // verification: bf16 groups sorted by address must not overlap and may only be separated by alignment padding
+    std::vector<GRange> all = x.pg;
+    all.insert(all.end(), x.ex.begin(), x.ex.end());
+    all.insert(all.end(), x.vit.begin(), x.vit.end());
+    all.push_back(x.vtail);
+    all.push_back(x.embed);
+    bool ok = f32_ok && x.f32_vis.valid();
+    for (auto& r : all) ok = ok && r.valid();
+    if (ok) {
+      std::sort(all.begin(), all.end(), [](const GRange& a, const GRange& b) { return a.lo < b.lo; });
+      for (size_t i = 1; i < all.size(); ++i)
+        if (all[i].lo < all[i - 1].hi || all[i].lo - all[i - 1].hi > 64) ok = false;
+      // the fp32 pieces: vision embeddings first, then everything else, disjoint
+      if (!(x.f32_vis.hi <= x.f32_main.lo || x.f32_main.hi <= x.f32_vis.lo)) ok = false;
+    }
+    x.chunked = ok;
+    x.all_bf16 = GRange{};
+    x.all_f32 = GRange{};
+    if (!all.empty() && all.front().valid() && e.embed.grad != nullptr) {
+      x.all_bf16.dtype = BFt;
+      x.all_bf16.lo = all.front().lo;
+      x.all_bf16.hi = all.back().hi;
+      for (auto& r : all) {
+        if (r.lo < x.all_bf16.lo) x.all_bf16.lo = r.lo;
+        if (r.hi > x.all_bf16.hi) x.all_bf16.hi = r.hi;
+      }
+    }
+    if (x.f32_main.valid() && x.f32_vis.valid()) {
+      x.all_f32.dtype = Ft;
+      x.all_f32.lo = x.f32_vis.lo < x.f32_main.lo ? x.f32_vis.lo : x.f32_main.lo;
+      x.all_f32.hi = x.f32_vis.hi > x.f32_main.hi ? x.f32_vis.hi : x.f32_main.hi;
     }
   }
   e.bound = true;

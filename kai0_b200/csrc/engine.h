@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/pi05.h"
+#include "exchange.h"
 #include "kernels.h"
 
 namespace pi05 {
@@ -133,6 +134,7 @@ struct Engine {
   float w_action = 1.0f, w_value = 0.0f;
   float* splitk_ws = nullptr;  // fp32 scratch of the small-M split-K GEMM path
   size_t splitk_ws_bytes = 0;
+  GradExchange xch;  // data-parallel gradient exchange overlapped with backward (exchange.h)
   bool taps_enabled = false;
   int profile_layer = -1;  // pi05_debug_profile_layer
   std::map<std::string, Tap> taps;

@@ -5,6 +5,7 @@
 //
 // Gradient buffers are overwritten, never accumulated (the caller's zero_grad(set_to_none=True) semantics,
 // train_pytorch.py:561).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 
@@ -327,14 +328,26 @@ static int vision_backward(Engine& e, int B) {
                 st);
   cast_f32_to_bf16(acc, e.post_ln_w.g<bf16>(), W, st);
   cast_f32_to_bf16(acc + W, e.post_ln_b.g<bf16>(), W, st);
+  CHECK_RC(exchange_range(e, e.xch.vtail));  // post-LN + projector gradients are final
+  constexpr int kVitGroup = 3;  // SigLIP layers per collective (~90 MB)
   for (int l = c.vit_depth - 1; l >= 0; --l) {
     if (l == e.profile_layer) cudaProfilerStart();
     CHECK_RC(vit_layer_backward(e, l, B));
     if (l == e.profile_layer) cudaProfilerStop();
+    if (l % kVitGroup == 0 && e.xch.comm != nullptr && e.xch.chunked) {
+      const int top = std::min(l + kVitGroup - 1, c.vit_depth - 1);  // layers [l, top] are contiguous in the arena
+      GRange r = e.xch.vit[l];
+      for (int j = l + 1; j <= top; ++j) {
+        if (e.xch.vit[j].lo < r.lo) r.lo = e.xch.vit[j].lo;
+        if (e.xch.vit[j].hi > r.hi) r.hi = e.xch.vit[j].hi;
+      }
+      CHECK_RC(exchange_range(e, r));
+    }
   }
   // patch embedding: fp32 weight / bias / position-embedding gradients (modeling_siglip.py:271-282)
   patch_embed_bwd(e.batch_copy.images, e.g_x1, e.patch_w.g<float>(), e.patch_b.g<float>(), e.pos_emb.g<float>(), nullptr,
                   nimg, c.image_size, c.vit_patch, W, st);
+  CHECK_RC(exchange_range(e, e.xch.f32_vis));
   return 0;
 }
 
@@ -351,6 +364,7 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
     return 8;
   }
   e.stream = st;
+  exchange_begin(e);
   const pi05_config& c = e.cfg;
   const int B = e.B, A = e.A, E = e.E, D = e.D, ad = c.action_dim, depth = c.paligemma.depth;
   const int M2 = B * A;
@@ -398,6 +412,9 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
     if (l == e.profile_layer) cudaProfilerStart();
     CHECK_RC(joint_layer_backward(e, l, B, /*g1_zero=*/l == depth - 1));
     if (l == e.profile_layer) cudaProfilerStop();
+    // this layer's bf16 weight gradients (both streams) are final: hand them to the exchange stream
+    CHECK_RC(exchange_range(e, e.xch.ex[l]));
+    CHECK_RC(exchange_range(e, e.xch.pg[l]));
   }
   if (depth == 0) fill_zero(e.g_x1, static_cast<size_t>(B) * e.P * D * 2, st);
   // ---- suffix front-end: action_in_proj, adaRMS dense layers, time MLP
@@ -423,11 +440,14 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st) {
   linear_f32_dgrad(e.g_f32c, e.tout_w.d<float>(), e.g_f32a, B, E, E, 0, st);  // d t1s
   silu_bwd(e.g_f32a, e.t1, e.g_f32c, static_cast<int64_t>(B) * E, st);        // d t1
   linear_f32_wgrad(e.g_f32c, e.temb, e.tin_w.g<float>(), e.tin_b.g<float>(), B, E, E, st);
+  CHECK_RC(exchange_range(e, e.xch.f32_main));  // norms, adaRMS dense, heads: every fp32 gradient but the patch embedding
   // ---- prefix: token embedding table (dense bf16 gradient, padding_idx 0 excluded) and the vision tower
   fill_zero(e.embed.grad, static_cast<size_t>(c.vocab_size) * D * 2, st);
   embed_tokens_bwd(e.batch_copy.tokens, e.g_x1, static_cast<int64_t>(e.P) * D, e.NI * e.T, e.embed.g<bf16>(),
                    e.g_embed_scratch, e.g_first, B, e.L, D, static_cast<float>(sqrt(static_cast<double>(D))), st);
+  CHECK_RC(exchange_range(e, e.xch.embed));
   CHECK_RC(vision_backward(e, B));
+  CHECK_RC(exchange_finish(e));
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     snprintf(e.err, sizeof(e.err), "pi05_backward: %s", cudaGetErrorString(ce));

@@ -10,6 +10,14 @@
 //   empty[s]  (count 1, per CTA): tcgen05.commit ... multicast::cluster to both CTAs frees the slot for both producers.
 //   tfull[a]  (count 1, per CTA): multicast commit after the last k-block -> each CTA's epilogue warps.
 //   tempty[a] (leader's copy, count 2 x 256): every epilogue thread of both CTAs arrives (peer: remote arrive).
+//
+// Tile schedule: DYNAMIC.  The leader's producer thread draws pair-tile indices from a global counter (atomicAdd) and
+// publishes them through a 4-slot ring in BOTH CTAs' shared memory (tq_full[slot]: count 1 per CTA, remote store +
+// release.cluster arrive for the peer's copy; tq_empty[slot]: leader's copy, one arrive per consumer warp of both CTAs).
+// A cluster that becomes resident late (SMs held by a concurrent kernel, e.g. the NCCL all-reduce of the gradient
+// exchange that overlaps backward) simply draws fewer tiles, where a static `tile += gridDim` walk would serialise its
+// whole share behind the others.  Which cluster computes a tile never changes the tile's arithmetic: results stay
+// bit-identical run to run.  The counter is returned to zero by the last cluster to finish (see gemm_host.h).
 #include <cstdio>
 
 #include "errors.h"
@@ -29,6 +37,8 @@ constexpr int STAGE_BYTES2 = A_STAGE_BYTES + B_HALF_BYTES;    // 32 KiB
 constexpr int TILE_BYTES2 = STAGES2 * STAGE_BYTES2;           // 192 KiB
 constexpr int SMEM_BYTES2 = TILE_BYTES2 + 1024 + 256 + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                // clears the CTA-rank bit of a shared::cluster address
+constexpr int TQ = 4;                                         // tile-index ring slots
+constexpr int TQ_CONSUMER_WARPS = 2 * (1 + NUM_EPI_WARPS);    // leader: MMA warp + epilogue warps; peer: producer + epilogue warps
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -74,9 +84,85 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
+// ---- cluster-scope mbarrier operations for the tile ring (data written remotely must be ordered by release / acquire at
+// cluster scope)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}"
+      ::"r"(addr), "r"(cta), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_acq_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_acq_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("pi05: tile-ring wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ int ld_shared_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// One consumer warp's view of the tile ring: wait for the next published index, read it, release the slot.
+struct TileRing {
+  uint32_t full0, empty0, slot0;
+  int slot;
+  uint32_t phase;
+  bool leader;
+  __device__ __forceinline__ int next() {  // all 32 lanes of a converged warp (or a single thread with one = true)
+    mbar_wait_acq_cluster(full0 + 8 * slot, phase);
+    const int t = ld_shared_s32(slot0 + 4 * slot);
+    return t;
+  }
+  __device__ __forceinline__ void release_warp() {  // after every lane has consumed the value
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) release_one();
+    advance();
+  }
+  __device__ __forceinline__ void release_one() {
+    if (leader)
+      mbar_arrive(empty0 + 8 * slot);
+    else
+      mbar_arrive_release_cluster(empty0 + 8 * slot, 0);  // this CTA's reads of the slot precede the leader's next store
+  }
+  __device__ __forceinline__ void advance() {
+    if (++slot == TQ) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+};
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p,
+             unsigned int* __restrict__ sched) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a0 = smem_base;
@@ -87,6 +173,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   const uint32_t tfull_bar0 = bar_base + 16 * STAGES2;
   const uint32_t tempty_bar0 = tfull_bar0 + 16;
   const uint32_t tmem_slot = tempty_bar0 + 16;
+  // tile-index ring (after the 12 + 4 pipeline barriers and the TMEM slot; the barrier area is 256 bytes)
+  const uint32_t tq_full0 = tmem_slot + 8;
+  const uint32_t tq_empty0 = tq_full0 + 8 * TQ;
+  const uint32_t tq_slot0 = tq_empty0 + 8 * TQ;
+  static_assert(16 * STAGES2 + 32 + 8 + 16 * TQ + 4 * TQ <= 256, "barrier area overflow");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,6 +194,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar0 + 8 * a, 1);
       mbar_init(tempty_bar0 + 8 * a, 2 * 32 * NUM_EPI_WARPS);
+    }
+    for (int q = 0; q < TQ; ++q) {
+      mbar_init(tq_full0 + 8 * q, 1);
+      mbar_init(tq_empty0 + 8 * q, TQ_CONSUMER_WARPS);
     }
     fence_barrier_init();
   }
@@ -121,16 +216,45 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   KParams pp = p;
   pp.num_m = (p.num_m + 1) / 2;
   const int total_tiles = pp.num_m * pp.num_n * pp.batch;
-  const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   constexpr int BN_OUT = (EPI == EPI_GEGLU) ? BN2 / 2 : BN2;
+  TileRing ring{tq_full0, tq_empty0, tq_slot0, 0, 0u, leader};
 
   if (warp_idx == 0) {
     // ============================== TMA producer (both CTAs) ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      // leader: draw + publish tile indices (the draw for tile n+1 is in flight while tile n's loads are issued);
+      // peer: follow the ring
+      int pub_slot = 0;
+      uint32_t pub_phase = 0;
+      auto draw = [&]() -> int {
+        const unsigned int t = atomicAdd(sched, 1u);
+        return t < static_cast<unsigned int>(total_tiles) ? static_cast<int>(t) : -1;
+      };
+      auto publish = [&](int t) {
+        mbar_wait_acq_cluster(tq_empty0 + 8 * pub_slot, pub_phase ^ 1);  // every consumer warp of both CTAs is done with the old value
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(tq_slot0 + 4 * pub_slot), "r"(t) : "memory");
+        st_cluster_u32(tq_slot0 + 4 * pub_slot, 1, static_cast<uint32_t>(t));
+        mbar_arrive(tq_full0 + 8 * pub_slot);
+        mbar_arrive_release_cluster(tq_full0 + 8 * pub_slot, 1);
+        if (++pub_slot == TQ) {
+          pub_slot = 0;
+          pub_phase ^= 1;
+        }
+      };
+      int tile, next_tile = -1;
+      if (leader) {
+        tile = draw();
+        publish(tile);
+      } else {
+        tile = ring.next();
+        ring.release_one();
+        ring.advance();
+      }
+      while (tile >= 0) {
+        if (leader) next_tile = draw();
         const TileCoord tc = decode_tile(tile, pp);
         const int m0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM;
         const int n0 = tc.n_blk * BN_OUT;
@@ -165,6 +289,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             phase ^= 1;
           }
         }
+        if (leader) {
+          publish(next_tile);
+          tile = next_tile;
+        } else {
+          tile = ring.next();
+          ring.release_one();
+          ring.advance();
+        }
+      }
+      if (leader) {
+        // the last cluster to run dry returns the counter (and the exit count) to zero for the next launch that uses it
+        if (atomicAdd(sched + 1, 1u) == static_cast<unsigned int>(num_clusters) - 1u) {
+          sched[0] = 0u;
+          sched[1] = 0u;
+          __threadfence();
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -183,7 +323,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;
       const uint32_t idesc = p.idesc;
       const int num_kb = p.num_kb;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (;;) {
+        const int tile = ring.next();
+        ring.release_warp();
+        if (tile < 0) break;
         mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
@@ -218,7 +361,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const int chalf = (warp_idx - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    for (;;) {
+      const int tile = ring.next();
+      ring.release_warp();
+      if (tile < 0) break;
       const TileCoord tc = decode_tile(tile, pp);
       const int row0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM + q * 32;
       const int n0 = tc.n_blk * BN_OUT;
@@ -267,7 +413,12 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cud
   const int pairs = ((kp.num_m + 1) / 2) * kp.num_n * kp.batch;
   int clusters = sms / 2;
   if (pairs < clusters) clusters = pairs;
-  launch_pdl(gemm2_kernel<EPI>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES2, stream, ta, tb, kp);
+  unsigned int* sched = next_sched_counter();
+  if (sched == nullptr) {
+    if (err) snprintf(err, err_len, "gemm2: tile-scheduler counters unavailable");
+    return 2;
+  }
+  launch_pdl(gemm2_kernel<EPI>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES2, stream, ta, tb, kp, sched);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -43,7 +43,8 @@ std::vector<ProfEntry> g_prof;
 // ---- the kernel --------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p,
+            unsigned int* __restrict__ sched) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B-aligned tiles
@@ -56,6 +57,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint32_t tfull_bar0 = bar_base + 16 * C::STAGES;
   const uint32_t tempty_bar0 = tfull_bar0 + 16;
   const uint32_t tmem_slot = tempty_bar0 + 16;
+  // dynamic tile schedule (same scheme as gemm2_sm100.cu, CTA-local): the producer thread draws tile indices from a
+  // global counter and publishes them through a 4-slot ring; consumers = MMA warp + epilogue warps
+  constexpr int TQ = 4;
+  const uint32_t tq_full0 = tmem_slot + 8;
+  const uint32_t tq_empty0 = tq_full0 + 8 * TQ;
+  const uint32_t tq_slot0 = tq_empty0 + 8 * TQ;
+  static_assert(16 * C::STAGES + 32 + 8 + 16 * TQ + 4 * TQ <= 256, "barrier area overflow");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,6 +78,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar0 + 8 * a, 1);
       mbar_init(tempty_bar0 + 8 * a, 32 * NUM_EPI_WARPS);
+    }
+    for (int q = 0; q < TQ; ++q) {
+      mbar_init(tq_full0 + 8 * q, 1);
+      mbar_init(tq_empty0 + 8 * q, 1 + NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -87,13 +99,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int total_tiles = p.num_m * p.num_n * p.batch;
   constexpr int BN_OUT = (EPI == EPI_GEGLU) ? BN / 2 : BN;  // output columns covered by one tile
+  int tq_slot = 0;
+  uint32_t tq_phase = 0;
+  // consumer side of the tile ring (whole converged warp): next index, then release the slot
+  auto ring_next = [&]() -> int {
+    mbar_wait(tq_full0 + 8 * tq_slot, tq_phase);
+    int t;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(tq_slot0 + 4 * tq_slot) : "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tq_empty0 + 8 * tq_slot);
+    if (++tq_slot == TQ) {
+      tq_slot = 0;
+      tq_phase ^= 1;
+    }
+    return t;
+  };
 
   if (warp_idx == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto draw = [&]() -> int {
+        const unsigned int t = atomicAdd(sched, 1u);
+        return t < static_cast<unsigned int>(total_tiles) ? static_cast<int>(t) : -1;
+      };
+      auto publish = [&](int t) {
+        mbar_wait(tq_empty0 + 8 * tq_slot, tq_phase ^ 1);
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(tq_slot0 + 4 * tq_slot), "r"(t) : "memory");
+        mbar_arrive(tq_full0 + 8 * tq_slot);
+        if (++tq_slot == TQ) {
+          tq_slot = 0;
+          tq_phase ^= 1;
+        }
+      };
+      int tile = draw();
+      publish(tile);
+      while (tile >= 0) {
+        const int next_tile = draw();  // in flight while this tile's loads are issued
         const TileCoord tc = decode_tile(tile, p);
         const int m0 = tc.m_blk * BM;
         const int n0 = tc.n_blk * BN_OUT;
@@ -126,6 +169,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             phase ^= 1;
           }
         }
+        publish(next_tile);
+        tile = next_tile;
+      }
+      // the last CTA to run dry returns the counter pair to zero for the next launch that uses it
+      if (atomicAdd(sched + 1, 1u) == gridDim.x - 1u) {
+        sched[0] = 0u;
+        sched[1] = 0u;
+        __threadfence();
       }
     }
   } else if (warp_idx == 1) {
@@ -145,7 +196,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;
       const uint32_t idesc = p.idesc;
       const int num_kb = p.num_kb;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (;;) {
+        if (ring_next() < 0) break;
         mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -180,7 +232,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int chalf = (warp_idx - 2) >> 2;  // which half of the tile's column chunks this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (;;) {
+      const int tile = ring_next();
+      if (tile < 0) break;
       const TileCoord tc = decode_tile(tile, p);
       const int row0 = tc.m_blk * BM + q * 32;
       const int n0 = tc.n_blk * BN_OUT;
@@ -294,6 +348,32 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, lon
   return true;
 }
 
+}  // namespace
+
+unsigned int* next_sched_counter() {
+  constexpr int kSlots = 64, kStrideWords = 32;  // one 128-byte line per launch: no false sharing between overlapping kernels
+  static std::mutex mu;
+  static std::map<int, unsigned int*> pools;
+  static std::map<int, unsigned int> cursor;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = pools.find(dev);
+  if (it == pools.end()) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, kSlots * kStrideWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, kSlots * kStrideWords * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    it = pools.emplace(dev, p).first;
+    cursor[dev] = 0;
+  }
+  unsigned int& c = cursor[dev];
+  unsigned int* out = it->second + static_cast<size_t>(c % kSlots) * kStrideWords;
+  ++c;
+  return out;
+}
+
+namespace {
+
 int num_sms() {
   static int n = [] {
     int dev = 0, v = 0;
@@ -320,7 +400,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, cuda
   }
   const int total = kp.num_m * kp.num_n * kp.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ta, tb, kp); count_launch();
+  unsigned int* sched = next_sched_counter();
+  if (sched == nullptr) {
+    if (err) snprintf(err, err_len, "gemm: tile-scheduler counters unavailable");
+    return 2;
+  }
+  launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, ta, tb, kp, sched); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) snprintf(err, err_len, "gemm launch: %s", cudaGetErrorString(e));

@@ -17,8 +17,10 @@ namespace {
 
 constexpr int NORM_BLOCKS = 1184;  // 8 per SM
 
+// gs: gradient pre-scale (1 / world size when the data-parallel exchange left SUMS in the arenas: the average DDP would
+// have produced is bf(g * gs), taken on the fly here and in the update kernels instead of in a separate 14 GB pass)
 __global__ void __launch_bounds__(256) sumsq_k(const bf16* __restrict__ gb, int64_t nb, const float* __restrict__ gf,
-                                               int64_t nf, float* __restrict__ partial) {
+                                               int64_t nf, float* __restrict__ partial, float gs) {
   pdl_enter();
   float acc = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -28,14 +30,17 @@ __global__ void __launch_bounds__(256) sumsq_k(const bf16* __restrict__ gb, int6
     float v[8];
     load8(gb + i * 8, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += v[k] * v[k];
+    for (int k = 0; k < 8; ++k) {
+      const float x = bfr(v[k] * gs);
+      acc += x * x;
+    }
   }
   for (int64_t i = nb8 * 8 + tid; i < nb; i += stride) {
-    const float v = __bfloat162float(gb[i]);
+    const float v = bfr(__bfloat162float(gb[i]) * gs);
     acc += v * v;
   }
   for (int64_t i = tid; i < nf; i += stride) {
-    const float v = gf[i];
+    const float v = gf[i] * gs;
     acc += v * v;
   }
   acc = warp_sum(acc);
@@ -88,7 +93,7 @@ __device__ __forceinline__ void adam_math(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m,
                                                     bf16* __restrict__ v, int64_t n, AdamArgs a,
-                                                    const float* __restrict__ coef_ptr) {
+                                                    const float* __restrict__ coef_ptr, float gs) {
   pdl_enter();
   const float coef = coef_ptr[1];
   const int64_t n8 = n / 8;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const 
     load8(m + i * 8, mm);
     load8(v + i * 8, vv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) adam_math(pp[k], bfr(gg[k] * coef), mm[k], vv[k], a);
+    for (int k = 0; k < 8; ++k) adam_math(pp[k], bfr(bfr(gg[k] * gs) * coef), mm[k], vv[k], a);
     store8(p + i * 8, pp);
     store8(m + i * 8, mm);
     store8(v + i * 8, vv);
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const 
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = n8 * 8; i < n; ++i) {
       float pp = __bfloat162float(p[i]), mm = __bfloat162float(m[i]), vv = __bfloat162float(v[i]);
-      adam_math(pp, bfr(__bfloat162float(g[i]) * coef), mm, vv, a);
+      adam_math(pp, bfr(bfr(__bfloat162float(g[i]) * gs) * coef), mm, vv, a);
       p[i] = __float2bfloat16_rn(pp);
       m[i] = __float2bfloat16_rn(mm);
       v[i] = __float2bfloat16_rn(vv);
@@ -118,13 +123,13 @@ __global__ void __launch_bounds__(256) adamw_bf16_k(bf16* __restrict__ p, const 
 
 __global__ void __launch_bounds__(256) adamw_f32_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamArgs a,
-                                                   const float* __restrict__ coef_ptr) {
+                                                   const float* __restrict__ coef_ptr, float gs) {
   pdl_enter();
   const float coef = coef_ptr[1];
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_math(pp, g[i] * coef, mm, vv, a);
+    adam_math(pp, (g[i] * gs) * coef, mm, vv, a);
     p[i] = pp;
     m[i] = mm;
     v[i] = vv;
@@ -138,7 +143,16 @@ extern "C" int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_b
                                      float* p_f32, const float* g_f32, float* m_f32, float* v_f32, int64_t n_f32, float lr,
                                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float max_norm,
                                      float* scratch, void* stream) {
+  return pi05_fused_clip_adamw_scaled(p_bf16, g_bf16, m_bf16, v_bf16, n_bf16, p_f32, g_f32, m_f32, v_f32, n_f32, lr, beta1,
+                                      beta2, eps, weight_decay, step, max_norm, 1.0f, scratch, stream);
+}
+
+extern "C" int pi05_fused_clip_adamw_scaled(void* p_bf16, const void* g_bf16, void* m_bf16, void* v_bf16, int64_t n_bf16,
+                                            float* p_f32, const float* g_f32, float* m_f32, float* v_f32, int64_t n_f32,
+                                            float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                                            float max_norm, float grad_scale, float* scratch, void* stream) {
   using namespace pi05;
+  const float gs = grad_scale;
   if (step < 1 || n_bf16 < 0 || n_f32 < 0 || !scratch) {
     set_error("pi05_fused_clip_adamw: bad argument (step >= 1, scratch of 4096 floats required)");
     return 1;
@@ -150,7 +164,7 @@ extern "C" int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_b
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = scratch + 8;  // scratch[0] = norm, scratch[1] = clip coefficient, [8, 8+NORM_BLOCKS) partial sums
-  launch_pdl(sumsq_k, dim3(NORM_BLOCKS), dim3(256), 0, st, static_cast<const bf16*>(g_bf16), n_bf16, g_f32, n_f32, partial);
+  launch_pdl(sumsq_k, dim3(NORM_BLOCKS), dim3(256), 0, st, static_cast<const bf16*>(g_bf16), n_bf16, g_f32, n_f32, partial, gs);
   count_launch();
   launch_pdl(finish_norm_k, dim3(1), dim3(256), 0, st, partial, NORM_BLOCKS, max_norm, scratch);
   count_launch();
@@ -166,11 +180,11 @@ extern "C" int pi05_fused_clip_adamw(void* p_bf16, const void* g_bf16, void* m_b
   a.bc2_sqrt = static_cast<float>(sqrt(bc2));
   if (n_bf16 > 0) {
     launch_pdl(adamw_bf16_k, dim3(148 * 16), dim3(256), 0, st, static_cast<bf16*>(p_bf16), static_cast<const bf16*>(g_bf16),
-                                          static_cast<bf16*>(m_bf16), static_cast<bf16*>(v_bf16), n_bf16, a, scratch);
+                                          static_cast<bf16*>(m_bf16), static_cast<bf16*>(v_bf16), n_bf16, a, scratch, gs);
     count_launch();
   }
   if (n_f32 > 0) {
-    launch_pdl(adamw_f32_k, dim3(148 * 8), dim3(256), 0, st, p_f32, g_f32, m_f32, v_f32, n_f32, a, scratch);
+    launch_pdl(adamw_f32_k, dim3(148 * 8), dim3(256), 0, st, p_f32, g_f32, m_f32, v_f32, n_f32, a, scratch, gs);
     count_launch();
   }
   cudaError_t e = cudaGetLastError();

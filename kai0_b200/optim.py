@@ -48,12 +48,14 @@ class FusedClipAdamW:
         self.step_count += 1
         dev = self.flat[0].device
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        rc = _lib.lib().pi05_fused_clip_adamw(
+        # model.grad_scale = 1 / world when the data-parallel exchange leaves SUMS in the arenas (average="optimizer")
+        rc = _lib.lib().pi05_fused_clip_adamw_scaled(
             self.flat[0].data_ptr(), gb.data_ptr(), self.m[0].data_ptr(), self.v[0].data_ptr(), self.flat[0].numel(),
             self.flat[1].data_ptr(), gf.data_ptr(), self.m[1].data_ptr(), self.v[1].data_ptr(), self.flat[1].numel(),
             float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-            int(self.step_count), float(g["max_norm"] or 0.0), self._scratch.data_ptr(), stream)
-        _lib.check(rc, "pi05_fused_clip_adamw")
+            int(self.step_count), float(g["max_norm"] or 0.0), float(getattr(self.model, "grad_scale", 1.0)),
+            self._scratch.data_ptr(), stream)
+        _lib.check(rc, "pi05_fused_clip_adamw_scaled")
         return self._scratch[0]
 
     def state_dict(self):

@@ -257,19 +257,15 @@ class _EngineFunction(torch.autograd.Function):
                     if model._aliases_grad_arena(p.grad):
                         p.grad = p.grad.detach().clone()
         grads = model._engine_backward(dloss.contiguous())
-        dead = model._dead_grad_names
         if model.direct_grads:
             # engine-owned gradients: .grad of every parameter is (a view of) the flat gradient arena; autograd only
             # sees the anchor.  Skips ~700 per-parameter AccumulateGrad copies per step.  Overwrite semantics.
             if model._flat_params is not None:
                 model._sync_flat_param_grads()  # the caller optimises the two flat tensors
-            for (n, p), g in zip(model._grad_params, grads):
-                p.grad = None if n in dead else g
+            for (_, p), g in zip(model._grad_params, grads):
+                p.grad = g
             return (None, None, None, None, None, torch.zeros_like(model._grad_anchor))
-        out = []
-        for (n, _), g in zip(model._grad_params, grads):
-            out.append(None if n in dead else (g.clone() if accumulating else g))
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, *[(g.clone() if accumulating else g) for g in grads])
 
 
 class PI0Pytorch(nn.Module):
@@ -358,6 +354,12 @@ class PI0Pytorch(nn.Module):
         self._engines = OrderedDict()  # (device index, train, num_images) -> dict(handle, workspace, max_batch, graphs); LRU order
         self._train_generation = 0
         self._dp_group = None
+        self._dp_comm = None
+        self._dp_overlap = False
+        self._dp_average = "in_place"
+        self._dp_world = 1
+        self._dp_max_ctas = 0
+        self.grad_scale = 1.0  # what an optimiser must multiply .grad by (1/world with average="optimizer")
         self._keep = None
         # parameters the reference's autograd leaves WITHOUT a gradient (nothing on the loss path reads the last layer's
         # prefix-stream output or the final prefix norm, pi0_pytorch.py:350-358): .grad stays None for them, so a stock
@@ -468,14 +470,72 @@ class PI0Pytorch(nn.Module):
         self._flat_params[0].grad = gb[: self._flat_used_bf16]
         self._flat_params[1].grad = gf
 
-    def enable_flat_allreduce(self, process_group=None):
-        """Engine-owned data parallelism: one NCCL all-reduce per dtype arena right after backward, averaged over
-        the group (equivalent to DDP's bucketed all-reduce, train_pytorch.py:440-447).  Use INSTEAD of wrapping in
-        DistributedDataParallel."""
+    def enable_flat_allreduce(self, process_group=None, *, overlap: bool | None = None, average: str = "in_place",
+                              max_ctas: int | None = None):
+        """Engine-owned data parallelism, INSTEAD of wrapping the module in DistributedDataParallel
+        (train_pytorch.py:440-447): the gradient arenas are all-reduced over the group and averaged, as DDP's bucketed
+        all-reduce does.
+
+        overlap=True (default on a CUDA module whose group runs on NCCL): the engine itself issues the collectives, chunk by chunk, while backward is still
+        running (pi05_set_grad_exchange): a dedicated NCCL communicator over the group's ranks, restricted to `max_ctas`
+        SMs (default 4, PI05_NCCL_MAX_CTAS), on an engine-owned high-priority stream; the GEMMs' dynamic tile schedule
+        absorbs the SMs NCCL holds.  overlap=False: two torch.distributed all-reduces after backward (round-1 behaviour).
+        average="in_place": .grad holds the average (any optimiser works);  "optimizer": .grad holds the SUM and
+        `kai0_b200.optim.FusedClipAdamW` applies 1 / world on the fly (saves a 14 GB read-modify-write per step)."""
         import torch.distributed as dist
 
+        if average not in ("in_place", "optimizer"):
+            raise ValueError("average must be 'in_place' or 'optimizer'")
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self._dp_group)
+        if overlap is None:
+            overlap = self._device().type == "cuda" and "nccl" in str(dist.get_backend(self._dp_group))
+        self._dp_overlap = bool(overlap)
+        self._dp_average = average
+        self.grad_scale = 1.0 / self._dp_world if average == "optimizer" else 1.0
         self.direct_grads = True  # no DDP hooks to feed, so gradients can be handed over without autograd copies
+        if self._dp_overlap and self._dp_comm is None:
+            import os
+
+            dev = self._device()
+            if dev.type != "cuda":
+                raise RuntimeError("enable_flat_allreduce(overlap=True): move the module to its CUDA device first")
+            if max_ctas is None:
+                max_ctas = int(os.environ.get("PI05_NCCL_MAX_CTAS", "4"))
+            rank = dist.get_rank(self._dp_group)
+            uid = C.create_string_buffer(128)
+            l = _lib.lib()
+            if rank == 0:
+                _lib.check(l.pi05_nccl_unique_id(uid), "pi05_nccl_unique_id")
+            box = [uid.raw]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self._dp_group, 0), group=self._dp_group)
+            comm = C.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.check(l.pi05_nccl_comm_create(C.c_char_p(box[0]), self._dp_world, rank, int(max_ctas), C.byref(comm)),
+                           "pi05_nccl_comm_create")
+            self._dp_comm = comm
+            self._dp_max_ctas = int(max_ctas)
+        for ent in self._engines.values():
+            self._apply_exchange(ent["handle"])
+
+    def _apply_exchange(self, handle):
+        if self._dp_group is None or not self._dp_overlap or self._dp_comm is None:
+            return
+        _lib.check(_lib.lib().pi05_set_grad_exchange(handle, self._dp_comm, self._dp_world,
+                                                     1 if self._dp_average == "in_place" else 0), "pi05_set_grad_exchange")
+
+    def exchange_description(self) -> str:
+        if self._dp_group is None:
+            return "none (single rank)"
+        if not self._dp_overlap:
+            return "two torch.distributed all-reduces (bf16 arena, fp32 arena) after backward, then 1/world"
+        calls, nbytes = C.c_int64(), C.c_int64()
+        h = self._train_engine_handle()
+        if h is not None:
+            _lib.lib().pi05_grad_exchange_stats(h, C.byref(calls), C.byref(nbytes))
+        return (f"engine-issued ncclAllReduce(sum) per gradient group, overlapped with backward on a high-priority stream "
+                f"(own communicator, maxCTAs {self._dp_max_ctas}; last backward: {calls.value} collectives, "
+                f"{nbytes.value / 1e9:.2f} GB); average {self._dp_average}")
 
     # ------------------------------------------------------------------ engine lifecycle
     def _device(self):
@@ -576,6 +636,8 @@ class PI0Pytorch(nn.Module):
                     self._flat_grad[dt] = torch.zeros_like(self._flat[dt])
         ent = {"handle": handle, "workspace": workspace, "max_batch": need_b, "graphs": {}}
         self._bind(handle, with_grads=train)
+        if train:
+            self._apply_exchange(handle)
         return ent
 
     def _aliases_grad_arena(self, t: Tensor) -> bool:
@@ -756,7 +818,7 @@ class PI0Pytorch(nn.Module):
     def _engine_backward(self, dloss):
         handle = self._train_engine_handle()
         _lib.check(_lib.lib().pi05_backward(handle, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
-        if self._dp_group is not None:
+        if self._dp_group is not None and not self._dp_overlap:
             self._allreduce_flat_grads()
         grads = []
         for name, p in self._grad_params:
@@ -778,7 +840,8 @@ class PI0Pytorch(nn.Module):
                 # the unused expert lm_head (0.53 GB of never-written gradient) sits last in the bf16 arena: skip it
                 g = g[: self._offsets[_UNUSED[0]][1]]
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._dp_group)
-            g.mul_(1.0 / world)
+            if self._dp_average == "in_place":
+                g.mul_(1.0 / world)
 
     # ------------------------------------------------------------------ public surface
     def forward(self, observation, actions, noise=None, time=None) -> Tensor:
@@ -805,7 +868,11 @@ class PI0Pytorch(nn.Module):
         self._train_generation += 1  # invalidates the stash any earlier, not yet back-propagated forward relied on
         self._train_key = (dev.index, True, self._engine_key[3])
         named = dict(self.named_parameters())
-        self._grad_params = [(n, named[n]) for n in self._offsets if n not in _UNUSED and named[n].requires_grad]
+        # autograd inputs = the parameters that can receive a gradient.  The unused lm_head and the parameters the loss
+        # cannot reach (self._dead_grad_names) are NOT inputs, so they are unreachable from the loss exactly as in the
+        # reference's graph: .grad stays None, and DistributedDataParallel(find_unused_parameters=True) marks them unused.
+        self._grad_params = [(n, named[n]) for n in self._offsets
+                             if n not in _UNUSED and n not in self._dead_grad_names and named[n].requires_grad]
         if self.direct_grads:
             if self._grad_anchor is None or self._grad_anchor.device != dev:
                 self._grad_anchor = torch.zeros(1, device=dev, requires_grad=True)

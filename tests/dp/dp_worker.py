@@ -1,0 +1,136 @@
+"""torchrun worker of tests/test_dp_nccl_gpu.py (world_size 2, one process per GPU, NCCL).
+
+Checks, on identical weights and a global batch of 4 split 2 + 2:
+  A. engine-owned exchange (enable_flat_allreduce: own NCCL communicator, collectives overlapped with backward, averaged in
+     place) == the UNCHANGED-script path: stock torch DistributedDataParallel around the module with the reference's
+     arguments (scripts/train_pytorch.py:441-447);
+  B. the averaged N = 2 gradients == the N = 1 gradients of the concatenated batch (bf16 rounding tolerance);
+  C. average="optimizer" (+ FusedClipAdamW, 1/world folded into the update) == average="in_place" after one step;
+  D. the one-shot C-ABI entry pi05_allreduce_grads on the same communicator == the overlapped exchange.
+Prints one line "DP_WORKER_OK ..." on rank 0 when everything holds.
+"""
+import ctypes as C
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+from oracle import pi05_oracle as O  # noqa: E402
+
+
+def grads_of(model):
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def run(model, b, rows):
+    sl = lambda t: t[rows].cuda()  # noqa: E731
+    bb = dict(b)
+    bb["images"] = [i[rows] for i in b["images"]]
+    bb["img_masks"] = [m[rows] for m in b["img_masks"]]
+    bb["tokens"], bb["token_mask"] = b["tokens"][rows], b["token_mask"][rows]
+    loss = model(H.Obs(bb, "cuda"), sl(b["actions"]), sl(b["noise"]), sl(b["time"]))
+    loss.mean().backward()
+    torch.cuda.synchronize()
+    return loss
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == 2
+    oc = H.mid_config()
+    b = O.synthetic_batch(oc, 4, seed=5, ragged=True)
+    mine = slice(2 * rank, 2 * rank + 2)
+
+    def fresh():
+        m, _ = H.build_pair(oc, seed=3, device="cuda")
+        m.train()
+        return m
+
+    # ---- A: engine exchange vs stock DDP
+    mx = fresh()
+    mx.enable_flat_allreduce()
+    assert mx._dp_overlap, "NCCL group on a CUDA module must take the overlapped engine path"
+    run(mx, b, mine)
+    gx = grads_of(mx)
+    calls, nbytes = C.c_int64(), C.c_int64()
+    from kai0_b200 import _lib
+
+    _lib.lib().pi05_grad_exchange_stats(mx._train_engine_handle(), C.byref(calls), C.byref(nbytes))
+    assert calls.value > 4 and nbytes.value > 0, (calls.value, nbytes.value)
+
+    my = fresh()
+    ddp = torch.nn.parallel.DistributedDataParallel(my, device_ids=[local], find_unused_parameters=True,
+                                                    gradient_as_bucket_view=True, static_graph=False)
+    bb = dict(b)
+    sl = lambda t: t[mine].cuda()  # noqa: E731
+    bb["images"] = [i[mine] for i in b["images"]]
+    bb["img_masks"] = [m[mine] for m in b["img_masks"]]
+    bb["tokens"], bb["token_mask"] = b["tokens"][mine], b["token_mask"][mine]
+    ddp(H.Obs(bb, "cuda"), sl(b["actions"]), sl(b["noise"]), sl(b["time"])).mean().backward()
+    torch.cuda.synchronize()
+    gy = grads_of(my)
+    assert set(gx) == set(gy), (sorted(set(gx) ^ set(gy))[:5])
+    worst_a = 0.0
+    for n in gx:
+        d = (gx[n].float() - gy[n].float()).abs().max().item()
+        s = gy[n].float().abs().max().item()
+        worst_a = max(worst_a, d / max(s, 1e-30))
+    # ---- B: N = 2 average == N = 1 on the concatenated batch
+    mz = fresh()
+    run(mz, b, slice(0, 4))
+    gz = grads_of(mz)
+    worst_b = 0.0
+    for n in gx:
+        if float(gz[n].float().norm()) < 1e-6:
+            continue
+        worst_b = max(worst_b, H.rel_err(gx[n], gz[n]))
+    # ---- C: sums in the arenas + 1/world folded into the fused optimiser
+    from kai0_b200.optim import FusedClipAdamW
+
+    def one_step(average):
+        m = fresh()
+        m.enable_flat_allreduce(average=average)
+        opt = FusedClipAdamW(m, lr=1e-3, max_norm=1.0)
+        run(m, b, mine)
+        norm = float(opt.step())
+        return m, norm
+
+    m1, n1 = one_step("in_place")
+    m2, n2 = one_step("optimizer")
+    same_c = all(torch.equal(p1, p2) for (_, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()))
+    # ---- D: one-shot C-ABI all-reduce (no overlap) on mx's communicator: local gradients first, then the single call
+    md = fresh()
+    md.direct_grads = True
+    run(md, b, mine)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib().pi05_allreduce_grads(md._train_engine_handle(), mx._dp_comm, world, 1, st), "pi05_allreduce_grads")
+    torch.cuda.synchronize()
+    gd = grads_of(md)
+    same_d = all(torch.equal(gd[n], gx[n]) for n in gx)
+    res = torch.tensor([worst_a, worst_b, float(same_c), float(same_d), abs(n1 - n2)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    ok_flags = torch.tensor([float(same_c), float(same_d)], device="cuda")
+    dist.all_reduce(ok_flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"worst engine-vs-DDP gradient difference {res[0].item():.3e} (relative to each tensor's max); "
+              f"worst N=2-vs-N=1 relative gradient error {res[1].item():.3e}; optimizer-folded == in-place: "
+              f"{bool(ok_flags[0].item())}; one-shot == overlapped: {bool(ok_flags[1].item())}; grad-norm difference "
+              f"{res[4].item():.3e}; {calls.value} collectives, {nbytes.value / 1e6:.1f} MB per backward", flush=True)
+        assert res[0].item() <= 1e-6, "engine exchange differs from stock DDP"
+        assert res[1].item() < 2e-2, "N=2 gradients differ from N=1 on the concatenated batch"
+        assert ok_flags[0].item() == 1.0 and ok_flags[1].item() == 1.0
+        print("DP_WORKER_OK", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,13 @@ def _worker(rank, world, port, q):
         dt, o, n, shape = model._offsets[name]
         view = model._flat_grad[dt][o:o + n].view(shape)
         alias = bool(torch.all(view == 1.5))
+        # average="optimizer": the arenas keep the SUM and the optimiser is told to scale by 1 / world
+        model.enable_flat_allreduce(average="optimizer")
+        for dt, flat in model._flat.items():
+            model._flat_grad[dt] = torch.full_like(flat, float(rank + 1))
+        model._allreduce_flat_grads()
+        ok = ok and bool(torch.all(model._flat_grad[torch.float32] == 3.0)) and model.grad_scale == 0.5
+        ok = ok and not model._dp_overlap  # gloo / CPU: the torch.distributed path, never the NCCL engine path
         q.put((rank, ok, same, alias))
     finally:
         dist.destroy_process_group()

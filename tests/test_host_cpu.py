@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"libpi05.so does not export {sym}"
     for sym in _lib.EXPORTS:
         assert sym in declared, f"{sym} is bound in _lib.py but not declared in include/pi05.h"
-    assert lib.pi05_abi_version() == 1
+    assert lib.pi05_abi_version() == 2
 
 
 def test_abi_struct_sizes_match_header():

@@ -174,25 +174,40 @@ def time_cpu(host_d, actions, steps: int, warmup: int, budget_s: float, threads:
     frac_target = min(1.0, left / (t_first * remaining * 1.3))
     depth = max(1, min(17, int(18 * frac_target)))
     vit = max(1, min(26, int(27 * depth / 18)))
-    # the vision depth is fixed when the reference modules are first loaded: truncate the built tower instead
+    b = time_cpu_bounded(host_d, actions, steps, max(warmup - 1, 0), depth, vit, threads)
+    b.update({"first_whole_sample_step_s": t_first, "measured_whole_sample_samples_per_s": 1.0 / t_first,
+              "build_s": t_build + b["build_s"],
+              "sample": b["sample"] + f"; ONE whole untruncated sample (all layers, same step) was run first as a warm-up: "
+                                      f"{t_first:.1f} s = {1.0 / t_first:.4f} samples/s incl. first-call overheads"})
+    return b
+
+
+def time_cpu_bounded(host_d, actions, steps: int, warmup: int, depth: int, vit: int, threads: int | None = None):
+    """`steps` timed reference training steps (B = 1) after `warmup` untimed ones on the reference model truncated to
+    `depth` of 18 joint Gemma layers and `vit` of 27 SigLIP layers (same widths, same per-layer code); samples/s is the
+    measured rate times the stated forward-FLOP fraction of a whole sample.  The embedding table and its
+    AdamW update are not depth-scaled, so the scaled figure slightly under-states the CPU."""
+    threads = threads or physical_threads()
+    torch.set_num_threads(threads)
+    t_build = time.time()
     m = build("cpu", depth=depth)
     enc = m.paligemma_with_expert.paligemma.model.vision_tower.vision_model.encoder
-    enc.layers = torch.nn.ModuleList(list(enc.layers)[:vit])
+    enc.layers = torch.nn.ModuleList(list(enc.layers)[:vit])  # the tower's depth is fixed when the modules are first loaded
     st = Stepper(m)
+    t_build = time.time() - t_build
+    d1, a1 = slice_batch(host_d, actions, 1)
     frac = (TF_VIT * vit / 27 + TF_JOINT * depth / 18 + TF_REST) / TF_FWD
-    for _ in range(max(warmup - 1, 0)):
+    for _ in range(warmup):
         st.step(d1, a1, "cpu")
     t1 = time.time()
     for _ in range(steps):
         st.step(d1, a1, "cpu")
     dt = (time.time() - t1) / max(steps, 1)
-    info.update({"mode": "bounded", "s_per_step": dt, "samples_per_s": frac / dt, "scale": frac,
-                 "measured_whole_sample_samples_per_s": 1.0 / t_first,
-                 "sample": f"B=1 per step on the reference model truncated to {vit}/27 SigLIP and {depth}/18 joint Gemma "
-                           f"layers = {100 * frac:.1f} % of a sample's FLOPs ({dt:.2f} s/step measured), scaled by that "
-                           f"ratio; ONE whole untruncated sample was also run first: {t_first:.1f} s "
-                           f"({1.0 / t_first:.4f} samples/s incl. first-call overheads); {threads} threads"})
-    return info
+    return {"threads": threads, "build_s": t_build, "mode": "bounded", "s_per_step": dt, "samples_per_s": frac / dt,
+            "scale": frac,
+            "sample": f"B=1 per step through the reference's own PI0Pytorch truncated to {vit}/27 SigLIP and {depth}/18 joint "
+                      f"Gemma layers = {100 * frac:.1f} % of a sample's forward FLOPs ({dt:.2f} s/step measured over {steps} "
+                      f"steps after {warmup} warm-up), scaled to a whole sample by that ratio; {threads} threads"}
 
 
 def time_gpu(host_d, actions, device, steps=3, warmup=2, batch=32):
