@@ -13,7 +13,7 @@
 //
 // Tile schedule: DYNAMIC.  The leader's producer thread draws pair-tile indices from a global counter (atomicAdd) and
 // publishes them through a 4-slot ring in BOTH CTAs' shared memory (tq_full[slot]: count 1 per CTA, remote store +
-// release.cluster arrive for the peer's copy; tq_empty[slot]: leader's copy, one arrive per consumer warp of both CTAs).
+// an asynchronous remote store that completes on the peer's barrier; tq_empty[slot]: leader's copy, one arrive per consumer warp of both CTAs).
 // A cluster that becomes resident late (SMs held by a concurrent kernel, e.g. the NCCL all-reduce of the gradient
 // exchange that overlaps backward) simply draws fewer tiles, where a static `tile += gridDim` walk would serialise its
 // whole share behind the others.  Which cluster computes a tile never changes the tile's arithmetic: results stay
@@ -84,44 +84,26 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
-// ---- cluster-scope mbarrier operations for the tile ring (data written remotely must be ordered by release / acquire at
-// cluster scope)
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+// ---- tile ring, remote half: the index reaches the peer CTA as an ASYNCHRONOUS remote store that completes on the peer's
+// mbarrier (st.async ... mbarrier::complete_tx, the same completion mechanism TMA uses), so no cluster-scope release /
+// acquire is needed: those compile to MEMBAR.ALL.GPU + CCTL.IVALL (L1 invalidate) and cost ~1.5 us per tile boundary
+// on the MMA warp's critical path (measured: K = 2048 GEMM classes 10 % slower).
+__device__ __forceinline__ void remote_expect_tx(uint32_t bar, uint32_t cta, uint32_t bytes) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(cta)
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+      ::"r"(bar), "r"(cta), "r"(bytes)
       : "memory");
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t cta, uint32_t v) {
+__device__ __forceinline__ void st_async_remote_u32(uint32_t addr, uint32_t bar, uint32_t cta, uint32_t v) {
   asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "st.shared::cluster.u32 [ra], %2;\n\t}"
-      ::"r"(addr), "r"(cta), "r"(v)
+      "{\n\t.reg .b32 ra, rb;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+      "mapa.shared::cluster.u32 rb, %1, %2;\n\t"
+      "st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [ra], %3, [rb];\n\t}"
+      ::"r"(addr), "r"(bar), "r"(cta), "r"(v)
       : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_acq_cluster(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait_acq_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("pi05: tile-ring wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
 }
 __device__ __forceinline__ int ld_shared_s32(uint32_t addr) {
   int v;
@@ -135,9 +117,10 @@ struct TileRing {
   int slot;
   uint32_t phase;
   bool leader;
-  __device__ __forceinline__ int next() {  // all 32 lanes of a converged warp (or a single thread with one = true)
-    mbar_wait_acq_cluster(full0 + 8 * slot, phase);
+  __device__ __forceinline__ int next() {  // all 32 lanes of a converged warp, or the single producer thread
+    mbar_wait(full0 + 8 * slot, phase);
     const int t = ld_shared_s32(slot0 + 4 * slot);
+    if (t < -1) __trap();  // never true: makes the slot release below wait for the load (write-after-read on the slot)
     return t;
   }
   __device__ __forceinline__ void release_warp() {  // after every lane has consumed the value
@@ -149,7 +132,7 @@ struct TileRing {
     if (leader)
       mbar_arrive(empty0 + 8 * slot);
     else
-      mbar_arrive_release_cluster(empty0 + 8 * slot, 0);  // this CTA's reads of the slot precede the leader's next store
+      mbar_arrive_cluster(empty0 + 8 * slot, 0);
   }
   __device__ __forceinline__ void advance() {
     if (++slot == TQ) {
@@ -183,6 +166,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // First tile index: drawn as the very first instruction, consumed after the prologue, so the atomic's round trip is off
+  // the critical path even in a 3 us kernel.  (Safe before griddepcontrol.wait: the only other writer of this counter pair
+  // is the reset of a launch 64 GEMMs ago; a PDL predecessor uses another pair.)
+  unsigned int first_raw = 0;
+  const bool dyn = p.static_sched == 0;
+  if (threadIdx.x == 0 && leader && dyn) first_raw = atomicAdd(sched, 1u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -229,24 +218,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       // peer: follow the ring
       int pub_slot = 0;
       uint32_t pub_phase = 0;
-      auto draw = [&]() -> int {
-        const unsigned int t = atomicAdd(sched, 1u);
-        return t < static_cast<unsigned int>(total_tiles) ? static_cast<int>(t) : -1;
+      auto to_tile = [&](unsigned int raw) -> int {
+        return raw < static_cast<unsigned int>(total_tiles) ? static_cast<int>(raw) : -1;
       };
       auto publish = [&](int t) {
-        mbar_wait_acq_cluster(tq_empty0 + 8 * pub_slot, pub_phase ^ 1);  // every consumer warp of both CTAs is done with the old value
+        mbar_wait(tq_empty0 + 8 * pub_slot, pub_phase ^ 1);  // every consumer warp of both CTAs is done with the old value
         asm volatile("st.shared.s32 [%0], %1;" ::"r"(tq_slot0 + 4 * pub_slot), "r"(t) : "memory");
-        st_cluster_u32(tq_slot0 + 4 * pub_slot, 1, static_cast<uint32_t>(t));
         mbar_arrive(tq_full0 + 8 * pub_slot);
-        mbar_arrive_release_cluster(tq_full0 + 8 * pub_slot, 1);
+        remote_expect_tx(tq_full0 + 8 * pub_slot, 1, 4);  // the peer's copy: 1 arrival + 4 bytes complete the phase
+        st_async_remote_u32(tq_slot0 + 4 * pub_slot, tq_full0 + 8 * pub_slot, 1, static_cast<uint32_t>(t));
         if (++pub_slot == TQ) {
           pub_slot = 0;
           pub_phase ^= 1;
         }
       };
       int tile, next_tile = -1;
-      if (leader) {
-        tile = draw();
+      // the next index is published a few k-blocks into the current tile: late enough for the draw to have returned,
+      // early enough that the peer's producer and the consumers never wait for it at the tile boundary
+      const int pub_kb = p.num_kb > 8 ? 8 : p.num_kb - 1;
+      const int cluster_id = blockIdx.x >> 1;
+      if (!dyn) {
+        tile = cluster_id < total_tiles ? cluster_id : -1;
+      } else if (leader) {
+        tile = to_tile(first_raw);
         publish(tile);
       } else {
         tile = ring.next();
@@ -254,7 +248,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         ring.advance();
       }
       while (tile >= 0) {
-        if (leader) next_tile = draw();
+        unsigned int next_raw = 0;
+        if (leader && dyn) next_raw = atomicAdd(sched, 1u);  // result first read at k-block pub_kb
         const TileCoord tc = decode_tile(tile, pp);
         const int m0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM;
         const int n0 = tc.n_blk * BN_OUT;
@@ -288,9 +283,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             stage = 0;
             phase ^= 1;
           }
+          if (leader && dyn && kb == pub_kb) {
+            next_tile = to_tile(next_raw);
+            publish(next_tile);
+          }
         }
-        if (leader) {
-          publish(next_tile);
+        if (!dyn) {
+          tile = tile + num_clusters < total_tiles ? tile + num_clusters : -1;
+        } else if (leader) {
           tile = next_tile;
         } else {
           tile = ring.next();
@@ -298,7 +298,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           ring.advance();
         }
       }
-      if (leader) {
+      if (leader && dyn) {
         // the last cluster to run dry returns the counter (and the exit count) to zero for the next launch that uses it
         if (atomicAdd(sched + 1, 1u) == static_cast<unsigned int>(num_clusters) - 1u) {
           sched[0] = 0u;
@@ -323,9 +323,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;
       const uint32_t idesc = p.idesc;
       const int num_kb = p.num_kb;
+      int stile = blockIdx.x >> 1;
       for (;;) {
-        const int tile = ring.next();
-        ring.release_warp();
+        int tile;
+        if (dyn) {
+          tile = ring.next();
+          ring.release_warp();
+        } else {
+          tile = stile < total_tiles ? stile : -1;
+          stile += num_clusters;
+        }
         if (tile < 0) break;
         mbar_wait(tempty_bar0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -361,9 +368,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const int chalf = (warp_idx - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int stile = blockIdx.x >> 1;
     for (;;) {
-      const int tile = ring.next();
-      ring.release_warp();
+      int tile;
+      if (dyn) {
+        tile = ring.next();
+        ring.release_warp();
+      } else {
+        tile = stile < total_tiles ? stile : -1;
+        stile += num_clusters;
+      }
       if (tile < 0) break;
       const TileCoord tc = decode_tile(tile, pp);
       const int row0 = (2 * tc.m_blk + static_cast<int>(rank)) * BM + q * 32;

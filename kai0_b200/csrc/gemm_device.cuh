@@ -41,6 +41,7 @@ struct KParams {
   float scale;
   int accumulate;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor geometry (overridable for bring-up: PI05_DBG_MN_LBO/SBO)
+  int static_sched;         // 1: static `tile += grid` walk instead of the dynamic tile ring (PI05_GEMM_STATIC=1: A/B runs)
 };
 
 struct TileCoord {

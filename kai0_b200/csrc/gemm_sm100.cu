@@ -67,6 +67,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // first tile index drawn before the prologue so the atomic's latency is hidden (see gemm2_sm100.cu)
+  unsigned int first_raw = 0;
+  const bool dyn = p.static_sched == 0;
+  if (threadIdx.x == 0 && dyn) first_raw = atomicAdd(sched, 1u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -102,7 +106,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   int tq_slot = 0;
   uint32_t tq_phase = 0;
   // consumer side of the tile ring (whole converged warp): next index, then release the slot
+  int stile = blockIdx.x;
   auto ring_next = [&]() -> int {
+    if (!dyn) {
+      const int t = stile < total_tiles ? stile : -1;
+      stile += gridDim.x;
+      return t;
+    }
     mbar_wait(tq_full0 + 8 * tq_slot, tq_phase);
     int t;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(tq_slot0 + 4 * tq_slot) : "memory");
@@ -120,9 +130,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      auto draw = [&]() -> int {
-        const unsigned int t = atomicAdd(sched, 1u);
-        return t < static_cast<unsigned int>(total_tiles) ? static_cast<int>(t) : -1;
+      auto to_tile = [&](unsigned int raw) -> int {
+        return raw < static_cast<unsigned int>(total_tiles) ? static_cast<int>(raw) : -1;
       };
       auto publish = [&](int t) {
         mbar_wait(tq_empty0 + 8 * tq_slot, tq_phase ^ 1);
@@ -133,10 +142,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tq_phase ^= 1;
         }
       };
-      int tile = draw();
-      publish(tile);
+      const int pub_kb = p.num_kb > 8 ? 8 : p.num_kb - 1;
+      int tile;
+      if (dyn) {
+        tile = to_tile(first_raw);
+        publish(tile);
+      } else {
+        tile = static_cast<int>(blockIdx.x) < total_tiles ? static_cast<int>(blockIdx.x) : -1;
+      }
       while (tile >= 0) {
-        const int next_tile = draw();  // in flight while this tile's loads are issued
+        unsigned int next_raw = 0;
+        if (dyn) next_raw = atomicAdd(sched, 1u);  // in flight while this tile's first loads are issued
+        int next_tile = -1;
         const TileCoord tc = decode_tile(tile, p);
         const int m0 = tc.m_blk * BM;
         const int n0 = tc.n_blk * BN_OUT;
@@ -168,12 +185,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             stage = 0;
             phase ^= 1;
           }
+          if (dyn && kb == pub_kb) {
+            next_tile = to_tile(next_raw);
+            publish(next_tile);
+          }
         }
-        publish(next_tile);
-        tile = next_tile;
+        tile = dyn ? next_tile : (tile + static_cast<int>(gridDim.x) < total_tiles ? tile + static_cast<int>(gridDim.x) : -1);
       }
       // the last CTA to run dry returns the counter pair to zero for the next launch that uses it
-      if (atomicAdd(sched + 1, 1u) == gridDim.x - 1u) {
+      if (dyn && atomicAdd(sched + 1, 1u) == gridDim.x - 1u) {
         sched[0] = 0u;
         sched[1] = 0u;
         __threadfence();
@@ -902,6 +922,15 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
   kp.accumulate = a.accumulate;
   kp.mn_lbo = BK * 128;
   kp.mn_sbo = 1024;
+  // Dynamic tile scheduling pays one atomic round trip per kernel (~0.3 us on a 3-10 us decode GEMM: measured +0.5 ms on
+  // the 10-step decode), and buys nothing when no CTA / cluster gets more than one tile: those launches walk statically.
+  static const bool static_sched = getenv("PI05_GEMM_STATIC") != nullptr;
+  {
+    const long long tiles = use2 ? static_cast<long long>((kp.num_m + 1) / 2) * kp.num_n * kp.batch
+                                 : static_cast<long long>(kp.num_m) * kp.num_n * kp.batch;
+    const long long slots = use2 ? num_sms() / 2 : num_sms();
+    kp.static_sched = (static_sched || tiles <= slots) ? 1 : 0;
+  }
   if (const char* e = getenv("PI05_DBG_MN_LBO")) kp.mn_lbo = static_cast<uint32_t>(atoi(e));
   if (const char* e = getenv("PI05_DBG_MN_SBO")) kp.mn_sbo = static_cast<uint32_t>(atoi(e));
   ProfEntry pe{};

@@ -79,7 +79,10 @@ def test_advantage_forward_backward_match_oracle(name, ni, B, wa, wv):
         if n not in pr:
             assert p.grad is None
             continue
-        gr = pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])
+        if pr[n].grad is None:  # unreachable from the loss: no gradient on either side (pi0_pytorch.py:350-358)
+            assert p.grad is None and n in model._dead_grad_names, n
+            continue
+        gr = pr[n].grad
         assert p.grad is not None and p.grad.shape == p.shape, n
         if n.endswith("self_attn.k_proj.bias") and "vision_tower" in n:
             # mathematically zero (softmax is invariant to a per-query constant): both sides hold bf16 rounding noise

@@ -288,16 +288,21 @@ def test_autograd_semantics_accumulation_stale_backward_and_interleaved_eval():
     model(*args(b1)).mean().backward()
     model(*args(b2)).mean().backward()
     acc = _named_grads(model)
+    # (comparisons are to ~1 bf16 ulp, not bit-exact: the norm-weight / bias reductions use fp32 atomics, so two runs of
+    # the same backward may differ in the last bit of those tensors)
+    def close(a, b, n):
+        assert H.rel_err(a, b) < 2e-3 or float((a - b).abs().max()) < 1e-6, (n, H.rel_err(a, b))
+
     for n in g1:
         p = dict(model.named_parameters())[n]
-        want = (g1[n].to(p.dtype) + g2[n].to(p.dtype)).float()
-        assert torch.equal(acc[n], want), n
+        close(acc[n], (g1[n].to(p.dtype) + g2[n].to(p.dtype)).float(), n)
+        assert H.rel_err(acc[n], g2[n]) > 1e-2 or float(g1[n].abs().max()) == 0.0, n  # really the sum, not the last one
     # zero_grad(set_to_none=False) then one backward: .grad == g (not 2 g)
     model.zero_grad(set_to_none=False)
     model(*args(b1)).mean().backward()
     again = _named_grads(model)
     for n in g1:
-        assert torch.equal(again[n], g1[n]), n
+        close(again[n], g1[n], n)
     # a validation forward and a decode between forward and backward leave the training stash alone
     model.zero_grad(set_to_none=True)
     loss = model(*args(b1))
@@ -307,7 +312,7 @@ def test_autograd_semantics_accumulation_stale_backward_and_interleaved_eval():
     loss.mean().backward()
     inter = _named_grads(model)
     for n in g1:
-        assert torch.equal(inter[n], g1[n]), n
+        close(inter[n], g1[n], n)
     # two training forwards, then backward of the first: refused
     model.zero_grad(set_to_none=True)
     l1 = model(*args(b1))
@@ -317,7 +322,7 @@ def test_autograd_semantics_accumulation_stale_backward_and_interleaved_eval():
     l2.mean().backward()  # the latest one is still valid
     last = _named_grads(model)
     for n in g2:
-        assert torch.equal(last[n], g2[n]), n
+        close(last[n], g2[n], n)
 
 
 def test_engines_are_kept_per_mode_and_image_count():
