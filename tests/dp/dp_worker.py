@@ -105,7 +105,21 @@ def main():
 
     m1, n1 = one_step("in_place")
     m2, n2 = one_step("optimizer")
-    same_c = all(torch.equal(p1, p2) for (_, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()))
+    # (two backward passes differ in the last bit of the norm-weight / bias gradients: fp32 atomics; compare to tolerance)
+    # (the two runs are separate backward passes: fp32-atomic noise in the norm reductions moves the clip coefficient in its
+    # last bit, which may flip the bf16 rounding of a few updated values by one ulp - compare in ulps, and count them)
+    worst_c, worst_c_name, frac_c = 0.0, None, 0.0
+    for (n_, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        a_, b_ = p1.float(), p2.float()
+        d = float(((a_ - b_).abs() / (a_.abs() + 1e-3)).max())
+        frac_c = max(frac_c, float((a_ != b_).float().mean()))
+        if d > worst_c:
+            worst_c, worst_c_name = d, n_
+    same_c = worst_c <= 2 ** -7 and frac_c < 1e-2 and abs(n1 - n2) < 1e-5 * max(n1, 1e-9)
+    if rank == 0:
+        print(f"C: after one optimiser step the two averaging modes differ by at most {worst_c:.3e} relative (1 bf16 ulp = "
+              f"7.8e-3) on {frac_c:.2e} of the elements of the worst tensor ({worst_c_name}); norms {n1:.6f} / {n2:.6f}",
+              flush=True)
     # ---- D: one-shot C-ABI all-reduce (no overlap) on mx's communicator: local gradients first, then the single call
     md = fresh()
     md.direct_grads = True
@@ -114,7 +128,7 @@ def main():
     _lib.check(_lib.lib().pi05_allreduce_grads(md._train_engine_handle(), mx._dp_comm, world, 1, st), "pi05_allreduce_grads")
     torch.cuda.synchronize()
     gd = grads_of(md)
-    same_d = all(torch.equal(gd[n], gx[n]) for n in gx)
+    same_d = all(H.rel_err(gd[n], gx[n]) < 1e-4 or float((gd[n].float() - gx[n].float()).abs().max()) < 1e-7 for n in gx)
     res = torch.tensor([worst_a, worst_b, float(same_c), float(same_d), abs(n1 - n2)], device="cuda", dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     ok_flags = torch.tensor([float(same_c), float(same_d)], device="cuda")
