@@ -371,7 +371,9 @@ def main():
                  "tokenized_prompt": dev_d["tokenized_prompt"],
                  "tokenized_prompt_mask": dev_d["tokenized_prompt_mask"]}
             a = dev_a
-        obs = Observation.from_dict(d)  # uint8 NHWC -> fp32 NCHW in [-1,1] (models/model.py:129-133)
+        # uint8 NHWC images go to the engine as they are: from_dict's `x / 255 * 2 - 1` (models/model.py:129-133) is taken
+        # inside the preprocessing kernel, which writes the patch-embedding GEMM operand directly
+        obs = Observation.from_dict(d, keep_uint8=True)
         losses = model(obs, a)
         loss = losses.mean()
         loss.backward()
@@ -497,7 +499,7 @@ def main():
         for i in range(5 + 20):
             t0 = time.perf_counter()
             d1, _ = to_device(one_d, one_a, dev)
-            acts = model.sample_actions(dev, Observation.from_dict(d1), num_steps=10)
+            acts = model.sample_actions(dev, Observation.from_dict(d1, keep_uint8=True), num_steps=10)
             acts_host = acts.cpu()  # synchronises
             if i >= 5:
                 lat.append((time.perf_counter() - t0) * 1e3)

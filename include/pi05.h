@@ -65,6 +65,11 @@ typedef struct pi05_batch {
   const uint8_t* image_masks;  /* [num_images][batch] bool */
   const int64_t* tokens;       /* [batch, max_token_len] */
   const uint8_t* token_mask;   /* [batch, max_token_len] bool */
+  /* Optional (ABI 2): the images already laid out as the operand of the patch-embedding GEMM by pi05_preprocess_patches,
+   * bf16 [num_images * batch * T, 3 * Kp] with T = (image_size / patch)^2, Kp = pi05_patch_row_kp(patch), rows ordered
+   * (image, sample, patch).  When set, `images` is not read (it may be NULL) and the fp32 im2col convolution is replaced
+   * by one tcgen05 GEMM on the split operands (see pi05_preprocess_patches). */
+  const void* patch_rows;
 } pi05_batch;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -137,6 +142,21 @@ size_t pi05_preprocess_scratch_floats(int32_t batch, int32_t out_size);
 int pi05_preprocess_image(const float* image, int32_t height, int32_t width, int32_t channels_last, int32_t batch,
                           int32_t out_size, int32_t train, int32_t geometric, const float* params, float* scratch,
                           float* out, void* stream);
+
+/* Same preprocessing for ONE image key, fused with what sits either side of it on the path:
+ *   in:  image dtype PI05_F32 (in [-1,1]) or PI05_U8 -- the uint8 -> fp32 `x / 255 * 2 - 1` of Observation.from_dict
+ *        (src/openpi/models/model.py:129-133) is then taken on the fly, same three fp32 roundings;
+ *   out: `rows` = this key's slice of pi05_batch.patch_rows: bf16 [batch * T, 3 * Kp], row = sample * T + patch,
+ *        column = c * patch^2 + (y % patch) * patch + (x % patch) (the flattening of the Conv2d weight,
+ *        modeling_siglip.py:220-226), each fp32 pixel v stored as the split hi = bf16(v), lo = bf16(v - hi) in three column
+ *        blocks [hi | lo | hi]; the engine multiplies them with the weight blocks [Whi | Whi | Wlo] in ONE bf16 GEMM with fp32
+ *        accumulation: v * w to 2^-16 relative, i.e. the fp32 convolution of the reference without its CUDA-core cost.
+ *        Columns [3 * patch^2, Kp) of every block are padding the caller zero-fills once.
+ * Everything else (layout sniffing, resize-with-pad, train-time augmentation, params, scratch) as pi05_preprocess_image. */
+int32_t pi05_patch_row_kp(int32_t patch);
+int pi05_preprocess_patches(const void* image, int32_t image_dtype, int32_t height, int32_t width, int32_t channels_last,
+                            int32_t batch, int32_t out_size, int32_t patch, int32_t train, int32_t geometric,
+                            const float* params, float* scratch, void* rows, void* stream);
 
 /* ---- stand-alone operator: the tcgen05 GEMM that every nn.Linear / matmul of the path maps to ----------- */
 typedef struct pi05_gemm_desc {

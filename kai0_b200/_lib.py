@@ -58,6 +58,7 @@ class Batch(C.Structure):
         ("image_masks", C.c_void_p),
         ("tokens", C.c_void_p),
         ("token_mask", C.c_void_p),
+        ("patch_rows", C.c_void_p),
     ]
 
 
@@ -125,6 +126,8 @@ EXPORTS = (
     "pi05_get_tap",
     "pi05_preprocess_scratch_floats",
     "pi05_preprocess_image",
+    "pi05_patch_row_kp",
+    "pi05_preprocess_patches",
     "pi05_debug_profile_layer",
     "pi05_debug_set_pdl",
     "pi05_gemm_bf16",
@@ -207,6 +210,10 @@ def lib() -> C.CDLL:
             l.pi05_preprocess_scratch_floats.argtypes = [C.c_int32, C.c_int32]
             l.pi05_preprocess_image.restype = C.c_int
             l.pi05_preprocess_image.argtypes = [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p] * 4
+            l.pi05_patch_row_kp.restype = C.c_int32
+            l.pi05_patch_row_kp.argtypes = [C.c_int32]
+            l.pi05_preprocess_patches.restype = C.c_int
+            l.pi05_preprocess_patches.argtypes = [C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p] * 4
         if hasattr(l, "pi05_fused_clip_adamw"):
             l.pi05_fused_clip_adamw.restype = C.c_int
             l.pi05_fused_clip_adamw.argtypes = (

@@ -252,6 +252,30 @@ int pi05_preprocess_image(const float* image, int32_t height, int32_t width, int
   return 0;
 }
 
+int32_t pi05_patch_row_kp(int32_t patch) { return pi05::patch_row_kp(patch); }
+
+int pi05_preprocess_patches(const void* image, int32_t image_dtype, int32_t height, int32_t width, int32_t channels_last,
+                            int32_t batch, int32_t out_size, int32_t patch, int32_t train, int32_t geometric,
+                            const float* params, float* scratch, void* rows, void* stream) {
+  if (!image || !rows || !scratch || batch <= 0 || height <= 0 || width <= 0 || out_size <= 1 || patch <= 0 ||
+      out_size % patch != 0 || (image_dtype != PI05_F32 && image_dtype != PI05_U8)) {
+    pi05::set_error("pi05_preprocess_patches: bad argument (image dtype must be PI05_F32 or PI05_U8, out_size % patch == 0)");
+    return 1;
+  }
+  if (train && !params) {
+    pi05::set_error("pi05_preprocess_patches: train != 0 needs the 6 augmentation parameters");
+    return 1;
+  }
+  pi05::preprocess_patches(image, image_dtype == PI05_U8 ? 1 : 0, height, width, channels_last, batch, out_size, patch, train,
+                           geometric, params, scratch, static_cast<pi05::bf16*>(rows), static_cast<cudaStream_t>(stream));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    pi05::set_error(cudaGetErrorString(ce));
+    return 9;
+  }
+  return 0;
+}
+
 int pi05_get_tap(pi05_engine* pe, const char* name, void* dst, int64_t* numel, int32_t* dtype, void* stream) {
   Engine* e = E(pe);
   if (!e || !name) {

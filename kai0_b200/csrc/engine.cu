@@ -104,6 +104,9 @@ int engine_plan(Engine& e, bool dry) {
 
   // ---- vision tower
   e.vit_x0 = ar.get<bf16>(Mv * W);
+  e.Kp = patch_row_kp(c.vit_patch);
+  e.patch_wb = ar.get<bf16>(W * 3 * e.Kp);
+  if (tr) e.g_patch_dw = ar.get<float>(W * 2 * e.Kp);
   e.va.resize(vdepth);
   VitLayerA shared{};
   for (int l = 0; l < vdepth; ++l) {
@@ -552,14 +555,29 @@ int engine_resolve_params(Engine& e) {
 // ------------------------------------------------------------------------------------------------------------
 // SigLIP tower + projector for all NI*B images at once (row-independent, so identical to the reference's
 // per-camera calls, pi0_pytorch.py:197-202); writes image tokens straight into prefix_embs.
-int vision_forward(Engine& e, const float* images, int B, bf16* prefix_embs) {
+int vision_forward(Engine& e, const float* images, const void* patch_rows, int B, bf16* prefix_embs) {
   const pi05_config& c = e.cfg;
   cudaStream_t st = e.stream;
   const int nimg = e.NI * B, T = e.T, W = e.W, VH = e.VH, vhd = e.vhd;
   const int Mv = nimg * T;
   const float ln_eps = 1e-6f;
-  patch_embed_fwd(images, e.patch_w.d<float>(), e.patch_b.d<float>(), e.pos_emb.d<float>(), e.vit_x0, nimg,
-                  c.image_size, c.vit_patch, W, st);
+  if (patch_rows != nullptr) {
+    // Patch embedding (modeling_siglip.py:271-282) on the tensor cores at fp32-class accuracy: the preprocessing kernel
+    // already wrote the im2col rows as the split [hi | lo | hi] (pi05_preprocess_patches); with the weight split
+    // [Whi | Whi | Wlo] ONE bf16 GEMM accumulates hi*Whi + lo*Whi + hi*Wlo in fp32 (the dropped lo*Wlo term is 2^-16
+    // relative), and the epilogue adds the fp32 bias and position embedding before the single rounding to bf16.
+    const int k = 3 * c.vit_patch * c.vit_patch;
+    split_patch_weight(e.patch_w.d<float>(), e.patch_wb, W, k, e.Kp, st);
+    GemmArgs g = mk_gemm(Mv, W, 3 * e.Kp, patch_rows, 3 * e.Kp, e.patch_wb, 3 * e.Kp, e.vit_x0, W, EPI_PATCH);
+    g.bias32 = e.patch_b.d<float>();
+    g.rowadd32 = e.pos_emb.d<float>();
+    g.rowadd_period = T;
+    g.ld_rowadd = W;
+    CHECK_RC(engine_gemm(e, g));
+  } else {
+    patch_embed_fwd(images, e.patch_w.d<float>(), e.patch_b.d<float>(), e.pos_emb.d<float>(), e.vit_x0, nimg,
+                    c.image_size, c.vit_patch, W, st);
+  }
   add_tap(e, "vit_embed", e.vit_x0, static_cast<int64_t>(Mv) * W, PI05_BF16);
   for (int l = 0; l < c.vit_depth; ++l) {
     const VitLayerP& p = e.vit[l];
@@ -655,7 +673,12 @@ int prefix_forward(Engine& e, const pi05_batch* b) {
   add_tap(e, "prefix_pos", e.pos, static_cast<int64_t>(B) * e.P, PI05_I32);
   add_tap(e, "prefix_nvalid", e.nvalid, B, PI05_I32);
   bf16* prefix_embs = e.a1[0].x_in;
-  CHECK_RC(vision_forward(e, b->images, B, prefix_embs));
+  if (b->images == nullptr && b->patch_rows == nullptr) {
+    snprintf(e.err, sizeof(e.err), "pi05_batch: neither images nor patch_rows given");
+    set_error(e.err);
+    return 8;
+  }
+  CHECK_RC(vision_forward(e, b->images, b->patch_rows, B, prefix_embs));
   embed_tokens_fwd(b->tokens, e.embed.d<bf16>(), prefix_embs, B, e.L, e.D, static_cast<int64_t>(e.P) * e.D, e.NI * e.T,
                    static_cast<float>(sqrt(static_cast<double>(e.D))), e.stream);
   add_tap(e, "prefix_embs", prefix_embs, static_cast<int64_t>(B) * e.P * e.D, PI05_BF16);

@@ -97,6 +97,9 @@ struct Engine {
   int *pos = nullptr, *nvalid = nullptr;
   // vision
   bf16* vit_x0 = nullptr;
+  bf16* patch_wb = nullptr;     // patch-row path: Conv2d weight split [W, 3*Kp] = [hi | hi | lo]
+  float* g_patch_dw = nullptr;  // its weight-gradient GEMM output [W, 2*Kp] fp32 before the fold
+  int Kp = 0;
   std::vector<VitLayerA> va;
   bf16* vit_post = nullptr;
   float *vit_post_mean = nullptr, *vit_post_rstd = nullptr;

@@ -345,8 +345,19 @@ static int vision_backward(Engine& e, int B) {
     }
   }
   // patch embedding: fp32 weight / bias / position-embedding gradients (modeling_siglip.py:271-282)
-  patch_embed_bwd(e.batch_copy.images, e.g_x1, e.patch_w.g<float>(), e.patch_b.g<float>(), e.pos_emb.g<float>(), nullptr,
-                  nimg, c.image_size, c.vit_patch, W, st);
+  if (e.batch_copy.patch_rows != nullptr) {
+    // dW = dY^T X with X = hi + lo (the first two column blocks of the patch rows): one MN-major tcgen05 GEMM into
+    // [W, 2*Kp] fp32, folded into the fp32 [W, 3*p*p] gradient
+    GemmArgs g = mk_gemm(W, 2 * e.Kp, Mv, e.g_x1, W, e.batch_copy.patch_rows, 3 * e.Kp, e.g_patch_dw, 2 * e.Kp, EPI_F32);
+    g.a_major = 1;
+    g.b_major = 1;
+    CHECK_RC(engine_gemm(e, g));
+    fold_patch_dw(e.g_patch_dw, e.patch_w.g<float>(), W, 3 * c.vit_patch * c.vit_patch, e.Kp, st);
+    patch_embed_bwd_pos_bias(e.g_x1, e.patch_b.g<float>(), e.pos_emb.g<float>(), nimg, T, W, st);
+  } else {
+    patch_embed_bwd(e.batch_copy.images, e.g_x1, e.patch_w.g<float>(), e.patch_b.g<float>(), e.pos_emb.g<float>(), nullptr,
+                    nimg, c.image_size, c.vit_patch, W, st);
+  }
   CHECK_RC(exchange_range(e, e.xch.f32_vis));
   return 0;
 }

@@ -21,7 +21,10 @@ enum GemmEpilogue : int {
   EPI_GEGLU_BWD = 7,
   // Backward of gelu_tanh fused into the fc2 dgrad (SigLIP): acc = d(act); res = pre-activation; D = bf(bf(acc)*gelu'(pre))
   EPI_GELU_BWD = 8,
-  EPI_COUNT = 9,
+  // SigLIP patch embedding (modeling_siglip.py:271-282): D = bf( (acc + bias32[n]) + rowadd32[row % rowadd_period, n] ),
+  // fp32 bias and fp32 position embedding added in the reference's order before the single rounding to bf16
+  EPI_PATCH = 9,
+  EPI_COUNT = 10,
 };
 
 // Optional (EPI_STORE, decode): the RoPE + q/k/v split that consumes a fused qkv projection (rope_pack_fwd in kernels.h,
@@ -77,6 +80,11 @@ struct GemmArgs {
   void* norm_out = nullptr;
   void* norm_gate_out = nullptr;
   const GemmRope* rope = nullptr;
+  // EPI_PATCH: fp32 bias [N] and fp32 per-row addend table [rowadd_period, ld_rowadd]
+  const float* bias32 = nullptr;
+  const float* rowadd32 = nullptr;
+  int rowadd_period = 1;
+  int64_t ld_rowadd = 0;
 };
 
 // Enqueue on `stream`.  Returns 0 on success; on failure returns non-zero and fills `err` (if given).

@@ -456,6 +456,7 @@ int launch_gemm2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KP
     case EPI_F32: return launch2<EPI_F32>(ta, tb, kp, s, err, err_len);
     case EPI_GEGLU_BWD: return launch2<EPI_GEGLU_BWD>(ta, tb, kp, s, err, err_len);
     case EPI_GELU_BWD: return launch2<EPI_GELU_BWD>(ta, tb, kp, s, err, err_len);
+    case EPI_PATCH: return launch2<EPI_PATCH>(ta, tb, kp, s, err, err_len);
     default:
       if (err) snprintf(err, err_len, "unknown epilogue %d", epi);
       return 1;

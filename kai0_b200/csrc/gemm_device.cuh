@@ -41,6 +41,10 @@ struct KParams {
   float scale;
   int accumulate;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor geometry (overridable for bring-up: PI05_DBG_MN_LBO/SBO)
+  const float* bias32;      // EPI_PATCH
+  const float* rowadd32;
+  int rowadd_period;
+  long long ld_rowadd;
   int static_sched;         // 1: static `tile += grid` walk instead of the dynamic tile ring (PI05_GEMM_STATIC=1: A/B runs)
 };
 
@@ -303,6 +307,19 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, int z0, int z1, 
       stage_load_bf16(stage, lane, pre + col, p.ldres, rows_valid, nvalid, x);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]) * gelu_tanh_grad_f(x[i]);
+      __nv_bfloat16* d =
+          static_cast<__nv_bfloat16*>(p.D) + z0 * p.dbs + z1 * p.dbs1 + static_cast<long long>(row0) * p.ldd + col;
+      stage_write_bf16(stage, lane, v);
+      stage_flush_bf16(stage, lane, d, p.ldd, rows_valid, nvalid);
+    } else if constexpr (EPI == EPI_PATCH) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? __fadd_rn(v[i], p.bias32[col + i]) : 0.0f;
+      if (row_ok) {
+        const float* ra = p.rowadd32 + static_cast<long long>(row % p.rowadd_period) * p.ld_rowadd + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nvalid) v[i] = __fadd_rn(v[i], ra[i]);
+      }
       __nv_bfloat16* d =
           static_cast<__nv_bfloat16*>(p.D) + z0 * p.dbs + z1 * p.dbs1 + static_cast<long long>(row0) * p.ldd + col;
       stage_write_bf16(stage, lane, v);

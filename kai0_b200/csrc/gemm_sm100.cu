@@ -447,6 +447,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const KP
     case EPI_F32: return launch<BN, EPI_F32>(ta, tb, kp, s, err, err_len);
     case EPI_GEGLU_BWD: return launch<BN, EPI_GEGLU_BWD>(ta, tb, kp, s, err, err_len);
     case EPI_GELU_BWD: return launch<BN, EPI_GELU_BWD>(ta, tb, kp, s, err, err_len);
+    case EPI_PATCH: return launch<BN, EPI_PATCH>(ta, tb, kp, s, err, err_len);
     default:
       if (err) snprintf(err, err_len, "unknown epilogue %d", epi);
       return 1;
@@ -920,6 +921,14 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
   kp.ldgate = a.ldgate;
   kp.scale = a.scale;
   kp.accumulate = a.accumulate;
+  kp.bias32 = a.bias32;
+  kp.rowadd32 = a.rowadd32;
+  kp.rowadd_period = a.rowadd_period > 0 ? a.rowadd_period : 1;
+  kp.ld_rowadd = a.ld_rowadd;
+  if (a.epilogue == EPI_PATCH && (a.bias32 == nullptr || a.rowadd32 == nullptr)) {
+    if (err) snprintf(err, err_len, "gemm: EPI_PATCH needs bias32 and rowadd32");
+    return 1;
+  }
   kp.mn_lbo = BK * 128;
   kp.mn_sbo = 1024;
   // Dynamic tile scheduling pays one atomic round trip per kernel (~0.3 us on a 3-10 us decode GEMM: measured +0.5 ms on

@@ -117,6 +117,13 @@ void add_row0_grad(bf16* g, const float* dx, int B, int A, int E, cudaStream_t s
 size_t preprocess_scratch_floats(int batch, int out_size);
 void preprocess_image(const float* data, int height, int width, int channels_last, int batch, int out_size, int train,
                       int geometric, const float* params, float* scratch, float* out, cudaStream_t st);
+// Same preprocessing, written straight into the patch-embedding GEMM operand (row f2): `data` fp32 [-1,1] or uint8 (is_u8),
+// rows = bf16 [batch * (out_size/patch)^2, 3 * patch_row_kp(patch)] for THIS image key, column blocks [hi | lo | hi].
+// The padding columns [3*patch*patch, Kp) of every block are never written: the caller zero-fills the buffer once.
+inline int patch_row_kp(int patch) { return (3 * patch * patch + 7) / 8 * 8; }
+void preprocess_patches(const void* data, int is_u8, int height, int width, int channels_last, int batch, int out_size,
+                        int patch, int train, int geometric, const float* params, float* scratch, bf16* rows,
+                        cudaStream_t st);
 
 // ---------------- fp32 SIMT linears (sgemm_f32.cu) ----------------
 // Y[M,N] = X[M,K] W[N,K]^T + bias   (nn.Linear in fp32: action_in/out_proj, time MLP, adaRMS dense)
@@ -139,5 +146,10 @@ void patch_embed_fwd(const float* images, const float* W, const float* bias, con
 // dW[c, 3*p*p] , dbias[c], dpos[patch, c] from dout (bf16 [n_img*patches, width])
 void patch_embed_bwd(const float* images, const bf16* dout, float* dW, float* dbias, float* dpos, float* scratch,
                      int n_img, int image_size, int patch, int width, cudaStream_t st);
+void patch_embed_bwd_pos_bias(const bf16* dout, float* dbias, float* dpos, int n_img, int tokens, int width, cudaStream_t st);
+// patch-row path (row f2): Conv2d weight fp32 [rows, k] -> bf16 [rows, 3*kp] = [hi | hi | lo]; and the fold of the
+// weight-gradient GEMM's two column blocks back into the fp32 [rows, k] gradient
+void split_patch_weight(const float* w, bf16* out, int rows, int k, int kp, cudaStream_t st);
+void fold_patch_dw(const float* d, float* dw, int rows, int k, int kp, cudaStream_t st);
 
 }  // namespace pi05

@@ -15,12 +15,43 @@ namespace pi05 {
 namespace {
 
 struct Img {
-  const float* p;
+  const void* p;
   int h, w;
   int cl;  // 1: [B,h,w,3]; 0: [B,3,h,w]
+  int u8;  // 1: uint8 pixels, converted on the fly exactly as Observation.from_dict does (models/model.py:129-133:
+           //    img.astype(float32) / 255.0 * 2.0 - 1.0, three separately rounded fp32 operations); 0: fp32 in [-1,1]
   __device__ __forceinline__ float at(int b, int c, int y, int x) const {
     const int64_t base = static_cast<int64_t>(b) * 3 * h * w;
-    return cl ? p[base + (static_cast<int64_t>(y) * w + x) * 3 + c] : p[base + (static_cast<int64_t>(c) * h + y) * w + x];
+    const int64_t idx = cl ? base + (static_cast<int64_t>(y) * w + x) * 3 + c : base + (static_cast<int64_t>(c) * h + y) * w + x;
+    if (u8) {
+      const float v = static_cast<float>(static_cast<const uint8_t*>(p)[idx]);
+      return __fsub_rn(__fmul_rn(__fdiv_rn(v, 255.0f), 2.0f), 1.0f);
+    }
+    return static_cast<const float*>(p)[idx];
+  }
+};
+
+// Where a preprocessed pixel goes: the fp32 NCHW image (rows == nullptr), or straight into the operand of the patch-embedding
+// GEMM: bf16 rows [batch * T, 3 * Kp], row = b * T + patch index, column = c * p * p + (y % p) * p + (x % p)
+// (the Conv2d weight's [3, p, p] flattening, modeling_siglip.py:220-226), stored as the split v = hi + lo with
+// hi = bf16(v), lo = bf16(v - hi) in three column blocks [hi | lo | hi] (see engine.cu::vision_forward for why).
+struct Sink {
+  float* nchw;
+  bf16* rows;
+  int S, p, P, Kp;
+  __device__ __forceinline__ void put(int b, int c, int y, int x, float v) const {
+    if (rows == nullptr) {
+      nchw[((static_cast<int64_t>(b) * 3 + c) * S + y) * S + x] = v;
+      return;
+    }
+    const int64_t row = static_cast<int64_t>(b) * P * P + (y / p) * P + (x / p);
+    const int col = c * p * p + (y % p) * p + (x % p);
+    const bf16 hi = __float2bfloat16_rn(v);
+    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    bf16* r = rows + row * (3 * Kp) + col;
+    r[0] = hi;
+    r[Kp] = lo;
+    r[2 * Kp] = hi;
   }
 };
 
@@ -36,7 +67,7 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 }
 
 // image_tools.py:55-126 for fp32 input: out NCHW [B,3,S,S]
-__global__ void resize_pad_k(Img src, int S, int rh, int rw, int ph0, int pw0, float* __restrict__ out, int B) {
+__global__ void resize_pad_k(Img src, int S, int rh, int rw, int ph0, int pw0, Sink out, int B) {
   pdl_enter();
   const int64_t total = static_cast<int64_t>(B) * 3 * S * S;
   const float sh = static_cast<float>(src.h) / rh, sw = static_cast<float>(src.w) / rw;
@@ -55,12 +86,12 @@ __global__ void resize_pad_k(Img src, int S, int rh, int rw, int ph0, int pw0, f
           ly1 * (lx0 * src.at(b, c, y1, x0) + lx1 * src.at(b, c, y1, x1));
       v = fminf(fmaxf(v, -1.0f), 1.0f);
     }
-    out[i] = v;
+    out.put(b, c, y, x, v);
   }
 }
 
 // plain layout change to NCHW (no resize, no augmentation)
-__global__ void to_nchw_k(Img src, float* __restrict__ out, int B) {
+__global__ void to_nchw_k(Img src, Sink out, int B) {
   pdl_enter();
   const int S = src.h;
   const int64_t total = static_cast<int64_t>(B) * 3 * S * S;
@@ -68,7 +99,7 @@ __global__ void to_nchw_k(Img src, float* __restrict__ out, int B) {
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % S), y = static_cast<int>((i / S) % S);
     const int c = static_cast<int>((i / (static_cast<int64_t>(S) * S)) % 3), b = static_cast<int>(i / (3LL * S * S));
-    out[i] = src.at(b, c, y, x);
+    out.put(b, c, y, x, src.at(b, c, y, x));
   }
 }
 
@@ -176,7 +207,7 @@ __global__ void __launch_bounds__(256) augment_geo_k(Img im, const float* __rest
 
 // pass 2: colour (preprocessing_pytorch.py:122-146)
 __global__ void __launch_bounds__(256) augment_colour_k(const float* __restrict__ tmp, const float* __restrict__ partial,
-                                                        const float* __restrict__ params, int S, float* __restrict__ out) {
+                                                        const float* __restrict__ params, int S, Sink out) {
   pdl_enter();
   const int b = blockIdx.y, npix = S * S;
   const float bright = params[3], contrast = params[4], satur = params[5];
@@ -184,7 +215,6 @@ __global__ void __launch_bounds__(256) augment_colour_k(const float* __restrict_
   for (int i = 0; i < kGeoBlocks; ++i) tot += partial[b * kGeoBlocks + i];
   const float mean = tot / static_cast<float>(3 * npix);
   const float* in = tmp + static_cast<int64_t>(b) * 3 * npix;
-  float* o = out + static_cast<int64_t>(b) * 3 * npix;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
     float v[3];
 #pragma unroll
@@ -197,7 +227,7 @@ __global__ void __launch_bounds__(256) augment_colour_k(const float* __restrict_
     for (int c = 0; c < 3; ++c) {
       float x = gray + (v[c] - gray) * satur;
       x = fminf(fmaxf(x, 0.f), 1.f);
-      o[c * npix + pix] = x * 2.0f - 1.0f;
+      out.put(b, c, pix / S, pix % S, x * 2.0f - 1.0f);
     }
   }
 }
@@ -213,11 +243,10 @@ size_t preprocess_scratch_floats(int batch, int out_size) {
   return static_cast<size_t>(2) * batch * 3 * out_size * out_size + static_cast<size_t>(batch) * kGeoBlocks;
 }
 
-void preprocess_image(const float* data, int height, int width, int channels_last, int batch, int out_size, int train,
-                      int geometric, const float* params, float* scratch, float* out, cudaStream_t st) {
-  const int S = out_size;
+static void preprocess_any(Img src, int batch, int out_size, int train, int geometric, const float* params,
+                           float* scratch, Sink out, cudaStream_t st) {
+  const int S = out_size, height = src.h, width = src.w;
   const int64_t n = static_cast<int64_t>(batch) * 3 * S * S;
-  Img src{data, height, width, channels_last};
   float* resized = scratch;      // [B,3,S,S]
   float* tmp = scratch + n;      // [B,3,S,S]
   float* partial = scratch + 2 * n;
@@ -226,11 +255,11 @@ void preprocess_image(const float* data, int height, int width, int channels_las
     const double ratio = std::max(static_cast<double>(width) / S, static_cast<double>(height) / S);  // image_tools.py:88
     const int rh = static_cast<int>(height / ratio), rw = static_cast<int>(width / ratio);
     const int ph0 = (S - rh) / 2, pw0 = (S - rw) / 2;
-    float* dst = train ? resized : out;
+    const Sink dst = train ? Sink{resized, nullptr, S, 1, 1, 0} : out;
     launch_pdl(resize_pad_k, dim3(blocks_for(n)), dim3(256), 0, st, src, S, rh, rw, ph0, pw0, dst, batch);
     count_launch();
     if (!train) return;
-    cur = Img{resized, S, S, 0};
+    cur = Img{resized, S, S, 0, 0};
   } else if (!train) {
     launch_pdl(to_nchw_k, dim3(blocks_for(n)), dim3(256), 0, st, src, out, batch);
     count_launch();
@@ -241,6 +270,20 @@ void preprocess_image(const float* data, int height, int width, int channels_las
   count_launch();
   launch_pdl(augment_colour_k, dim3(grid), dim3(256), 0, st, tmp, partial, params, S, out);
   count_launch();
+}
+
+void preprocess_image(const float* data, int height, int width, int channels_last, int batch, int out_size, int train,
+                      int geometric, const float* params, float* scratch, float* out, cudaStream_t st) {
+  preprocess_any(Img{data, height, width, channels_last, 0}, batch, out_size, train, geometric, params, scratch,
+                 Sink{out, nullptr, out_size, 1, 1, 0}, st);
+}
+
+void preprocess_patches(const void* data, int is_u8, int height, int width, int channels_last, int batch, int out_size,
+                        int patch, int train, int geometric, const float* params, float* scratch, bf16* rows,
+                        cudaStream_t st) {
+  const int Kp = patch_row_kp(patch);
+  preprocess_any(Img{data, height, width, channels_last, is_u8}, batch, out_size, train, geometric, params, scratch,
+                 Sink{nullptr, rows, out_size, patch, out_size / patch, Kp}, st);
 }
 
 }  // namespace pi05

@@ -279,10 +279,59 @@ void patch_embed_bwd(const float* images, const bf16* dout, float* dW, float* db
   const int splits = rows >= 4096 ? 16 : 1;
   run(LinearBF16{dout, 1, width}, Im2colT{Im2col{images, image_size, patch, P}}, EpiF32{dW, K, nullptr, 2}, width, K,
       rows, splits, st);
-  const int64_t total = static_cast<int64_t>(P) * P * width;
-  launch_pdl(patch_dpos_k, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, dout, dpos, n_img, P * P, width); count_launch();
-  // dbias = column sum of dpos
-  launch_pdl(colsum_f32_k, dim3((width + 127) / 128), dim3(128), 0, st, dpos, P * P, width, dbias); count_launch();
+  patch_embed_bwd_pos_bias(dout, dbias, dpos, n_img, P * P, width, st);
+}
+
+// d(position embedding)[t, c] = sum over images of dout[img, t, c]; d(bias)[c] = column sum of that
+void patch_embed_bwd_pos_bias(const bf16* dout, float* dbias, float* dpos, int n_img, int tokens, int width,
+                              cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(tokens) * width;
+  launch_pdl(patch_dpos_k, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, dout, dpos, n_img, tokens, width); count_launch();
+  launch_pdl(colsum_f32_k, dim3((width + 127) / 128), dim3(128), 0, st, dpos, tokens, width, dbias); count_launch();
+}
+
+namespace {
+// fp32 weight [rows, k] -> bf16 [rows, 3 * kp] = [hi | hi | lo] with hi = bf16(w), lo = bf16(w - hi); padding columns zero
+__global__ void __launch_bounds__(256) split_weight_k(const float* __restrict__ w, bf16* __restrict__ out, int rows, int k,
+                                                      int kp) {
+  pdl_enter();
+  const int64_t total = static_cast<int64_t>(rows) * kp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / kp), c = static_cast<int>(i % kp);
+    bf16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    if (c < k) {
+      const float v = w[static_cast<int64_t>(r) * k + c];
+      hi = __float2bfloat16_rn(v);
+      lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    bf16* o = out + static_cast<int64_t>(r) * 3 * kp + c;
+    o[0] = hi;
+    o[kp] = hi;
+    o[2 * kp] = lo;
+  }
+}
+// dW[r, c] = d[r, c] + d[r, kp + c]   (the two column blocks [hi | lo] of the split input)
+__global__ void __launch_bounds__(256) fold_patch_dw_k(const float* __restrict__ d, float* __restrict__ dw, int rows, int k,
+                                                       int kp) {
+  pdl_enter();
+  const int64_t total = static_cast<int64_t>(rows) * k;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / k), c = static_cast<int>(i % k);
+    const float* s = d + static_cast<int64_t>(r) * 2 * kp + c;
+    dw[i] = s[0] + s[kp];
+  }
+}
+}  // namespace
+
+void split_patch_weight(const float* w, bf16* out, int rows, int k, int kp, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(rows) * kp;
+  launch_pdl(split_weight_k, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, w, out, rows, k, kp); count_launch();
+}
+void fold_patch_dw(const float* d, float* dw, int rows, int k, int kp, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(rows) * k;
+  launch_pdl(fold_patch_dw_k, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, d, dw, rows, k, kp); count_launch();
 }
 
 }  // namespace pi05

@@ -219,6 +219,17 @@ def _attach(root: nn.Module, dotted: str, param: nn.Parameter, top_cls=_Node):
     mod.register_parameter(parts[-1], param)
 
 
+class _PatchRows:
+    """The preprocessed images of one batch, already laid out as the patch-embedding GEMM operand (pi05_batch.patch_rows)."""
+
+    def __init__(self, rows: Tensor, num_images: int):
+        self.rows = rows
+        self.num_images = num_images
+
+    def __len__(self):
+        return self.num_images
+
+
 class _EngineFunction(torch.autograd.Function):
     """One autograd node for the whole network: forward = pi05_forward, backward = pi05_backward.
 
@@ -306,6 +317,9 @@ class PI0Pytorch(nn.Module):
         # preprocessing with train=True (pi0_pytorch.py:318), so this is on by default; parity tests that compare
         # against un-augmented oracles switch it off or inject the drawn parameters (_augment_params_override).
         self.augment = True
+        # preprocessing writes straight into the patch-embedding GEMM operand (row f2); False: fp32 NCHW images + the fp32
+        # im2col convolution on CUDA cores (round-1 path, kept as the cross-check in tests/test_preprocess_gpu.py)
+        self.use_patch_rows = True
         self._augment_params_override = None
         self._pre_scratch = None
 
@@ -702,10 +716,13 @@ class PI0Pytorch(nn.Module):
             p[i, 5:6] = 0.5 + torch.rand(1, device=dev) * 1.0
         return p
 
-    def _preprocess_observation(self, observation, *, train=True):
-        """preprocessing_pytorch.py:20-173 on the device (pi05_preprocess_image per key): layout sniffing, resize-with-pad
-        to image_size, train-time augmentation, default masks.  Returns the images already stacked in the engine's
-        layout, fp32 [num_images, B, 3, S, S]."""
+    def _preprocess_observation(self, observation, *, train=True, rows=False, engine_train=None):
+        """preprocessing_pytorch.py:20-173 on the device, one launch group per image key: layout sniffing, resize-with-pad
+        to image_size, train-time augmentation, default masks.  Images may be fp32 in [-1, 1] (what Observation.from_dict
+        hands over) or uint8 -- then from_dict's `x / 255 * 2 - 1` (models/model.py:129-133) is taken inside the kernel.
+        rows=False: returns the images stacked in the engine's layout, fp32 [num_images, B, 3, S, S] (pi05_preprocess_image).
+        rows=True (what forward / sample_actions use, `use_patch_rows`): the kernels write straight into the operand of the
+        patch-embedding GEMM (pi05_preprocess_patches) and a `_PatchRows` handle is returned."""
         images = getattr(observation, "images")
         keys = self._image_keys(images)
         state = observation.state
@@ -719,7 +736,23 @@ class PI0Pytorch(nn.Module):
         B = int(state.shape[0])
         aug = bool(train and self.augment and self._apply_aug)
         l = _lib.lib()
-        out = torch.empty((len(keys), B, 3, S, S), dtype=torch.float32, device=dev)
+        patch = self.ecfg.vit_patch
+        if rows:
+            kp = int(l.pi05_patch_row_kp(patch))
+            T = (S // patch) ** 2
+            # Owned by the active engine (train and inference engines have their own, so a validation forward cannot
+            # overwrite the rows a pending backward still reads) and zero-filled ONCE: the kernels never touch the padding
+            # columns [3 p^2, Kp) of each block, which must read as 0 in the GEMM.
+            ent = {}
+            if engine_train is not None:  # the engine that will consume the rows becomes the active one first
+                self._ensure_engine(B, train=bool(engine_train), num_images=len(keys))
+                ent = self._engine_ent
+            out = ent.get("rows")
+            if out is None or out.shape != (len(keys) * B * T, 3 * kp):
+                out = torch.zeros((len(keys) * B * T, 3 * kp), dtype=torch.bfloat16, device=dev)
+                ent["rows"] = out
+        else:
+            out = torch.empty((len(keys), B, 3, S, S), dtype=torch.float32, device=dev)
         need = l.pi05_preprocess_scratch_floats(B, S)
         if self._pre_scratch is None or self._pre_scratch.numel() < need or self._pre_scratch.device != dev:
             self._pre_scratch = torch.empty(need, dtype=torch.float32, device=dev)
@@ -727,6 +760,7 @@ class PI0Pytorch(nn.Module):
         out_masks = []
         masks = getattr(observation, "image_masks", {}) or {}
         stream = self._stream()
+        keep = []
         for i, key in enumerate(keys):
             img = images[key]
             if img.dim() != 4 or img.shape[0] != B:
@@ -735,21 +769,40 @@ class PI0Pytorch(nn.Module):
             if not channels_first and img.shape[-1] != 3:
                 raise ValueError(f"image {key} has neither 3 channels first nor last: {tuple(img.shape)}")
             h, w = (img.shape[2], img.shape[3]) if channels_first else (img.shape[1], img.shape[2])
-            if img.dtype != torch.float32:
-                raise ValueError(f"image {key} must be float32 in [-1, 1] (Observation.from_dict converts uint8), got {img.dtype}")
+            if img.dtype == torch.uint8:
+                if not rows:
+                    # the fp32-image entry point mirrors the reference's function, which only ever sees from_dict's output
+                    img = img.to(dev).to(torch.float32) / 255.0 * 2.0 - 1.0
+            elif img.dtype != torch.float32:
+                raise ValueError(f"image {key} must be uint8 or float32 in [-1, 1] (Observation.from_dict), got {img.dtype}")
             img = img.to(dev).contiguous()
-            _lib.check(
-                l.pi05_preprocess_image(
-                    C.c_void_p(img.data_ptr()), int(h), int(w), 0 if channels_first else 1, B, S, 1 if aug else 0,
-                    0 if "wrist" in key else 1, C.c_void_p(params[i].data_ptr()) if aug else None,
-                    C.c_void_p(self._pre_scratch.data_ptr()), C.c_void_p(out[i].data_ptr()), stream,
-                ),
-                "pi05_preprocess_image",
-            )
+            keep.append(img)
+            p_i = C.c_void_p(params[i].data_ptr()) if aug else None
+            if rows:
+                _lib.check(
+                    l.pi05_preprocess_patches(
+                        C.c_void_p(img.data_ptr()), 3 if img.dtype == torch.uint8 else 0, int(h), int(w),
+                        0 if channels_first else 1, B, S, patch, 1 if aug else 0, 0 if "wrist" in key else 1, p_i,
+                        C.c_void_p(self._pre_scratch.data_ptr()),
+                        C.c_void_p(out.data_ptr() + i * B * T * 3 * kp * 2), stream,
+                    ),
+                    "pi05_preprocess_patches",
+                )
+            else:
+                _lib.check(
+                    l.pi05_preprocess_image(
+                        C.c_void_p(img.data_ptr()), int(h), int(w), 0 if channels_first else 1, B, S, 1 if aug else 0,
+                        0 if "wrist" in key else 1, p_i, C.c_void_p(self._pre_scratch.data_ptr()),
+                        C.c_void_p(out[i].data_ptr()), stream,
+                    ),
+                    "pi05_preprocess_image",
+                )
             if key in masks:
                 out_masks.append(masks[key])
             else:
                 out_masks.append(torch.ones(batch_shape, dtype=torch.bool, device=state.device))
+        if rows:
+            out = _PatchRows(out, len(keys))
         return out, out_masks, observation.tokenized_prompt, observation.tokenized_prompt_mask, state
 
     def _image_keys(self, images):
@@ -761,7 +814,10 @@ class PI0Pytorch(nn.Module):
         dev = self._device()
         if len(images) != self._engine_key[3]:
             raise ValueError(f"expected {self._engine_key[3]} images, got {len(images)}")
-        if isinstance(images, torch.Tensor):
+        rows = None
+        if isinstance(images, _PatchRows):
+            rows, imgs = images.rows, images.rows  # kept alive through `keep`
+        elif isinstance(images, torch.Tensor):
             imgs = images  # already [num_images, B, 3, S, S] fp32 from _preprocess_observation
         else:
             imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
@@ -775,7 +831,8 @@ class PI0Pytorch(nn.Module):
             raise ValueError("token id out of range")
         b = _lib.Batch()
         b.batch = B
-        b.images = imgs.data_ptr()
+        b.images = imgs.data_ptr() if rows is None else None
+        b.patch_rows = rows.data_ptr() if rows is not None else None
         b.image_masks = masks.data_ptr()
         b.tokens = toks.data_ptr()
         b.token_mask = tmask.data_ptr()
@@ -846,7 +903,11 @@ class PI0Pytorch(nn.Module):
     # ------------------------------------------------------------------ public surface
     def forward(self, observation, actions, noise=None, time=None) -> Tensor:
         """Training forward (pi0_pytorch.py:316-373): returns the un-reduced loss [B, horizon, action_dim] fp32."""
-        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=True)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # (the reference draws the augmentation parameters first, then noise, then time: same order here)
+        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(
+            observation, train=True, rows=self.use_patch_rows, engine_train=need_grad)
+        self._ensure_engine(int(actions.shape[0]), train=need_grad, num_images=len(images))
         dev = self._device()
         actions = actions.to(dev, torch.float32).contiguous()
         if noise is None:
@@ -855,9 +916,6 @@ class PI0Pytorch(nn.Module):
             time = self.sample_time(actions.shape[0], actions.device)
         noise = noise.to(dev, torch.float32).contiguous()
         time = time.to(dev, torch.float32).contiguous()
-        B = actions.shape[0]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        self._ensure_engine(B, train=need_grad, num_images=len(images))
         pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         return self._run_training_forward(pack, actions, noise, time, need_grad)
 
@@ -882,7 +940,8 @@ class PI0Pytorch(nn.Module):
     @torch.no_grad()
     def sample_actions(self, device, observation, noise=None, num_steps=10) -> Tensor:
         """Inference (pi0_pytorch.py:375-419): prefix pass + KV cache, then `num_steps` Euler steps."""
-        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(observation, train=False)
+        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(
+            observation, train=False, rows=self.use_patch_rows, engine_train=False)
         bsize = state.shape[0]
         dev = self._device()
         if noise is None:
@@ -908,7 +967,8 @@ class PI0Pytorch(nn.Module):
         """The decode path is ~2400 small launches for one observation; replaying them as ONE CUDA graph removes the
         per-launch host cost.  Static device buffers hold the inputs; the graph is captured once per (batch, steps)."""
         imgs, masks, toks, tmask = keep
-        key = (b.batch, num_steps)
+        is_rows = bool(b.patch_rows)
+        key = (b.batch, num_steps, is_rows)
         ent = self._graphs.get(key)
         l = _lib.lib()
         if ent is None:
@@ -916,7 +976,9 @@ class PI0Pytorch(nn.Module):
                       out=torch.empty_like(noise))
             sb = _lib.Batch()
             sb.batch = b.batch
-            sb.images, sb.image_masks = st["imgs"].data_ptr(), st["masks"].data_ptr()
+            sb.images = None if is_rows else st["imgs"].data_ptr()
+            sb.patch_rows = st["imgs"].data_ptr() if is_rows else None
+            sb.image_masks = st["masks"].data_ptr()
             sb.tokens, sb.token_mask = st["toks"].data_ptr(), st["tmask"].data_ptr()
             l.pi05_set_taps(self._engine, 0)
 
@@ -1000,7 +1062,9 @@ class AdvantageEstimator(PI0Pytorch):
         progress = getattr(observation, "progress", None)
         if progress is None:
             raise ValueError("AdvantageEstimator.forward needs observation.progress (pi0_pytorch.py:574)")
-        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(observation, train=self.training)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        images, img_masks, lang_tokens, lang_masks, _state = self._preprocess_observation(
+            observation, train=self.training, rows=self.use_patch_rows, engine_train=need_grad)
         dev = self._device()
         actions = actions.to(dev, torch.float32).contiguous()
         if noise is None:
@@ -1011,7 +1075,6 @@ class AdvantageEstimator(PI0Pytorch):
         time = time.to(dev, torch.float32).contiguous()
         B = actions.shape[0]
         self._adv_progress = progress.to(dev, torch.float32).reshape(B).contiguous()
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         self._ensure_engine(B, train=need_grad, num_images=len(images))
         pack = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         loss = self._run_training_forward(pack, actions, noise, time, need_grad)
@@ -1023,7 +1086,8 @@ class AdvantageEstimator(PI0Pytorch):
     @torch.no_grad()
     def sample_values(self, device, observation) -> Tensor:
         """pi0_pytorch.py:596-644: value (progress) of the current observation, [B, 1] fp32."""
-        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(observation, train=False)
+        images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(
+            observation, train=False, rows=self.use_patch_rows, engine_train=False)
         bsize = state.shape[0]
         dev = self._device()
         noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev).contiguous()
