@@ -262,9 +262,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]/[2]: 32)")
     ap.add_argument("--ref-budget", type=float, default=420.0,
                     help="--impl reference: seconds the whole run (build + warm-up + K steps) should stay within")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N>1: exchange the gradients after backward (two torch.distributed all-reduces) instead of the "
-                         "engine's overlapped chunked exchange")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N>1: the engine's chunked exchange overlapped with backward instead of one exchange at the end of "
+                         "backward (measured slower on power-capped B200s: profiles/r02_exchange_overlap.md)")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the reference_gpu anchor (the reference's own eager module timed on this GPU, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -342,9 +342,10 @@ def main():
     model.train()
     use_fused = not (args.per_param_optimizer or args.torch_optimizer)
     if world > 1:
-        # engine-owned exchange: chunked ncclAllReduce overlapped with backward; with the fused optimiser the 1/world
-        # average is folded into the update instead of a separate pass over the 7 GB of gradients
-        model.enable_flat_allreduce(overlap=not args.no_overlap, average="optimizer" if use_fused else "in_place")
+        # engine-owned exchange (pi05_set_grad_exchange): ncclAllReduce of the two gradient arenas issued by pi05_backward
+        # itself; with the fused optimiser the 1/world average is folded into the update instead of a separate pass over
+        # the 7 GB of gradients
+        model.enable_flat_allreduce(overlap=args.overlap, average="optimizer" if use_fused else "in_place")
     # optimiser over the two flat arenas (public opt-in): element-wise identical to the per-parameter
     # AdamW / global-norm clip of train_pytorch.py:469-475,557, in 2 tensors instead of ~700
     params = model.flat_parameters() if not args.per_param_optimizer else [p for p in model.parameters() if p.requires_grad]

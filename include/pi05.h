@@ -211,18 +211,23 @@ int pi05_fused_clip_adamw_scaled(void* p_bf16, const void* g_bf16, void* m_bf16,
  * `nccl_comm` is an ncclComm_t created by the caller over the data-parallel ranks (libnccl is resolved at run time with
  * dlopen: the library has no link-time NCCL dependency).
  *
- * pi05_set_grad_exchange: from now on pi05_backward itself exchanges the gradients, OVERLAPPED with the rest of backward:
- * as soon as the kernels producing one contiguous group of the gradient arena (an expert layer, a PaliGemma layer, the fp32
- * norm / adaRMS / head block, the embedding table, groups of SigLIP layers) are enqueued, a ncclAllReduce(sum) of that range
- * is enqueued on an engine-owned high-priority stream behind an event; at the end of pi05_backward the caller's stream
- * waits for the exchange stream.  average_in_place != 0: every range is also multiplied by 1 / nranks on the exchange
- * stream (what DDP's averaging leaves in .grad); 0: the arenas hold sums and the caller folds 1 / nranks into its
- * optimiser (pi05_fused_clip_adamw_scaled).  nccl_comm = NULL switches the exchange off again.
- * The tcgen05 GEMMs schedule tiles dynamically, so the few SMs the NCCL kernels occupy cost their share and no more.
+ * pi05_set_grad_exchange: from now on pi05_backward itself exchanges the gradients (sum all-reduce of both arenas, the
+ * never-used expert lm_head excluded) before it returns control of `stream`:
+ *   overlap = 0: ONE exchange at the end of backward on the caller's stream, at NCCL's full speed;
+ *   overlap = 1: OVERLAPPED with backward: as soon as the kernels producing one contiguous group of the gradient arena
+ *     (an expert layer, a PaliGemma layer, the fp32 norm / adaRMS / head block, the embedding table, groups of SigLIP
+ *     layers) are enqueued, a ncclAllReduce of that range is enqueued on an engine-owned high-priority stream behind an
+ *     event; at the end the caller's stream waits for that stream.  Create the communicator with few CTAs for this mode
+ *     (pi05_nccl_comm_create max_ctas): the tcgen05 GEMMs schedule tiles dynamically, so the SMs the NCCL kernels hold cost
+ *     their share and no more.  Measured on power-capped B200s the overlapped mode is SLOWER (N = 2: 479 vs 471 ms,
+ *     N = 8: 483-486 vs 478 ms per step): the NCCL kernels' power comes out of the GEMMs' clock.  It is kept for parts
+ *     that are not power-limited; overlap = 0 is what bench.py uses.
+ * average_in_place != 0: every range is also multiplied by 1 / nranks (what DDP's averaging leaves in .grad); 0: the
+ * arenas hold sums and the caller folds 1 / nranks into its optimiser (pi05_fused_clip_adamw_scaled).
+ * nccl_comm = NULL switches the exchange off again.
  *
- * pi05_allreduce_grads: the same exchange as ONE blocking-order step on `stream` after pi05_backward (no overlap): sum
- * all-reduce of both gradient arenas (the never-used expert lm_head excluded), then 1 / nranks when average != 0. */
-int pi05_set_grad_exchange(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_t average_in_place);
+ * pi05_allreduce_grads: the overlap = 0 exchange as a separate call on `stream` after pi05_backward. */
+int pi05_set_grad_exchange(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_t average_in_place, int32_t overlap);
 int pi05_allreduce_grads(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_t average, void* stream);
 /* Communicator helpers for hosts without an NCCL binding of their own (the Python host uses them through ctypes):
  * rank 0 calls pi05_nccl_unique_id (128 bytes out) and ships the id to every rank by its own means (torch.distributed's

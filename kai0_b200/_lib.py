@@ -227,7 +227,7 @@ def lib() -> C.CDLL:
             )
         if hasattr(l, "pi05_set_grad_exchange"):
             l.pi05_set_grad_exchange.restype = C.c_int
-            l.pi05_set_grad_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+            l.pi05_set_grad_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
             l.pi05_allreduce_grads.restype = C.c_int
             l.pi05_allreduce_grads.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
             l.pi05_grad_exchange_stats.restype = C.c_int

@@ -104,13 +104,13 @@ void pi05_destroy(pi05_engine* e) {
   delete E(e);
 }
 
-int pi05_set_grad_exchange(pi05_engine* pe, void* nccl_comm, int32_t nranks, int32_t average_in_place) {
+int pi05_set_grad_exchange(pi05_engine* pe, void* nccl_comm, int32_t nranks, int32_t average_in_place, int32_t overlap) {
   Engine* e = E(pe);
   if (!e) {
     pi05::set_error("pi05_set_grad_exchange: null engine");
     return 1;
   }
-  return pi05::exchange_setup(*e, nccl_comm, nranks, average_in_place);
+  return pi05::exchange_setup(*e, nccl_comm, nranks, average_in_place, overlap);
 }
 
 int pi05_allreduce_grads(pi05_engine* pe, void* nccl_comm, int32_t nranks, int32_t average, void* stream) {

@@ -119,7 +119,7 @@ int reduce_on(Engine& e, const GRange& r, void* comm, int nranks, bool average, 
 
 }  // namespace
 
-int exchange_setup(Engine& e, void* comm, int nranks, int average_in_place) {
+int exchange_setup(Engine& e, void* comm, int nranks, int average_in_place, int overlap) {
   GradExchange& x = e.xch;
   if (comm == nullptr) {
     x.comm = nullptr;
@@ -154,6 +154,7 @@ int exchange_setup(Engine& e, void* comm, int nranks, int average_in_place) {
   x.comm = comm;
   x.nranks = nranks;
   x.average_in_place = average_in_place != 0;
+  x.overlap = overlap != 0;
   return 0;
 }
 
@@ -176,7 +177,7 @@ void exchange_begin(Engine& e) {
 
 int exchange_range(Engine& e, const GRange& r) {
   GradExchange& x = e.xch;
-  if (x.comm == nullptr || !x.chunked || !r.valid()) return 0;
+  if (x.comm == nullptr || !x.overlap || !x.chunked || !r.valid()) return 0;
   cudaEvent_t ev = x.events[x.ev_cursor++ % x.events.size()];
   cudaEventRecord(ev, e.stream);        // everything that writes this range is enqueued before this point
   cudaStreamWaitEvent(x.stream, ev, 0);
@@ -201,6 +202,13 @@ int exchange_ranges(Engine& e, const GRange& a, const GRange& b) {
 int exchange_finish(Engine& e) {
   GradExchange& x = e.xch;
   if (x.comm == nullptr) return 0;
+  if (!x.overlap) {
+    // one exchange of both arenas on the compute stream right behind backward, at NCCL's full speed.  On the power-capped
+    // B200s this was measured FASTER than the overlapped mode at N = 2 and N = 8 (profiles/r02_exchange_overlap.md).
+    int rc = x.all_bf16.valid() ? reduce_on(e, x.all_bf16, x.comm, x.nranks, x.average_in_place, e.stream) : 0;
+    if (rc == 0 && x.all_f32.valid()) rc = reduce_on(e, x.all_f32, x.comm, x.nranks, x.average_in_place, e.stream);
+    return rc;
+  }
   if (!x.chunked) {  // ranges could not be verified at bind time: one exchange of both arenas behind backward
     cudaEvent_t ev = x.events[x.ev_cursor++ % x.events.size()];
     cudaEventRecord(ev, e.stream);

@@ -19,6 +19,7 @@ struct GradExchange {
   void* comm = nullptr;  // ncclComm_t (opaque)
   int nranks = 1;
   bool average_in_place = false;
+  bool overlap = false;  // true: chunk by chunk under backward on `stream`; false: one exchange at the end of backward
   bool chunked = false;  // group ranges verified contiguous at bind time
   cudaStream_t stream = nullptr;       // engine-owned, highest priority
   std::vector<cudaEvent_t> events;     // ready[i]: producing kernels enqueued on the compute stream
@@ -31,7 +32,7 @@ struct GradExchange {
 };
 
 struct Engine;
-int exchange_setup(Engine& e, void* comm, int nranks, int average_in_place);
+int exchange_setup(Engine& e, void* comm, int nranks, int average_in_place, int overlap);
 void exchange_destroy(Engine& e);
 void exchange_begin(Engine& e);                                 // start of a backward
 int exchange_range(Engine& e, const GRange& r);                 // "this range is final on e.stream"

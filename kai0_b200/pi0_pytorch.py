@@ -370,6 +370,7 @@ class PI0Pytorch(nn.Module):
         self._dp_group = None
         self._dp_comm = None
         self._dp_overlap = False
+        self._dp_engine = False
         self._dp_average = "in_place"
         self._dp_world = 1
         self._dp_max_ctas = 0
@@ -484,16 +485,17 @@ class PI0Pytorch(nn.Module):
         self._flat_params[0].grad = gb[: self._flat_used_bf16]
         self._flat_params[1].grad = gf
 
-    def enable_flat_allreduce(self, process_group=None, *, overlap: bool | None = None, average: str = "in_place",
+    def enable_flat_allreduce(self, process_group=None, *, overlap: bool = False, average: str = "in_place",
                               max_ctas: int | None = None):
         """Engine-owned data parallelism, INSTEAD of wrapping the module in DistributedDataParallel
         (train_pytorch.py:440-447): the gradient arenas are all-reduced over the group and averaged, as DDP's bucketed
-        all-reduce does.
+        all-reduce does.  On a CUDA module whose group runs on NCCL the ENGINE issues the collectives from inside
+        pi05_backward on a communicator of its own (pi05_set_grad_exchange; the unique id travels through
+        torch.distributed); otherwise (gloo / CPU tests) two torch.distributed all-reduces follow backward.
 
-        overlap=True (default on a CUDA module whose group runs on NCCL): the engine itself issues the collectives, chunk by chunk, while backward is still
-        running (pi05_set_grad_exchange): a dedicated NCCL communicator over the group's ranks, restricted to `max_ctas`
-        SMs (default 4, PI05_NCCL_MAX_CTAS), on an engine-owned high-priority stream; the GEMMs' dynamic tile schedule
-        absorbs the SMs NCCL holds.  overlap=False: two torch.distributed all-reduces after backward (round-1 behaviour).
+        overlap=False (default): one exchange at the end of backward at NCCL's full speed.  overlap=True: chunk by chunk
+        while backward is still running, on a communicator restricted to `max_ctas` SMs (default 4, PI05_NCCL_MAX_CTAS) --
+        measured slower on power-capped B200s (see include/pi05.h), kept as an option.
         average="in_place": .grad holds the average (any optimiser works);  "optimizer": .grad holds the SUM and
         `kai0_b200.optim.FusedClipAdamW` applies 1 / world on the fly (saves a 14 GB read-modify-write per step)."""
         import torch.distributed as dist
@@ -502,20 +504,19 @@ class PI0Pytorch(nn.Module):
             raise ValueError("average must be 'in_place' or 'optimizer'")
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
         self._dp_world = dist.get_world_size(self._dp_group)
-        if overlap is None:
-            overlap = self._device().type == "cuda" and "nccl" in str(dist.get_backend(self._dp_group))
+        self._dp_engine = self._device().type == "cuda" and "nccl" in str(dist.get_backend(self._dp_group))
+        if overlap and not self._dp_engine:
+            raise RuntimeError("enable_flat_allreduce(overlap=True) needs a CUDA module and an NCCL process group")
         self._dp_overlap = bool(overlap)
         self._dp_average = average
         self.grad_scale = 1.0 / self._dp_world if average == "optimizer" else 1.0
         self.direct_grads = True  # no DDP hooks to feed, so gradients can be handed over without autograd copies
-        if self._dp_overlap and self._dp_comm is None:
+        if self._dp_engine and self._dp_comm is None:
             import os
 
             dev = self._device()
-            if dev.type != "cuda":
-                raise RuntimeError("enable_flat_allreduce(overlap=True): move the module to its CUDA device first")
             if max_ctas is None:
-                max_ctas = int(os.environ.get("PI05_NCCL_MAX_CTAS", "4"))
+                max_ctas = int(os.environ.get("PI05_NCCL_MAX_CTAS", "4")) if overlap else 0  # 0 = NCCL's default
             rank = dist.get_rank(self._dp_group)
             uid = C.create_string_buffer(128)
             l = _lib.lib()
@@ -533,23 +534,26 @@ class PI0Pytorch(nn.Module):
             self._apply_exchange(ent["handle"])
 
     def _apply_exchange(self, handle):
-        if self._dp_group is None or not self._dp_overlap or self._dp_comm is None:
+        if self._dp_group is None or not self._dp_engine or self._dp_comm is None:
             return
         _lib.check(_lib.lib().pi05_set_grad_exchange(handle, self._dp_comm, self._dp_world,
-                                                     1 if self._dp_average == "in_place" else 0), "pi05_set_grad_exchange")
+                                                     1 if self._dp_average == "in_place" else 0,
+                                                     1 if self._dp_overlap else 0), "pi05_set_grad_exchange")
 
     def exchange_description(self) -> str:
         if self._dp_group is None:
             return "none (single rank)"
-        if not self._dp_overlap:
+        if not self._dp_engine:
             return "two torch.distributed all-reduces (bf16 arena, fp32 arena) after backward, then 1/world"
         calls, nbytes = C.c_int64(), C.c_int64()
         h = self._train_engine_handle()
         if h is not None:
             _lib.lib().pi05_grad_exchange_stats(h, C.byref(calls), C.byref(nbytes))
-        return (f"engine-issued ncclAllReduce(sum) per gradient group, overlapped with backward on a high-priority stream "
-                f"(own communicator, maxCTAs {self._dp_max_ctas}; last backward: {calls.value} collectives, "
-                f"{nbytes.value / 1e9:.2f} GB); average {self._dp_average}")
+        how = ("per gradient group, overlapped with backward on a high-priority stream" if self._dp_overlap
+               else "of the two gradient arenas at the end of pi05_backward")
+        return (f"engine-issued ncclAllReduce(sum) {how} (own communicator, maxCTAs "
+                f"{self._dp_max_ctas or 'default'}; last backward: {calls.value} collectives, {nbytes.value / 1e9:.2f} GB); "
+                f"average {self._dp_average}")
 
     # ------------------------------------------------------------------ engine lifecycle
     def _device(self):
@@ -875,7 +879,7 @@ class PI0Pytorch(nn.Module):
     def _engine_backward(self, dloss):
         handle = self._train_engine_handle()
         _lib.check(_lib.lib().pi05_backward(handle, C.c_void_p(dloss.data_ptr()), self._stream()), "pi05_backward")
-        if self._dp_group is not None and not self._dp_overlap:
+        if self._dp_group is not None and not self._dp_engine:
             self._allreduce_flat_grads()
         grads = []
         for name, p in self._grad_params:

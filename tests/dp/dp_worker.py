@@ -56,8 +56,8 @@ def main():
 
     # ---- A: engine exchange vs stock DDP
     mx = fresh()
-    mx.enable_flat_allreduce()
-    assert mx._dp_overlap, "NCCL group on a CUDA module must take the overlapped engine path"
+    mx.enable_flat_allreduce(overlap=True)
+    assert mx._dp_engine and mx._dp_overlap
     run(mx, b, mine)
     gx = grads_of(mx)
     calls, nbytes = C.c_int64(), C.c_int64()
@@ -97,7 +97,8 @@ def main():
 
     def one_step(average):
         m = fresh()
-        m.enable_flat_allreduce(average=average)
+        m.enable_flat_allreduce(average=average)  # default mode: one engine-issued exchange at the end of backward
+        assert m._dp_engine and not m._dp_overlap
         opt = FusedClipAdamW(m, lr=1e-3, max_norm=1.0)
         run(m, b, mine)
         norm = float(opt.step())

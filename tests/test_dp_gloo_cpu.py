@@ -50,7 +50,7 @@ def _worker(rank, world, port, q):
             model._flat_grad[dt] = torch.full_like(flat, float(rank + 1))
         model._allreduce_flat_grads()
         ok = ok and bool(torch.all(model._flat_grad[torch.float32] == 3.0)) and model.grad_scale == 0.5
-        ok = ok and not model._dp_overlap  # gloo / CPU: the torch.distributed path, never the NCCL engine path
+        ok = ok and not model._dp_engine  # gloo / CPU: the torch.distributed path, never the NCCL engine path
         q.put((rank, ok, same, alias))
     finally:
         dist.destroy_process_group()
