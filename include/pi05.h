@@ -43,6 +43,7 @@ typedef struct pi05_config {
   int32_t max_batch;      /* largest per-GPU batch the workspace is sized for */
   int32_t train;          /* 1: size the activation stash for backward */
   int32_t value_head;     /* 1: AdvantageEstimator value head (pi0_pytorch.py:473-481) */
+  int32_t rtc;            /* 1 (inference engines): per-layer suffix stash + suffix backward scratch for pi05_denoise_rtc */
 } pi05_config;
 
 /* dtype codes used in tensor descriptors */
@@ -102,6 +103,22 @@ int pi05_set_taps(pi05_engine* e, int enabled);
 int pi05_prefill(pi05_engine* e, const pi05_batch* b, void* stream);
 /* `num_steps` Euler steps from `noise` [batch,H,A] fp32 -> actions_out (pi0_pytorch.py:401-419,421-461) */
 int pi05_denoise(pi05_engine* e, const float* noise, int num_steps, float* actions_out, void* stream);
+
+/* Real-time-chunking guided decoding.  The reference has it in its JAX model only
+ * (src/openpi/models/pi0_rtc.py:234-360); this is that sampler on the PyTorch-path network: per Euler step the velocity of
+ * pi05_denoise's step AND the vector-Jacobian product of the denoiser x - t v(x) with the prefix-weighted error to the
+ * previous chunk (pi0_rtc.py:331-339), i.e. an input-gradient backward through the action expert, then
+ * v <- nan_to_num(v - guidance * J^T err), x <- x + dt v (:348-350).  Engine created with cfg.rtc = 1; pi05_prefill first.
+ *   prev_chunk   device fp32 [batch, action_horizon, action_dim], already NaN-cleaned and padded / cut to action_dim (:317-324)
+ *   time_weights device fp32 [action_horizon]  = get_prefix_weights(delay, execute_horizon, horizon, schedule) (:47-61,337)
+ *   dim_mask     device fp32 [action_dim]      = 1 for the first min(14, provided, action_dim) dims (:326-327)
+ *   guidance     HOST   fp32 [num_steps]       = min(c * inv_r2, max_guidance_weight) of every step (:341-347)
+ *   mask_rows / provided: with mask_prefix_delay the first `mask_rows` horizon rows of the first `provided` dims of the
+ *     denoiser input are overwritten by prev_chunk (:328-333); 0 / 0 otherwise.
+ * Exactly num_steps steps (lax.scan, :354-358), time an fp32 running sum from 1.0 by -1/num_steps. */
+int pi05_denoise_rtc(pi05_engine* e, const float* noise, int32_t num_steps, const float* prev_chunk,
+                     const float* time_weights, const float* dim_mask, const float* guidance, int32_t mask_rows,
+                     int32_t provided, float* actions_out, void* stream);
 
 /* ---- AdvantageEstimator (pi0_pytorch.py:464-644); engine created with cfg.value_head = 1 ------------------ */
 /* Replaces AdvantageEstimator.forward (pi0_pytorch.py:499-592).  progress: [batch] fp32 (clamped to [-1,1] inside,

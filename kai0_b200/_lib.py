@@ -38,6 +38,7 @@ class Config(C.Structure):
         ("max_batch", C.c_int32),
         ("train", C.c_int32),
         ("value_head", C.c_int32),
+        ("rtc", C.c_int32),
     ]
 
 
@@ -121,6 +122,7 @@ EXPORTS = (
     "pi05_set_taps",
     "pi05_prefill",
     "pi05_denoise",
+    "pi05_denoise_rtc",
     "pi05_forward_advantage",
     "pi05_forward_value",
     "pi05_get_tap",
@@ -190,6 +192,9 @@ def lib() -> C.CDLL:
             l.pi05_prefill.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p]
             l.pi05_denoise.restype = C.c_int
             l.pi05_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            l.pi05_denoise_rtc.restype = C.c_int
+            l.pi05_denoise_rtc.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
             l.pi05_forward_value.restype = C.c_int
             l.pi05_forward_value.argtypes = [C.c_void_p, C.POINTER(Batch)] + [C.c_void_p] * 4
             l.pi05_forward_advantage.restype = C.c_int

@@ -252,6 +252,18 @@ int pi05_preprocess_image(const float* image, int32_t height, int32_t width, int
   return 0;
 }
 
+int pi05_denoise_rtc(pi05_engine* pe, const float* noise, int32_t num_steps, const float* prev_chunk,
+                     const float* time_weights, const float* dim_mask, const float* guidance, int32_t mask_rows,
+                     int32_t provided, float* actions_out, void* stream) {
+  Engine* e = E(pe);
+  if (!e || !noise || !actions_out) {
+    pi05::set_error("pi05_denoise_rtc: null argument");
+    return 1;
+  }
+  return pi05::engine_denoise_rtc(*e, noise, num_steps, prev_chunk, time_weights, dim_mask, guidance, mask_rows, provided,
+                                  actions_out, static_cast<cudaStream_t>(stream));
+}
+
 int32_t pi05_patch_row_kp(int32_t patch) { return pi05::patch_row_kp(patch); }
 
 int pi05_preprocess_patches(const void* image, int32_t image_dtype, int32_t height, int32_t width, int32_t channels_last,

@@ -94,6 +94,7 @@ int engine_plan(Engine& e, bool dry) {
   const int vdepth = c.vit_depth;
   const int64_t vmlp = c.vit_mlp_dim, mlp1 = c.paligemma.mlp_dim, mlp2 = c.expert.mlp_dim;
   const bool tr = e.train;
+  const bool rtc = !tr && c.rtc != 0;  // inference engine that also runs pi05_denoise_rtc: suffix stash per layer
 
   e.rope_cos = ar.get<bf16>((S + 1) * (hd / 2));
   e.rope_sin = ar.get<bf16>((S + 1) * (hd / 2));
@@ -145,7 +146,23 @@ int engine_plan(Engine& e, bool dry) {
   GemmaLayerA sh1{}, sh2{};
   for (int l = 0; l < depth; ++l) {
     GemmaLayerA &p1 = e.a1[l], &p2 = e.a2[l];
-    if (tr || l == 0) {
+    if (rtc && l > 0) {  // own suffix buffers per layer (M2 rows: ~4 MB each), prefix buffers shared
+      p1 = sh1;
+      p2.n1 = ar.get<bf16>(M2 * E);
+      p2.qkv = ar.get<bf16>(M2 * QW);
+      p2.Q = ar.get<bf16>(M2 * H * hd);
+      p2.P = ar.get<bf16>(B * A * H * e.Spad);
+      p2.O = ar.get<bf16>(M2 * H * hd);
+      p2.o_lin = ar.get<bf16>(M2 * E);
+      p2.n2 = ar.get<bf16>(M2 * E);
+      p2.GU = ar.get<bf16>(M2 * 2 * mlp2);
+      p2.Hh = ar.get<bf16>(M2 * mlp2);
+      p2.d_lin = ar.get<bf16>(M2 * E);
+      p2.gate1 = ar.get<bf16>(B * E);
+      p2.gate2 = ar.get<bf16>(B * E);
+      p2.rstd1 = ar.get<float>(M2);
+      p2.rstd2 = ar.get<float>(M2);
+    } else if (tr || l == 0) {
       p1.n1 = ar.get<bf16>(M1 * D);
       p1.qkv = ar.get<bf16>(M1 * QW);
       p1.Q = ar.get<bf16>(M1 * H * hd);
@@ -269,6 +286,25 @@ int engine_plan(Engine& e, bool dry) {
     e.g_acc = ar.get<float>(e.g_acc_elems);
     e.g_embed_scratch = ar.get<float>(B * e.L * D);
     e.g_first = ar.get<int>(B * e.L);
+  }
+  if (rtc) {  // the suffix half of the backward scratch (engine_rtc.cu)
+    auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
+    e.g_x2 = ar.get<bf16>(M2 * E);
+    e.g_x2b = ar.get<bf16>(M2 * E);
+    e.g_P = ar.get<bf16>(B * A * H * e.Spad);
+    e.g2_do = ar.get<bf16>(M2 * E);
+    e.g2_big = ar.get<bf16>(M2 * 2 * mlp2);
+    e.g2_t1 = ar.get<bf16>(M2 * mx(QW, E));
+    e.g2_t2 = ar.get<bf16>(M2 * mx(H * hd, E));
+    e.g2_t3 = ar.get<bf16>(M2 * H * hd);
+    e.g_dK = ar.get<float>(B * S * hd);
+    e.g_dV = ar.get<float>(B * S * hd);
+    e.g_dmods = ar.get<float>(B * 3 * E);
+    e.g_f32a = ar.get<float>(M2 * E);
+    e.g_f32b = ar.get<float>(M2 * E);
+    e.g_f32c = ar.get<float>(M2 * E);
+    e.rtc_tap_v = ar.get<float>(M2 * c.action_dim);
+    e.rtc_tap_j = ar.get<float>(M2 * c.action_dim);
   }
   ar.alloc(256);
   if (!dry && ar.overflow) {

@@ -97,6 +97,7 @@ struct Engine {
   int *pos = nullptr, *nvalid = nullptr;
   // vision
   bf16* vit_x0 = nullptr;
+  float *rtc_tap_v = nullptr, *rtc_tap_j = nullptr;  // copies of step 0's velocity / VJP for the parity taps (cfg.rtc)
   bf16* patch_wb = nullptr;     // patch-row path: Conv2d weight split [W, 3*Kp] = [hi | hi | lo]
   float* g_patch_dw = nullptr;  // its weight-gradient GEMM output [W, 2*Kp] fp32 before the fold
   int Kp = 0;
@@ -160,5 +161,10 @@ int engine_backward(Engine& e, const float* dloss, cudaStream_t st);
 // engine_decode.cu
 int engine_prefill(Engine& e, const pi05_batch* b, cudaStream_t st);
 int engine_denoise(Engine& e, const float* noise, int num_steps, float* actions_out, cudaStream_t st);
+// engine_rtc.cu
+int engine_denoise_rtc(Engine& e, const float* noise, int num_steps, const float* prev, const float* time_weights,
+                       const float* dim_mask, const float* guidance, int mask_rows, int provided, float* actions_out,
+                       cudaStream_t st);
+void add_tap(Engine& e, const char* name, const void* p, int64_t n, int dtype);
 
 }  // namespace pi05

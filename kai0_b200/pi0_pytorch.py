@@ -587,7 +587,7 @@ class PI0Pytorch(nn.Module):
         except Exception:  # noqa: BLE001
             pass
 
-    def _ensure_engine(self, batch: int, train: bool, num_images: int | None = None):
+    def _ensure_engine(self, batch: int, train: bool, num_images: int | None = None, rtc: bool = False):
         """Makes the engine for (device, train, num_images) the active one, creating it on first use.  Engines are kept
         (an AdvantageEstimator alternating 3- and 6-image calls, or a validation forward between training steps, does not
         re-plan 100+ GB of workspace each time); when a new workspace does not fit in free device memory the least
@@ -598,7 +598,7 @@ class PI0Pytorch(nn.Module):
                 "PI0Pytorch (B200 engine) has no CPU path: move the module to an sm_100 CUDA device first"
             )
         ni = int(num_images or self.ecfg.num_images)
-        key = (dev.index, bool(train), ni)
+        key = (dev.index, bool(train), ni, bool(rtc) and not train)
         ent = self._engines.get(key)
         if ent is not None and ent["max_batch"] < batch:
             self._evict_engine(key)  # grown batch: re-plan this one
@@ -614,7 +614,7 @@ class PI0Pytorch(nn.Module):
         self._engine_key = (dev.index, bool(train), ent["max_batch"], ni)
 
     def _create_engine(self, dev, key, need_b):
-        _, train, ni = key
+        _, train, ni, rtc = key
         l = _lib.lib()
         c = _lib.Config()
         for dst, src in ((c.paligemma, self.pg), (c.expert, self.ex)):
@@ -626,6 +626,7 @@ class PI0Pytorch(nn.Module):
         c.action_dim, c.action_horizon, c.max_token_len = e.action_dim, e.action_horizon, e.max_token_len
         c.num_images, c.max_batch, c.train = ni, need_b, 1 if train else 0
         c.value_head = 1 if self._value_head else 0
+        c.rtc = 1 if rtc else 0
         nbytes = l.pi05_workspace_bytes(C.byref(c))
         if nbytes == 0:
             raise RuntimeError(f"pi05_workspace_bytes: {_lib.last_error()}")
@@ -720,7 +721,7 @@ class PI0Pytorch(nn.Module):
             p[i, 5:6] = 0.5 + torch.rand(1, device=dev) * 1.0
         return p
 
-    def _preprocess_observation(self, observation, *, train=True, rows=False, engine_train=None):
+    def _preprocess_observation(self, observation, *, train=True, rows=False, engine_train=None, engine_rtc=False):
         """preprocessing_pytorch.py:20-173 on the device, one launch group per image key: layout sniffing, resize-with-pad
         to image_size, train-time augmentation, default masks.  Images may be fp32 in [-1, 1] (what Observation.from_dict
         hands over) or uint8 -- then from_dict's `x / 255 * 2 - 1` (models/model.py:129-133) is taken inside the kernel.
@@ -749,7 +750,7 @@ class PI0Pytorch(nn.Module):
             # columns [3 p^2, Kp) of each block, which must read as 0 in the GEMM.
             ent = {}
             if engine_train is not None:  # the engine that will consume the rows becomes the active one first
-                self._ensure_engine(B, train=bool(engine_train), num_images=len(keys))
+                self._ensure_engine(B, train=bool(engine_train), num_images=len(keys), rtc=engine_rtc)
                 ent = self._engine_ent
             out = ent.get("rows")
             if out is None or out.shape != (len(keys) * B * T, 3 * kp):
@@ -928,7 +929,7 @@ class PI0Pytorch(nn.Module):
         if not need_grad:
             return self._engine_forward(pack, actions, noise, time)
         self._train_generation += 1  # invalidates the stash any earlier, not yet back-propagated forward relied on
-        self._train_key = (dev.index, True, self._engine_key[3])
+        self._train_key = (dev.index, True, self._engine_key[3], False)
         named = dict(self.named_parameters())
         # autograd inputs = the parameters that can receive a gradient.  The unused lm_head and the parameters the loss
         # cannot reach (self._dead_grad_names) are NOT inputs, so they are unreachable from the loss exactly as in the
@@ -942,18 +943,30 @@ class PI0Pytorch(nn.Module):
         return _EngineFunction.apply(self, pack, actions, noise, time, *[p for _, p in self._grad_params])
 
     @torch.no_grad()
-    def sample_actions(self, device, observation, noise=None, num_steps=10) -> Tensor:
-        """Inference (pi0_pytorch.py:375-419): prefix pass + KV cache, then `num_steps` Euler steps."""
+    def sample_actions(self, device, observation, noise=None, num_steps=10, *, prev_action_chunk=None,
+                       inference_delay=None, execute_horizon=None, mask_prefix_delay=False,
+                       prefix_attention_schedule="exp", max_guidance_weight=0.5, enable_rtc=True) -> Tensor:
+        """Inference (pi0_pytorch.py:375-419): prefix pass + KV cache, then `num_steps` Euler steps.
+
+        The keyword arguments after `num_steps` are the real-time-chunking interface of the reference's JAX model
+        (src/openpi/models/pi0_rtc.py:234-251; its PyTorch class has none): with `prev_action_chunk` given and `enable_rtc`,
+        every step is guided towards the previous chunk through the vector-Jacobian product of the denoiser
+        (pi05_denoise_rtc); without it this is exactly the reference PyTorch sampler."""
+        use_rtc = bool(enable_rtc) and prev_action_chunk is not None
         images, img_masks, lang_tokens, lang_masks, state = self._preprocess_observation(
-            observation, train=False, rows=self.use_patch_rows, engine_train=False)
+            observation, train=False, rows=self.use_patch_rows, engine_train=False, engine_rtc=use_rtc)
         bsize = state.shape[0]
         dev = self._device()
         if noise is None:
             noise = self.sample_noise((bsize, self.ecfg.action_horizon, self.ecfg.action_dim), dev)
         noise = noise.to(dev, torch.float32).contiguous()
-        self._ensure_engine(bsize, train=False, num_images=len(images))
+        self._ensure_engine(bsize, train=False, num_images=len(images), rtc=use_rtc)
         b, keep = self._make_batch(images, img_masks, lang_tokens, lang_masks)
         taps = bool(getattr(self, "_taps", False))
+        if use_rtc:
+            return self._sample_actions_rtc(b, keep, noise, int(num_steps), prev_action_chunk, inference_delay,
+                                            execute_horizon, bool(mask_prefix_delay), prefix_attention_schedule,
+                                            float(max_guidance_weight), taps)
         if self.use_cuda_graph and not taps:
             return self._sample_actions_graphed(b, keep, noise, int(num_steps))
         l = _lib.lib()
@@ -965,6 +978,79 @@ class PI0Pytorch(nn.Module):
             "pi05_denoise",
         )
         del keep
+        return out
+
+    @staticmethod
+    def rtc_prefix_weights(start: int, end: int, total: int, schedule: str) -> Tensor:
+        """pi0_rtc.py:47-61 (`get_prefix_weights`): 1 up to `start`, decaying to 0 at `end`, 0 afterwards."""
+        start = min(start, end)
+        idx = torch.arange(total, dtype=torch.float32)
+        if schedule == "ones":
+            w = torch.ones(total)
+        elif schedule == "zeros":
+            w = (idx < start).to(torch.float32)
+        elif schedule in ("linear", "exp"):
+            w = torch.clamp((start - 1 - idx) / (end - start + 1) + 1, 0, 1)
+            if schedule == "exp":
+                w = w * torch.expm1(w) / (math.e - 1)
+        else:
+            raise ValueError(f"Invalid schedule: {schedule}")
+        return torch.where(idx >= end, torch.zeros(()), w)
+
+    @staticmethod
+    def rtc_guidance_weights(num_steps: int, max_guidance_weight: float) -> list:
+        """pi0_rtc.py:341-347 for every step: time is the fp32 running sum 1, 1 + dt, ... (dt = -1 / num_steps, :256)."""
+        dt = torch.tensor(-1.0 / num_steps, dtype=torch.float32)
+        time = torch.tensor(1.0, dtype=torch.float32)
+        mx = torch.tensor(max_guidance_weight, dtype=torch.float32)
+        out = []
+        for _ in range(num_steps):
+            tau = torch.clamp(1.0 - time, 1e-3, 1.0)
+            sq = (1 - tau) ** 2
+            inv_r2 = (sq + tau**2) / sq
+            c = torch.nan_to_num((1 - tau) / tau, posinf=max_guidance_weight)
+            gw = c * inv_r2
+            out.append(float(torch.where(torch.isnan(gw), gw, torch.minimum(gw, mx))))
+            time = time + dt
+        return out
+
+    def _sample_actions_rtc(self, b, keep, noise, num_steps, prev_action_chunk, inference_delay, execute_horizon,
+                            mask_prefix_delay, schedule, max_guidance_weight, taps):
+        H, A = self.ecfg.action_horizon, self.ecfg.action_dim
+        dev = self._device()
+        exec_h = int(min(max(execute_horizon if execute_horizon is not None else H, 1), H))  # pi0_rtc.py:305-306
+        d = int(min(max(0 if inference_delay is None else inference_delay, 0), H))             # :307-308
+        prev = torch.as_tensor(prev_action_chunk, dtype=torch.float32, device=dev)
+        if prev.dim() == 2:
+            prev = prev[None]
+        exec_h = min(exec_h, prev.shape[1])                                                    # :313
+        provided_before_pad = prev.shape[-1]
+        prev = torch.nan_to_num(prev, nan=0.0, posinf=0.0, neginf=0.0)                         # :317
+        if prev.shape[-1] > A:                                                                 # :319-324
+            prev = prev[..., :A]
+        elif prev.shape[-1] < A:
+            prev = torch.cat([prev, torch.zeros(*prev.shape[:-1], A - prev.shape[-1], device=dev)], dim=-1)
+        if prev.shape[0] != noise.shape[0] or prev.shape[1] != H:
+            raise ValueError(f"prev_action_chunk must be [batch, {H}, <= {A}], got {tuple(prev.shape)}")
+        prev = prev.contiguous()
+        provided = min(14, provided_before_pad, A)                                             # :326
+        dim_mask = (torch.arange(A) < provided).to(torch.float32).to(dev)
+        weights = self.rtc_prefix_weights(d, exec_h, H, schedule).to(dev).contiguous()         # :337
+        gws = self.rtc_guidance_weights(num_steps, max_guidance_weight)
+        garr = (C.c_float * num_steps)(*gws)
+        l = _lib.lib()
+        l.pi05_set_taps(self._engine, 1 if taps else 0)
+        _lib.check(l.pi05_prefill(self._engine, C.byref(b), self._stream()), "pi05_prefill")
+        out = torch.empty_like(noise)
+        _lib.check(
+            l.pi05_denoise_rtc(self._engine, C.c_void_p(noise.data_ptr()), num_steps, C.c_void_p(prev.data_ptr()),
+                               C.c_void_p(weights.data_ptr()), C.c_void_p(dim_mask.data_ptr()), garr,
+                               d if (mask_prefix_delay and provided > 0) else 0,
+                               provided if (mask_prefix_delay and provided > 0) else 0,
+                               C.c_void_p(out.data_ptr()), self._stream()),
+            "pi05_denoise_rtc",
+        )
+        self._engine_ent["keep_rtc"] = (keep, prev, weights, dim_mask)  # alive until the stream has consumed them
         return out
 
     def _sample_actions_graphed(self, b, keep, noise, num_steps):

@@ -1,6 +1,7 @@
-"""CPU checks of oracle/rtc_oracle.py (prepared; the engine does not implement RTC yet).
-PARITY UNPINNED: the reference's RTC exists only in JAX (models/pi0_rtc.py) and cannot run here — these tests pin the
-restatement to known answers of the schedules and to properties of the guided sampler."""
+"""CPU checks of oracle/rtc_oracle.py (the engine side is tests/test_rtc_gpu.py).
+PARITY UNPINNED AGAINST JAX: the reference's RTC exists only in its JAX model (models/pi0_rtc.py) and cannot run here —
+these tests pin the restatement to known answers of the schedules, to properties of the guided sampler, and pin the
+vector-Jacobian product it relies on with central finite differences of the PyTorch-path denoise step in float32."""
 import math
 
 import pytest
@@ -64,3 +65,31 @@ def test_guidance_pulls_the_executed_prefix_towards_the_previous_chunk():
     masked = R.sample_actions_rtc(p, oc, *args, prev_action_chunk=target14, inference_delay=2, execute_horizon=6,
                                   mask_prefix_delay=True)
     assert bool(torch.isfinite(masked).all())
+
+
+def test_vjp_of_the_denoiser_matches_central_finite_differences():
+    """pi0_rtc.py:331: `jax.vjp(denoiser, x)` with denoiser(x) = x - t * v(x).  For float32 weights, <J^T e, d> must equal
+    <e, (f(x + h d) - f(x - h d)) / 2h> for random directions d (central differences, h = 1e-2 on O(1) inputs)."""
+    oc = O.tiny_config()
+    p = {k: v.to(torch.float32) for k, v in O.init_params(oc, seed=5).items()}
+    b = O.synthetic_batch(oc, 2)
+    with torch.no_grad():
+        prefix_pad, cache = O.prefill(p, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, oc.action_horizon, oc.action_dim, generator=g)
+    e = torch.randn(x.shape, generator=g)
+    for t in (1.0, 0.6, 0.1):
+        tb = torch.full((2,), t)
+
+        def f(z):
+            return z - t * O.denoise_step(p, oc, prefix_pad, cache, z, tb)
+
+        xl = x.clone().requires_grad_(True)
+        (vjp,) = torch.autograd.grad(f(xl), xl, grad_outputs=e)
+        for _ in range(3):
+            d = torch.randn(x.shape, generator=g)
+            h = 1e-2
+            with torch.no_grad():
+                fd = (f(x + h * d) - f(x - h * d)) / (2 * h)
+            lhs, rhs = float((vjp * d).sum()), float((e * fd).sum())
+            assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0), (t, lhs, rhs)
