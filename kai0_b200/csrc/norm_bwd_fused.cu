@@ -6,6 +6,8 @@
 //   phase B: thread t owns columns t, t+256, ... and adds the slab's 8 rows from shared memory into its dw (db)
 //            accumulators, which live in registers for the whole kernel;
 // one atomicAdd per column per block at the end.  Arithmetic per element is identical to the two-kernel version.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "errors.h"
 #include "kernels.h"
@@ -150,6 +152,129 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 1) norm_bwd_slab_k(cons
   }
 }
 
+// Register-accumulating variant: no shared-memory phase at all.  A lane owns the SAME columns (lane * 8 + k * 256) of every
+// row its warp visits, so the weight (bias) gradient is accumulated in registers across rows while the row is still in
+// registers for dx; warps never synchronise inside the row loop (one warp's loads overlap another's arithmetic), the
+// residual gradient is loaded together with dy / x (one memory latency per row, not two), and the 8 warps of a block are
+// reduced through shared memory once at the end (one atomicAdd per column per block).  Same arithmetic per element.
+template <bool LN, int CH>
+__global__ void __launch_bounds__(256, 1) norm_bwd_reg_k(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                         const void* __restrict__ w_, const float* __restrict__ mean_i,
+                                                         const float* __restrict__ rstd_i, const bf16* __restrict__ dres,
+                                                         bf16* __restrict__ dx, float* __restrict__ dw32,
+                                                         float* __restrict__ db32, int rows, int width) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw);  // [8][width] (weight grads), then reused for the bias grads
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[CH][8], ab[LN ? CH : 1][8];
+#pragma unroll
+  for (int k = 0; k < CH; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      aw[k][i] = 0.f;
+      if (LN) ab[k][i] = 0.f;
+    }
+  const float inv_w = 1.0f / static_cast<float>(width);
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const int64_t off = static_cast<int64_t>(row) * width;
+    uint4 pd[CH], pv[CH], pr[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < width) {
+        pd[k] = *reinterpret_cast<const uint4*>(dy + off + c);
+        pv[k] = *reinterpret_cast<const uint4*>(x + off + c);
+        if (dres) pr[k] = *reinterpret_cast<const uint4*>(dres + off + c);
+      }
+    }
+    const float mean = LN ? mean_i[row] : 0.f;
+    const float rstd = rstd_i[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < width) {
+        float d[8], v[8], ww[8];
+        unpack8(pd[k], d);
+        unpack8(pv[k], v);
+        if (LN) load8(static_cast<const bf16*>(w_) + c, ww);
+        else load8f(static_cast<const float*>(w_) + c, ww);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = LN ? (v[i] - mean) * rstd : v[i] * rstd;
+          const float g = LN ? d[i] * ww[i] : d[i] * (1.0f + ww[i]);
+          if (LN) s1 += g;
+          s2 += g * xh;
+          aw[k][i] += d[i] * xh;
+          if (LN) ab[k][i] += d[i];
+        }
+      }
+    }
+    if (LN) s1 = warp_sum(s1) * inv_w;
+    s2 = warp_sum(s2) * inv_w;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < width) {
+        float d[8], v[8], ww[8], o[8];
+        unpack8(pd[k], d);
+        unpack8(pv[k], v);
+        if (LN) load8(static_cast<const bf16*>(w_) + c, ww);
+        else load8f(static_cast<const float*>(w_) + c, ww);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = LN ? (v[i] - mean) * rstd : v[i] * rstd;
+          const float g = LN ? d[i] * ww[i] : d[i] * (1.0f + ww[i]);
+          o[i] = LN ? bfr(rstd * (g - s1 - xh * s2)) : bfr(rstd * (g - xh * s2));
+        }
+        if (dres) {
+          float r[8];
+          unpack8(pr[k], r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        store8(dx + off + c, o);
+      }
+    }
+  }
+  // ---- block reduction of the per-warp accumulators, then one atomicAdd per column
+#pragma unroll
+  for (int pass = 0; pass < (LN ? 2 : 1); ++pass) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int c = lane * 8 + k * 256;
+      if (c < width) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[warp * width + c + i] = pass == 0 ? aw[k][i] : ab[LN ? k : 0][i];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < width; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += red[wv * width + c];
+      atomicAdd((pass == 0 ? dw32 : db32) + c, t);
+    }
+    __syncthreads();
+  }
+}
+
+template <bool LN, int CH>
+void launch_reg(const bf16* dy, const bf16* x, const void* w, const float* mean, const float* rstd, const bf16* dres,
+                bf16* dx, float* dw32, float* db32, int rows, int width, int sms, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(8) * width * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(norm_bwd_reg_k<LN, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * CH * 4);
+    attr_set = true;
+  }
+  const int per_sm = (LN ? CH <= 3 : CH <= 4) ? 2 : 1;  // register budget (ptxas: RMS 128 regs at CH 4, LN 126 at CH 3)
+  const int want = (rows + 7) / 8;
+  const int grid = want < per_sm * sms ? want : per_sm * sms;
+  launch_pdl(norm_bwd_reg_k<LN, CH>, dim3(grid), dim3(256), smem, st, dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width);
+}
+
 template <bool LN, int CH, int NW>
 void launch_slab(const bf16* dy, const bf16* x, const void* w, const float* mean, const float* rstd, const bf16* dres,
                  bf16* dx, float* dw32, float* db32, int rows, int width, int sms, cudaStream_t st) {
@@ -177,9 +302,11 @@ bool launch_fused(const bf16* dy, const bf16* x, const void* w, const float* mea
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  static const bool use_slab = getenv("PI05_NORM_BWD_SLAB") != nullptr;  // A/B: the round-1 shared-memory slab kernel
 #define PI05_NORM_CASE(C, W)                                                                               \
   case C:                                                                                                  \
-    launch_slab<LN, C, W>(dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width, sms, st);               \
+    if (use_slab) launch_slab<LN, C, W>(dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width, sms, st); \
+    else launch_reg<LN, C>(dy, x, w, mean, rstd, dres, dx, dw32, db32, rows, width, sms, st);             \
     break;
   switch (ch) {
     PI05_NORM_CASE(1, 8)

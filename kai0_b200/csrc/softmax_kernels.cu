@@ -32,34 +32,48 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
     const int tok = static_cast<int>(row % rows_per_batch) / q_per_token;
     qmasked = qpad[static_cast<int64_t>(b) * tokens + tok] == 0;
   }
+  // The kernel is instruction-bound, not bandwidth-bound, when every element pays for the mask logic (measured 2.4 TB/s):
+  // masks are resolved per 8-key chunk -- all valid (the common case: no per-element work), all masked, or mixed.
   float v[CH][8];
   float mx = -CUDART_INF_F;
+  constexpr uint64_t kAllValid = 0x0101010101010101ull;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const int j0 = (i * 32 + lane) * 8;
-    if (j0 < ld) {
-      if (j0 + 8 <= n_keys) {
-        load8(sr + j0, v[i]);
-      } else {  // last chunk: never read the (unwritten) pitch padding
+    if (j0 + 8 <= n_keys) {
+      load8(sr + j0, v[i]);
+      // pad flags of this chunk: one 8-byte load inside the (8-aligned) prefix; suffix keys are always valid
+      uint64_t flags = kAllValid;
+      if (padb != nullptr && j0 < n_prefix) {
+        if (j0 + 8 <= n_prefix && ((reinterpret_cast<uintptr_t>(padb) + j0) & 7) == 0) {
+          flags = *reinterpret_cast<const uint64_t*>(padb + j0);
+        } else {
+          flags = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[i][e] = (j0 + e < n_keys) ? __bfloat162float(sr[j0 + e]) : 0.f;
+          for (int e = 0; e < 8; ++e)
+            flags |= static_cast<uint64_t>((j0 + e >= n_prefix || padb[j0 + e] != 0) ? 1 : 0) << (8 * e);
+        }
       }
-      // the 8 pad flags of this chunk in one 8-byte load when the chunk lies inside the (8-aligned) prefix
-      uint64_t flags = ~0ull;
-      const bool vec_ok = padb != nullptr && j0 + 8 <= n_prefix && ((reinterpret_cast<uintptr_t>(padb) + j0) & 7) == 0;
-      if (vec_ok) flags = *reinterpret_cast<const uint64_t*>(padb + j0);
+      if (qmasked) flags = 0;
+      if (flags != kAllValid) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (((flags >> (8 * e)) & 0xFFull) == 0) v[i][e] += kMaskValue;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[i][e]);
+    } else if (j0 < n_keys) {  // ragged last chunk of the row: never read the (unwritten) pitch padding
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = j0 + e;
-        if (j >= n_keys) {
-          v[i][e] = -CUDART_INF_F;  // pitch padding: excluded from max / sum
+        if (j < n_keys) {
+          float x = __bfloat162float(sr[j]);
+          const bool ok = !qmasked && (j >= n_prefix || padb == nullptr || padb[j] != 0);
+          if (!ok) x += kMaskValue;
+          v[i][e] = x;
+          mx = fmaxf(mx, x);
         } else {
-          bool ok;
-          if (vec_ok) ok = ((flags >> (8 * e)) & 0xFFull) != 0;
-          else ok = (j >= n_prefix || padb == nullptr || padb[j] != 0);
-          const bool valid = !qmasked && ok;
-          if (!valid) v[i][e] += kMaskValue;
-          mx = fmaxf(mx, v[i][e]);
+          v[i][e] = -CUDART_INF_F;  // excluded from max / sum
         }
       }
     } else {
@@ -69,12 +83,18 @@ __global__ void __launch_bounds__(256) softmax_fwd_vec_k(bf16* __restrict__ s, i
   }
   mx = warp_max(mx);
   float sum = 0.f;
+  // exp(x - mx) = 2^((x - mx) * log2e) with one ex2.approx per element (rel. error ~1e-6, far below the bf16 rounding of
+  // P); exp(-inf) = 0.  The subtraction comes FIRST: a fully masked row (padded query) has mx = -2.38e38, and
+  // mx * log2e would overflow to -inf and turn the row into NaNs that the next layer's keys spread to valid rows.
+  constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
   for (int i = 0; i < CH; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      v[i][e] = __expf(v[i][e] - mx);  // ex2.approx form (rel. error ~1e-6, far below the bf16 rounding of P); exp(-inf) = 0
-      sum += v[i][e];
+      float ex;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((v[i][e] - mx) * kLog2e));
+      v[i][e] = ex;
+      sum += ex;
     }
   sum = warp_sum(sum);
   // one IEEE reciprocal per row instead of 1024 divisions (<= 1 ulp from x/sum in fp32, i.e. far below the bf16
