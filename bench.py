@@ -42,13 +42,13 @@ UNIT = "samples/s"
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the four dominant GEMM classes at the bench's
-# shapes, from the committed `ncu --set full` captures (profiles/r01_ncu_gemm_{geglu,dgrad,wgrad,down}.md);
+# shapes, from the committed `ncu --set full` captures (profiles/r02_ncu_gemm_{geglu,dgrad,wgrad,down}.md, round-2 code);
 # key = (M, N, K, epilogue, majors) as printed by pi05_gemm_profile_report
 NCU_TRAFFIC_BYTES = {
-    (30976, 32768, 2048, 5, 0): 5332.3e6,   # GeGLU forward (fused gate|up weight)
-    (30976, 2048, 32768, 0, 1): 5550.0e6,   # dgrad of gate|up
-    (32768, 2048, 30976, 0, 3): 5455.0e6,   # wgrad of gate|up
-    (30976, 2048, 16384, 4, 0): 2944.2e6,   # down projection + residual
+    (30976, 32768, 2048, 5, 0): 5301.8e6,   # GeGLU forward (fused gate|up weight)          profiles/r02_ncu_gemm_geglu.md
+    (30976, 2048, 32768, 0, 1): 6036.1e6,   # dgrad of gate|up                              profiles/r02_ncu_gemm_dgrad.md
+    (32768, 2048, 30976, 0, 3): 5536.2e6,   # wgrad of gate|up                              profiles/r02_ncu_gemm_wgrad.md
+    (30976, 2048, 16384, 4, 0): 3068.0e6,   # down projection + residual                    profiles/r02_ncu_gemm_down.md
 }
 
 
@@ -539,7 +539,7 @@ def main():
             roofline = {
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": NCU_TRAFFIC_BYTES.get((top["M"], top["N"], top["K"], top["epi"], top["majors"])),
-                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_gemm_*.md)",
+                "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r02_ncu_gemm_*.md)",
                 "algorithmic_bytes": 2.0 * (top["M"] * top["K"] + top["N"] * top["K"] + top["M"] * top["N"]) * top["batch"],
                 "kernel": f"gemm_kernel<256,{top['epi']}> M={top['M']} N={top['N']} K={top['K']} "
                           f"majors={top['majors']} ({top['launches']} launches in the timed region)",

@@ -241,7 +241,7 @@ int engine_plan(Engine& e, bool dry) {
   }
   // small-M split-K (decode) needs a few MB; the training wave-quantisation path up to s * M * N fp32 partials of a
   // weight-gradient GEMM (largest user: 4 x 2560 x 2048 x 4 B = 84 MB)
-  e.splitk_ws_bytes = static_cast<size_t>(tr ? 128 : 16) << 20;
+  e.splitk_ws_bytes = static_cast<size_t>(tr ? 128 : 64) << 20;
   e.splitk_ws = ar.get<float>(e.splitk_ws_bytes / sizeof(float));
   {
     const int64_t ns = Engine::kMaxDecodeSteps;

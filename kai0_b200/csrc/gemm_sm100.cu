@@ -665,6 +665,37 @@ __global__ void __launch_bounds__(1024) splitk_finish_rope_k(const float* __rest
   *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
+// RES finish of the few-tile long-K path (no bias / gate / second output): D = bf(res + bf(sum of partials)), 4 outputs per
+// thread, 16-byte partial loads, 8-byte residual loads and stores, fixed summation order.
+__global__ void __launch_bounds__(256) splitk_sum_res4_k(const float* __restrict__ ws, int splits, long long total4, int n4,
+                                                         __nv_bfloat16* __restrict__ D, long long ldd,
+                                                         const __nv_bfloat16* __restrict__ res, long long ldres) {
+  pdl_enter();
+  const long long total = total4 * 4;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(ws)[q];
+    for (int z = 1; z < splits; ++z) {
+      const float4 v = reinterpret_cast<const float4*>(ws + z * total)[q];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    const long long m = q / n4;
+    const int n = static_cast<int>(q % n4) * 4;
+    const uint2 r = *reinterpret_cast<const uint2*>(res + m * ldres + n);
+    const float r0 = __uint_as_float(r.x << 16), r1 = __uint_as_float(r.x & 0xFFFF0000u);
+    const float r2 = __uint_as_float(r.y << 16), r3 = __uint_as_float(r.y & 0xFFFF0000u);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(bf16_round(acc.x) + r0, bf16_round(acc.y) + r1);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(bf16_round(acc.z) + r2, bf16_round(acc.w) + r3);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(D + m * ldd + n) = o;
+  }
+}
+
 // STORE-only finish of the wave-quantisation path: 4 outputs per thread, 16-byte partial loads, fixed summation order.
 __global__ void __launch_bounds__(256) splitk_sum_store4_k(const float* __restrict__ ws, int splits, long long total4,
                                                            int n4, __nv_bfloat16* __restrict__ D, long long ldd) {
@@ -788,6 +819,71 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
   if (a.epilogue == EPI_GEGLU && a.b_major != 0) {
     if (err) snprintf(err, err_len, "gemm: GEGLU epilogue needs a K-major [2N,K] weight");
     return 1;
+  }
+  // ---- few-tile, long-K path (the prefix pass of the decode: M = 968 rows against a 16384-deep down-projection): with
+  // 128 x 128 tiles each CTA streams 8 MB of operands for 0.5 GFLOP and the GEMM is L2-bound; 256 x 256 pair tiles quarter
+  // the operand traffic per flop but leave only 32 of them for 74 clusters.  Split K so that pairs * s fills one wave, fp32
+  // partials + the general finish kernel (sum in a fixed order, then the STORE / RES epilogue).
+  if (a.M > BM && a.batch == 1 && a.splitk_ws != nullptr && a.a_major == 0 && a.b_major == 0 && a.block_n == 0 &&
+      (a.epilogue == EPI_STORE || a.epilogue == EPI_RES) && a.K % BK == 0 && a.K >= 4096 && a.norm_mod == nullptr &&
+      a.rope == nullptr) {
+    const long long pairs = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + 255) / 256);
+    const long long slots = num_sms() / 2;
+    const int kb = a.K / BK;
+    int sp = 1;
+    for (int c = 2; c <= 8; ++c)
+      if (pairs * c <= slots && kb % c == 0 && a.K / c >= 2048 &&
+          static_cast<size_t>(c) * a.M * a.N * sizeof(float) <= a.splitk_ws_bytes)
+        sp = c;
+    if (sp > 1 && pairs * 2 <= slots) {
+      const int Kc = a.K / sp;
+      GemmArgs part = a;
+      part.splitk_ws = nullptr;
+      part.K = Kc;
+      part.batch = sp;
+      part.batch_inner = 0;
+      part.a_batch_stride = Kc;
+      part.b_batch_stride = Kc;
+      part.epilogue = EPI_F32;
+      part.accumulate = 0;
+      part.D = a.splitk_ws;
+      part.ldd = a.N;
+      part.d_batch_stride = static_cast<int64_t>(a.M) * a.N;
+      part.block_n = 256;
+      part.bias = nullptr;
+      part.res = nullptr;
+      part.gate = nullptr;
+      part.D2 = nullptr;
+      int rc = gemm_bf16(part, stream, err, err_len);
+      if (rc != 0) return rc;
+      const long long total = static_cast<long long>(a.M) * a.N;
+      long long grid = (total + 255) / 256;
+      if (grid > num_sms() * 16) grid = num_sms() * 16;
+      const bool vec4 = a.N % 4 == 0 && a.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 7) == 0;
+      if (vec4 && a.epilogue == EPI_RES && a.bias == nullptr && a.gate == nullptr && a.D2 == nullptr && a.ldres % 4 == 0 &&
+          (reinterpret_cast<uintptr_t>(a.res) & 7) == 0) {
+        long long g4 = (total / 4 + 255) / 256;
+        if (g4 > num_sms() * 16) g4 = num_sms() * 16;
+        launch_pdl(splitk_sum_res4_k, dim3(static_cast<int>(g4)), dim3(256), 0, stream, a.splitk_ws, sp, total / 4, a.N / 4,
+                   static_cast<__nv_bfloat16*>(a.D), a.ldd, static_cast<const __nv_bfloat16*>(a.res), a.ldres);
+        count_launch();
+        return 0;
+      }
+      if (vec4 && a.epilogue == EPI_STORE) {
+        long long g4 = (total / 4 + 255) / 256;
+        if (g4 > num_sms() * 16) g4 = num_sms() * 16;
+        launch_pdl(splitk_sum_store4_k, dim3(static_cast<int>(g4)), dim3(256), 0, stream, a.splitk_ws, sp, total / 4, a.N / 4,
+                   static_cast<__nv_bfloat16*>(a.D), a.ldd);
+        count_launch();
+        return 0;
+      }
+      launch_pdl(splitk_finish_k, dim3(static_cast<int>(grid)), dim3(256), 0, stream, a.splitk_ws, sp, a.M, a.N, a.epilogue,
+                 static_cast<__nv_bfloat16*>(a.D), a.ldd, static_cast<__nv_bfloat16*>(a.D2), a.ldd2,
+                 static_cast<const __nv_bfloat16*>(a.bias), static_cast<const __nv_bfloat16*>(a.res), a.ldres,
+                 static_cast<const __nv_bfloat16*>(a.gate), a.gate_rows > 0 ? a.gate_rows : 1, a.ldgate);
+      count_launch();
+      return 0;
+    }
   }
   int bn = a.block_n;
   if (bn == 0) {

@@ -12,6 +12,146 @@ namespace pi05 {
 namespace {
 constexpr int WARPS = 8;
 
+// ---------------------------------------------------------------- register-resident forward (width <= 2048)
+// The row is loaded ONCE, with all of its 16-byte loads in flight, and stays in registers for the statistics and the
+// normalisation (the loop kernels below re-read it 2-3 times with one dependent load per iteration: 12-15 us for the
+// 968-row prefix norms of the decode path, where there is no occupancy to hide it).  Same summation order per lane
+// (chunk 0..CH-1, element 0..7) as the loop kernels: results are bit-identical.
+__device__ __forceinline__ void unpack8v(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(WARPS * 32) layernorm_fwd_vec_k(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const bf16* __restrict__ b, bf16* __restrict__ y,
+                                                                  float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                                  int rows, int width, float eps) {
+  pdl_enter();
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + static_cast<int64_t>(row) * width;
+  uint4 px[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < width) px[k] = *reinterpret_cast<const uint4*>(xr + c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (lane * 8 + k * 256 < width) {
+      float v[8];
+      unpack8v(px[k], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[i];
+    }
+  }
+  const float mean = warp_sum(s) / width;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (lane * 8 + k * 256 < width) {
+      float v[8];
+      unpack8v(px[k], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[i] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / width + eps);
+  bf16* yr = y + static_cast<int64_t>(row) * width;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < width) {
+      float v[8], ww[8], bb[8], o[8];
+      unpack8v(px[k], v);
+      load8(w + c, ww);
+      load8(b + c, bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
+      store8(yr + c, o);
+    }
+  }
+  if (lane == 0 && mean_o) {
+    mean_o[row] = mean;
+    rstd_o[row] = rstd;
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(WARPS * 32) rmsnorm_fwd_vec_k(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ mod, int rows_per_batch,
+                                                                bf16* __restrict__ y, float* __restrict__ rstd_o,
+                                                                bf16* __restrict__ gate_out, int rows, int width,
+                                                                float eps) {
+  pdl_enter();
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + static_cast<int64_t>(row) * width;
+  uint4 px[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < width) px[k] = *reinterpret_cast<const uint4*>(xr + c);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (lane * 8 + k * 256 < width) {
+      float v[8];
+      unpack8v(px[k], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+    }
+  }
+  const float var = warp_sum(ss) / width;
+  const float rstd = rsqrtf(var + eps);  // modeling_gemma.py:68-70
+  bf16* yr = y + static_cast<int64_t>(row) * width;
+  const int b = row / rows_per_batch;
+  const float* m = mod ? mod + static_cast<int64_t>(b) * 3 * width : nullptr;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane * 8 + k * 256;
+    if (c < width) {
+      float v[8], o[8];
+      unpack8v(px[k], v);
+      if (m == nullptr) {
+        float ww[8];
+        load8f(w + c, ww);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __fmul_rn(__fmul_rn(v[i], rstd), __fadd_rn(1.0f, ww[i]));  // :80
+      } else {
+        float sc[8], sh[8];
+        load8f(m + c, sc);
+        load8f(m + width + c, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = __fadd_rn(__fmul_rn(__fmul_rn(v[i], rstd), __fadd_rn(1.0f, sc[i])), sh[i]);  // :102
+      }
+      store8(yr + c, o);
+    }
+  }
+  if (lane == 0 && rstd_o) rstd_o[row] = rstd;
+  if (m != nullptr && gate_out != nullptr && (row % rows_per_batch) == 0) {
+    bf16* g = gate_out + static_cast<int64_t>(b) * width;
+    for (int c = lane * 8; c < width; c += 256) {
+      float gv[8];
+      load8f(m + 2 * width + c, gv);
+      store8(g + c, gv);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm fwd
 __global__ void __launch_bounds__(WARPS * 32) layernorm_fwd_k(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                               const bf16* __restrict__ b, bf16* __restrict__ y,
@@ -321,7 +461,22 @@ __global__ void __launch_bounds__(256) gated_residual_bwd_k(const bf16* __restri
 
 void layernorm_fwd(const bf16* x, const bf16* w, const bf16* b, bf16* y, float* mean, float* rstd, int rows, int width,
                    float eps, cudaStream_t st) {
-  launch_pdl(layernorm_fwd_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, x, w, b, y, mean, rstd, rows, width, eps); count_launch();
+  const dim3 grid(ceil_div(rows, WARPS)), block(WARPS * 32);
+  const int ch = (width + 255) / 256;
+  if (width % 8 == 0 && ch <= 8) {
+#define PI05_LN_CASE(C)                                                                                         \
+  case C:                                                                                                       \
+    launch_pdl(layernorm_fwd_vec_k<C>, grid, block, 0, st, x, w, b, y, mean, rstd, rows, width, eps);           \
+    break;
+    switch (ch) {
+      PI05_LN_CASE(1) PI05_LN_CASE(2) PI05_LN_CASE(3) PI05_LN_CASE(4) PI05_LN_CASE(5) PI05_LN_CASE(6) PI05_LN_CASE(7)
+      default: launch_pdl(layernorm_fwd_vec_k<8>, grid, block, 0, st, x, w, b, y, mean, rstd, rows, width, eps);
+    }
+#undef PI05_LN_CASE
+  } else {
+    launch_pdl(layernorm_fwd_k, grid, block, 0, st, x, w, b, y, mean, rstd, rows, width, eps);
+  }
+  count_launch();
 }
 
 void layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* mean, const float* rstd,
@@ -335,8 +490,23 @@ void layernorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* me
 
 void rmsnorm_fwd(const bf16* x, const float* w, const float* mod, int rows_per_batch, bf16* y, float* rstd,
                  bf16* gate_out, int rows, int width, float eps, cudaStream_t st) {
-  launch_pdl(rmsnorm_fwd_k, dim3(ceil_div(rows, WARPS)), dim3(WARPS * 32), 0, st, x, w, mod, rows_per_batch > 0 ? rows_per_batch : rows,
-                                                              y, rstd, gate_out, rows, width, eps); count_launch();
+  const dim3 grid(ceil_div(rows, WARPS)), block(WARPS * 32);
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
+  const int ch = (width + 255) / 256;
+  if (width % 8 == 0 && ch <= 8) {
+#define PI05_RMS_CASE(C)                                                                                              \
+  case C:                                                                                                             \
+    launch_pdl(rmsnorm_fwd_vec_k<C>, grid, block, 0, st, x, w, mod, rpb, y, rstd, gate_out, rows, width, eps);        \
+    break;
+    switch (ch) {
+      PI05_RMS_CASE(1) PI05_RMS_CASE(2) PI05_RMS_CASE(3) PI05_RMS_CASE(4) PI05_RMS_CASE(5) PI05_RMS_CASE(6) PI05_RMS_CASE(7)
+      default: launch_pdl(rmsnorm_fwd_vec_k<8>, grid, block, 0, st, x, w, mod, rpb, y, rstd, gate_out, rows, width, eps);
+    }
+#undef PI05_RMS_CASE
+  } else {
+    launch_pdl(rmsnorm_fwd_k, grid, block, 0, st, x, w, mod, rpb, y, rstd, gate_out, rows, width, eps);
+  }
+  count_launch();
 }
 
 void rmsnorm_bwd(const bf16* dy, const bf16* x, const float* w, const float* mod, int rows_per_batch,

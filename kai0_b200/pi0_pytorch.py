@@ -198,6 +198,14 @@ class _Node(nn.Module):
     def __len__(self):
         return sum(1 for k in self._modules if k.isdigit())
 
+    def _apply(self, fn, recurse=True):
+        """The parameters below this node are views of the top-level module's flat arenas, which only PI0Pytorch._apply
+        moves (it never recurses into the skeleton).  Reaching this method means `.to()` / `.cuda()` / `.half()` was called
+        on a SUB-module: that would re-point its parameters away from the arenas the engine reads."""
+        raise RuntimeError(
+            "kai0_b200: move / cast the whole PI0Pytorch module, not a sub-module: its parameters are views of the "
+            "top-level module's flat arenas (the reference's mixed dtype map is fixed: gemma_pytorch.py:63-83)")
+
 
 class _PaliGemmaWithExpert(_Node):
     def to_bfloat16_for_selected_params(self, precision: str = "bfloat16"):
@@ -436,6 +444,12 @@ class PI0Pytorch(nn.Module):
                 p.grad = None
             self._destroy_engine()
         return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        if assign:
+            raise ValueError("kai0_b200: load_state_dict(assign=True) would replace the parameters by tensors outside the "
+                             "flat arenas the engine reads; load with assign=False (values are copied into the arenas)")
+        return super().load_state_dict(state_dict, strict=strict)
 
     def state_dict(self, *args, **kwargs):
         """Checkpoints must not see the flat arenas: `safetensors.torch.save_model` (train_pytorch.py:167) refuses

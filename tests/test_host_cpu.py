@@ -200,3 +200,27 @@ def test_every_kernel_honours_the_pdl_contract():
                 missing.append(f"{fn}:{name[-1] if name else '?'}")
     assert not missing, missing
     assert not raw, raw
+
+
+def test_submodule_moves_and_assigning_loads_are_refused():
+    """`.to()` on a sub-module or `load_state_dict(assign=True)` would silently detach parameters from the
+    flat arenas the engine reads; both raise instead."""
+    import pytest
+    import torch
+
+    from kai0_b200.pi0_pytorch import GemmaVariant, PI0Pytorch, Pi05EngineConfig
+
+    cfg = Pi05EngineConfig(paligemma_variant=GemmaVariant(64, 2, 128, 8, 1, 16),
+                           action_expert_variant=GemmaVariant(32, 2, 64, 8, 1, 16), vit_width=32, vit_depth=1,
+                           vit_mlp_dim=64, vit_heads=2, image_size=28, vocab_size=64)
+    m = PI0Pytorch(cfg)
+    with pytest.raises(RuntimeError, match="whole PI0Pytorch"):
+        m.paligemma_with_expert.to(torch.float32)
+    with pytest.raises(ValueError, match="assign"):
+        m.load_state_dict(m.state_dict(), assign=True)
+    # the supported forms still work and keep the parameters views of the arenas
+    m.load_state_dict(m.state_dict())
+    m.to("cpu")
+    p = m.action_in_proj.weight
+    lo = m._flat[torch.float32].data_ptr()
+    assert lo <= p.data_ptr() < lo + m._flat[torch.float32].numel() * 4

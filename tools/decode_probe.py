@@ -40,6 +40,24 @@ def main():
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     print(f"host enqueue time {1e3 * (t1 - t0):.2f} ms")
+    # prefill vs denoise split (eager launches with programmatic dependent launch on, CUDA events on the stream)
+    import ctypes as C
+
+    from kai0_b200 import _lib as L
+
+    images, img_masks, toks, tmask, _ = model._preprocess_observation(obs, train=False, rows=True, engine_train=False)
+    b, keep = model._make_batch(images, img_masks, toks, tmask)
+    out = torch.empty_like(noise)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for _ in range(3):
+        ev[0].record()
+        L.check(L.lib().pi05_prefill(model._engine, C.byref(b), st), "prefill")
+        ev[1].record()
+        L.check(L.lib().pi05_denoise(model._engine, C.c_void_p(noise.data_ptr()), 10, C.c_void_p(out.data_ptr()), st), "denoise")
+        ev[2].record()
+        torch.cuda.synchronize()
+    print(f"eager (no graph): prefill {ev[0].elapsed_time(ev[1]):.2f} ms, 10-step denoise {ev[1].elapsed_time(ev[2]):.2f} ms")
     from torch.profiler import ProfilerActivity, profile
 
     from kai0_b200 import _lib
