@@ -87,11 +87,15 @@ def main():
     mz = fresh()
     run(mz, b, slice(0, 4))
     gz = grads_of(mz)
-    worst_b = 0.0
+    worst_b, worst_b_name = 0.0, None
     for n in gx:
-        if float(gz[n].float().norm()) < 1e-6:
-            continue
-        worst_b = max(worst_b, H.rel_err(gx[n], gz[n]))
+        if float(gz[n].float().norm()) < 1e-6 or ("vision_tower" in n and n.endswith("self_attn.k_proj.bias")):
+            continue  # mathematically-zero gradients (softmax invariance): rounding noise on both sides
+        e_ = H.rel_err(gx[n], gz[n])
+        if e_ > worst_b:
+            worst_b, worst_b_name = e_, n
+    if rank == 0:
+        print(f"B: worst N=2-vs-N=1 tensor: {worst_b_name} ({worst_b:.3e})", flush=True)
     # ---- C: sums in the arenas + 1/world folded into the fused optimiser
     from kai0_b200.optim import FusedClipAdamW
 
@@ -111,9 +115,12 @@ def main():
     # last bit, which may flip the bf16 rounding of a few updated values by one ulp - compare in ulps, and count them)
     worst_c, worst_c_name, frac_c = 0.0, None, 0.0
     for (n_, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if "lm_head" in n_:
+            continue  # never trained, not part of the seeded weights (left at its unseeded initialisation)
         a_, b_ = p1.float(), p2.float()
-        d = float(((a_ - b_).abs() / (a_.abs() + 1e-3)).max())
-        frac_c = max(frac_c, float((a_ != b_).float().mean()))
+        rel_ = (a_ - b_).abs() / (a_.abs() + 1e-3)
+        d = float(rel_.max())
+        frac_c = max(frac_c, float((rel_ > 1e-5).float().mean()))  # beyond fp32 last-bit noise: bf16 one-ulp flips
         if d > worst_c:
             worst_c, worst_c_name = d, n_
     same_c = worst_c <= 2 ** -7 and frac_c < 1e-2 and abs(n1 - n2) < 1e-5 * max(n1, 1e-9)

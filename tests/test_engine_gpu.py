@@ -120,7 +120,7 @@ def test_sample_actions_matches_oracle_and_golden(name):
     assert H.rel_err(a5, r5) < TOL_ACTIONS
 
 
-@pytest.mark.parametrize("name,B", [("tiny", 3), ("mid", 2)])
+@pytest.mark.parametrize("name,B", [("tiny", 3), ("mid", 2), ("mid", 4)])
 def test_backward_matches_oracle_autograd(name, B):
     oc = _cfg(name)
     model, params = H.build_pair(oc, seed=1)
@@ -357,3 +357,34 @@ def test_engines_are_kept_per_mode_and_image_count():
     model.sample_values("cuda", o6)
     assert model._engine is h6
     assert v3a.shape == v3b.shape == (2, 1)
+
+
+def test_sharded_gradients_average_to_the_full_batch_gradient():
+    """Data-parallel equivalence without any collective (the 2-GPU NCCL version is tests/dp/dp_worker.py): the mean of the
+    per-shard gradients of loss.mean() equals the gradient on the concatenated batch, to bf16 rounding."""
+    oc = H.mid_config()
+    b = O.synthetic_batch(oc, 4, seed=5, ragged=True)
+
+    def grads(rows):
+        model, _ = H.build_pair(oc, seed=3)
+        model.train()
+        bb = dict(b)
+        bb["images"] = [i[rows] for i in b["images"]]
+        bb["img_masks"] = [m[rows] for m in b["img_masks"]]
+        bb["tokens"], bb["token_mask"] = b["tokens"][rows], b["token_mask"][rows]
+        loss = model(H.Obs(bb, "cuda"), b["actions"][rows].cuda(), b["noise"][rows].cuda(), b["time"][rows].cuda())
+        loss.mean().backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    g0, g1, gf = grads(slice(0, 2)), grads(slice(2, 4)), grads(slice(0, 4))
+    assert set(g0) == set(g1) == set(gf)
+    worst = (0.0, None)
+    for n in gf:
+        # mathematically-zero gradients hold only rounding noise: the SigLIP key biases (softmax is invariant to a per-query
+        # constant) and tensors whose norm is nothing next to the largest
+        if float(gf[n].norm()) < 1e-6 or ("vision_tower" in n and n.endswith("self_attn.k_proj.bias")):
+            continue
+        worst = max(worst, (H.rel_err(0.5 * (g0[n] + g1[n]), gf[n]), n))
+    print(f"\n[dp-equivalence] worst tensor {worst[1]}: {worst[0]:.3e}")
+    assert worst[0] < 2e-2, worst
