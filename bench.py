@@ -37,6 +37,19 @@ TRAIN_TFLOP_PER_SAMPLE = 3 * FWD_TFLOP_PER_SAMPLE
 # (engine.cu joint_layer_forward `prefix_live`): 2*968*2048*2048 + 3*2*968*2048*16384 + 2*2*(968*8)*968*256 flop forward
 SKIPPED_FWD_TFLOP_PER_SAMPLE = (2 * 968 * 2048 * 2048 + 3 * 2 * 968 * 2048 * 16384 + 2 * 2 * 968 * 8 * 968 * 256) / 1e12
 EXECUTED_TRAIN_TFLOP_PER_SAMPLE = TRAIN_TFLOP_PER_SAMPLE - 3 * SKIPPED_FWD_TFLOP_PER_SAMPLE
+
+
+def executed_train_tflop_per_sample(prefix_rows: int) -> float:
+    """FLOPs the engine executes per trained sample when the prefix has `prefix_rows` rows (968 dense; 768 + the batch's
+    longest prompt rounded up to 8 with prompt padding removal): SigLIP and the expert stream do not depend on it, the
+    PaliGemma projections / MLP scale with it, attention with prefix^2 + suffix * (prefix + suffix); the last layer's dead
+    prefix work is skipped either way (SURVEY.md §8d constants)."""
+    P, A = prefix_rows, 50
+    lin = 3.8368 * P / 968.0
+    attn = 4 * 8 * 256 * (P * P + A * (P + A)) * 18 / 1e12
+    fwd = 0.6605 + lin + 0.0311 + attn + 0.0003
+    dead = (2 * P * 2048 * 2048 + 3 * 2 * P * 2048 * 16384 + 2 * 2 * P * 8 * P * 256) / 1e12
+    return 3 * (fwd - dead)
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 
@@ -262,6 +275,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]/[2]: 32)")
     ap.add_argument("--ref-budget", type=float, default=420.0,
                     help="--impl reference: seconds the whole run (build + warm-up + K steps) should stay within")
+    ap.add_argument("--no-skip-padding", action="store_true",
+                    help="compute the padded prompt slots too (dense, as the reference does); default: the engine drops the "
+                         "slots that are padding in every sample of the batch, outputs and gradients unchanged")
     ap.add_argument("--overlap", action="store_true",
                     help="N>1: the engine's chunked exchange overlapped with backward instead of one exchange at the end of "
                          "backward (measured slower on power-capped B200s: profiles/r02_exchange_overlap.md)")
@@ -338,6 +354,7 @@ def main():
     model = PI0Pytorch(cfg, max_batch=B, init_weights=False).to(dev)
     model.reset_parameters()
     model.check_inputs = False
+    model.skip_prompt_padding = not args.no_skip_padding
     model.direct_grads = True  # public knob: .grad = views of the flat gradient arena (no per-parameter autograd copies)
     model.train()
     use_fused = not (args.per_param_optimizer or args.torch_optimizer)
@@ -512,6 +529,8 @@ def main():
 
     if rank == 0:
         peaks, peaks_kind = load_peaks()
+        ent_keep = model._engines[model._train_key]["keep"][0]
+        prefix_rows = 3 * (cfg.image_size // cfg.vit_patch) ** 2 + int(ent_keep[2].shape[1])  # image tokens + prompt slots kept
         samples = world * B * args.steps
         value = samples / (ms_dev / 1e3)
         e2e = samples / (ms_e2e / 1e3)
@@ -549,8 +568,9 @@ def main():
                 # model FLOPs (14.02 TFLOP per trained sample, dead last-layer prefix work included) and the
                 # FLOPs the engine actually executes (that work is skipped: 13.39 TFLOP), both against the same peak
                 "step_model_flops_utilisation": (value / world) * TRAIN_TFLOP_PER_SAMPLE / peak_tf,
-                "step_hardware_flops_utilisation": (value / world) * EXECUTED_TRAIN_TFLOP_PER_SAMPLE / peak_tf,
-                "tflop_per_sample": {"model": TRAIN_TFLOP_PER_SAMPLE, "executed": EXECUTED_TRAIN_TFLOP_PER_SAMPLE},
+                "step_hardware_flops_utilisation": (value / world) * executed_train_tflop_per_sample(prefix_rows) / peak_tf,
+                "tflop_per_sample": {"model": TRAIN_TFLOP_PER_SAMPLE, "executed_dense_prefix": EXECUTED_TRAIN_TFLOP_PER_SAMPLE,
+                                     "executed": executed_train_tflop_per_sample(prefix_rows), "prefix_rows": prefix_rows},
             }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -563,7 +583,12 @@ def main():
                               "flat arenas" if use_fused else
                               "torch.optim.AdamW(fused) + clip_grad_norm_(1.0) over "
                               + ("model.parameters()" if args.per_param_optimizer else "model.flat_parameters()")),
-                "gradient_exchange": None if world == 1 else model.exchange_description(), "exchange": exchange},
+                "gradient_exchange": None if world == 1 else model.exchange_description(), "exchange": exchange,
+                "prompt_padding": ("removed: the synthetic prompts hold 96 valid of 200 slots (SURVEY.md §8d); the slots that are "
+                                   "padding in every sample of the batch are not computed (pi05_batch.token_len), outputs and "
+                                   "gradients unchanged (tests/test_engine_gpu.py::test_prompt_padding_removal_is_lossless); "
+                                   f"prefix rows {prefix_rows} of 968" if not args.no_skip_padding else
+                                   "computed (dense, --no-skip-padding)")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host_d, host_a),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss,
                     "clocks": clocks_e2e},

@@ -71,6 +71,12 @@ typedef struct pi05_batch {
    * (image, sample, patch).  When set, `images` is not read (it may be NULL) and the fp32 im2col convolution is replaced
    * by one tcgen05 GEMM on the split operands (see pi05_preprocess_patches). */
   const void* patch_rows;
+  /* Optional (ABI 2): number of prompt slots actually present in `tokens` / `token_mask`, which are then [batch, token_len]
+   * (0 = max_token_len).  A caller whose prompts are left-aligned (valid slots first, as the reference's tokenizer pads:
+   * models/tokenizer.py:35-38) may drop the trailing slots that are padding in EVERY sample of the batch: padded slots are
+   * masked keys (probability exactly 0) and their own rows feed nothing, so every output and every gradient is unchanged
+   * while the prefix shrinks from num_images * T + max_token_len to num_images * T + token_len rows. */
+  int32_t token_len;
 } pi05_batch;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */

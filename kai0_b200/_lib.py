@@ -60,6 +60,7 @@ class Batch(C.Structure):
         ("tokens", C.c_void_p),
         ("token_mask", C.c_void_p),
         ("patch_rows", C.c_void_p),
+        ("token_len", C.c_int32),
     ]
 
 

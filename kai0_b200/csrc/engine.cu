@@ -68,6 +68,7 @@ int engine_plan(Engine& e, bool dry) {
   e.T = (c.image_size / c.vit_patch) * (c.image_size / c.vit_patch);
   e.NI = c.num_images;
   e.L = c.max_token_len;
+  e.Lmax = c.max_token_len;
   e.P = e.NI * e.T + e.L;
   e.A = c.action_horizon;
   e.S = e.P + e.A;
@@ -312,6 +313,24 @@ int engine_plan(Engine& e, bool dry) {
     set_error(e.err);
     return 5;
   }
+  return 0;
+}
+
+// pi05_batch.token_len: the prompt length of THIS batch (<= cfg.max_token_len).  Every extent and stride that depends on the
+// prefix length (P, S and their 8-element pitches) is a run-time value read at launch time; the workspace was planned for
+// the maximum, so a shorter prefix uses the leading part of each buffer.
+int engine_set_token_len(Engine& e, int token_len, const char* who) {
+  const int L = token_len > 0 ? token_len : e.Lmax;
+  if (L > e.Lmax) {
+    snprintf(e.err, sizeof(e.err), "%s: pi05_batch.token_len %d exceeds max_token_len %d", who, L, e.Lmax);
+    set_error(e.err);
+    return 8;
+  }
+  e.L = L;
+  e.P = e.NI * e.T + L;
+  e.S = e.P + e.A;
+  e.Ppad = round_up(e.P, 8);
+  e.Spad = round_up(e.S, 8);
   return 0;
 }
 
@@ -896,6 +915,7 @@ static int forward_network(Engine& e, const pi05_batch* b, const float* actions,
   }
   e.stream = st;
   e.taps.clear();
+  CHECK_RC(engine_set_token_len(e, b->token_len, who));
   const int B = b->batch;
   e.B = B;
   e.batch_copy = *b;

@@ -71,6 +71,7 @@ struct Engine {
   int device = 0;
   // derived sizes
   int T = 0, NI = 0, L = 0, P = 0, A = 0, S = 0, Spad = 0, Ppad = 0;
+  int Lmax = 0;  // cfg.max_token_len: buffers are planned for it; L / P / S / Ppad / Spad are those of the CURRENT batch
   int D = 0, E = 0, W = 0, H = 0, hd = 0, VH = 0, vhd = 0, Bmax = 0;
   bool train = false;
 
@@ -148,6 +149,7 @@ struct Engine {
 
 // engine.cu
 int engine_plan(Engine& e, bool dry);
+int engine_set_token_len(Engine& e, int token_len, const char* who);
 int engine_resolve_params(Engine& e);
 int engine_forward(Engine& e, const pi05_batch* b, const float* actions, const float* noise, const float* time,
                    float* loss_out, cudaStream_t st);

@@ -162,6 +162,7 @@ int engine_prefill(Engine& e, const pi05_batch* b, cudaStream_t st) {
   }
   e.stream = st;
   e.taps.clear();
+  CHECK_RC(engine_set_token_len(e, b->token_len, "pi05_prefill"));
   e.B = b->batch;
   CHECK_RC(prefix_forward(e, b));
   const int depth = e.cfg.paligemma.depth;

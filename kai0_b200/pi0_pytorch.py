@@ -328,6 +328,12 @@ class PI0Pytorch(nn.Module):
         # preprocessing writes straight into the patch-embedding GEMM operand (row f2); False: fp32 NCHW images + the fp32
         # im2col convolution on CUDA cores (round-1 path, kept as the cross-check in tests/test_preprocess_gpu.py)
         self.use_patch_rows = True
+        # Prompt padding removal: slots that are padding in EVERY sample of the batch (left-aligned masks, as the reference's
+        # tokenizer produces: models/tokenizer.py:35-38) are dropped before the engine call (pi05_batch.token_len).  Outputs
+        # and gradients are unchanged: a padded slot is a masked key (probability exactly 0) and its own row feeds nothing.
+        # Off automatically while taps are recorded (parity tests compare full-length intermediates).
+        self.skip_prompt_padding = True
+        self._token_len_cache = []
         self._augment_params_override = None
         self._pre_scratch = None
 
@@ -829,6 +835,28 @@ class PI0Pytorch(nn.Module):
             raise ValueError(f"images dict missing keys: expected {IMAGE_KEYS}, got {list(images)}")
         return IMAGE_KEYS
 
+    def _effective_token_len(self, lang_masks) -> int:
+        """Number of leading prompt slots to keep: the longest valid prompt of the batch, rounded up to 8, when every mask
+        row is left-aligned; the full length otherwise.  One small device->host read per NEW mask tensor (cached by
+        tensor object + version, so a resident batch costs nothing)."""
+        L = int(lang_masks.shape[1])
+        if not self.skip_prompt_padding or getattr(self, "_taps", False):
+            return L
+        # cache by tensor OBJECT (weak reference) + version counter: a pointer would be reused by a later allocation
+        import weakref
+
+        for ref, version, value in self._token_len_cache:
+            if ref() is lang_masks and version == lang_masks._version:
+                return value
+        m = lang_masks.to(torch.bool)
+        lens = m.sum(dim=1)
+        aligned = (m == (torch.arange(L, device=m.device)[None, :] < lens[:, None])).all()
+        ok, mx = torch.stack([aligned.to(torch.int64), lens.max().to(torch.int64)]).tolist()
+        out = L if not ok else min(L, max(8, (int(mx) + 7) // 8 * 8))
+        self._token_len_cache = [e for e in self._token_len_cache if e[0]() is not None][-7:]
+        self._token_len_cache.append((weakref.ref(lang_masks), lang_masks._version, out))
+        return out
+
     def _make_batch(self, images, img_masks, lang_tokens, lang_masks):
         dev = self._device()
         if len(images) != self._engine_key[3]:
@@ -841,13 +869,14 @@ class PI0Pytorch(nn.Module):
         else:
             imgs = torch.stack([i.to(dev, torch.float32) for i in images], dim=0).contiguous()
         masks = torch.stack([m.to(dev) for m in img_masks], dim=0).to(torch.uint8).contiguous()
-        toks = lang_tokens.to(dev, torch.int64).contiguous()
-        tmask = lang_masks.to(dev).to(torch.uint8).contiguous()
-        B = toks.shape[0]
-        if toks.shape[1] != self.ecfg.max_token_len:
-            raise ValueError(f"tokenized_prompt length {toks.shape[1]} != max_token_len {self.ecfg.max_token_len}")
-        if self.check_inputs and (int(toks.min()) < 0 or int(toks.max()) >= self.ecfg.vocab_size):
+        if lang_tokens.shape[1] != self.ecfg.max_token_len:
+            raise ValueError(f"tokenized_prompt length {lang_tokens.shape[1]} != max_token_len {self.ecfg.max_token_len}")
+        if self.check_inputs and (int(lang_tokens.min()) < 0 or int(lang_tokens.max()) >= self.ecfg.vocab_size):
             raise ValueError("token id out of range")
+        token_len = self._effective_token_len(lang_masks)
+        toks = lang_tokens[:, :token_len].to(dev, torch.int64).contiguous()
+        tmask = lang_masks[:, :token_len].to(dev).to(torch.uint8).contiguous()
+        B = toks.shape[0]
         b = _lib.Batch()
         b.batch = B
         b.images = imgs.data_ptr() if rows is None else None
@@ -855,6 +884,7 @@ class PI0Pytorch(nn.Module):
         b.image_masks = masks.data_ptr()
         b.tokens = toks.data_ptr()
         b.token_mask = tmask.data_ptr()
+        b.token_len = token_len
         return b, (imgs, masks, toks, tmask)
 
     def sample_noise(self, shape, device):  # pi0_pytorch.py:172-179
@@ -1072,7 +1102,7 @@ class PI0Pytorch(nn.Module):
         per-launch host cost.  Static device buffers hold the inputs; the graph is captured once per (batch, steps)."""
         imgs, masks, toks, tmask = keep
         is_rows = bool(b.patch_rows)
-        key = (b.batch, num_steps, is_rows)
+        key = (b.batch, num_steps, is_rows, int(b.token_len))
         ent = self._graphs.get(key)
         l = _lib.lib()
         if ent is None:
@@ -1084,6 +1114,7 @@ class PI0Pytorch(nn.Module):
             sb.patch_rows = st["imgs"].data_ptr() if is_rows else None
             sb.image_masks = st["masks"].data_ptr()
             sb.tokens, sb.token_mask = st["toks"].data_ptr(), st["tmask"].data_ptr()
+            sb.token_len = b.token_len
             l.pi05_set_taps(self._engine, 0)
 
             def run():

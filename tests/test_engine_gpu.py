@@ -388,3 +388,39 @@ def test_sharded_gradients_average_to_the_full_batch_gradient():
         worst = max(worst, (H.rel_err(0.5 * (g0[n] + g1[n]), gf[n]), n))
     print(f"\n[dp-equivalence] worst tensor {worst[1]}: {worst[0]:.3e}")
     assert worst[0] < 2e-2, worst
+
+
+def test_prompt_padding_removal_is_lossless():
+    """pi05_batch.token_len: dropping the prompt slots that are padding in every sample changes no output and no gradient
+    (a padded slot is a masked key with probability exactly 0, and its own row feeds nothing).  Not bit for bit: the suffix
+    keys sit at another offset of the key dimension, so the tensor cores group the P·V and weight-gradient accumulations
+    differently and a few bf16 roundings flip - the comparison is to that noise (measured values are printed)."""
+    oc = H.mid_config()
+    b = O.synthetic_batch(oc, 3, seed=21, ragged=True)  # 19 / 16 / 13 valid prompt slots of 40
+    out = {}
+    for skip in (True, False):
+        model, _ = H.build_pair(oc, seed=12)
+        model.skip_prompt_padding = skip
+        model.train()
+        loss = model(H.Obs(b, "cuda"), b["actions"].cuda(), b["noise"].cuda(), b["time"].cuda())
+        loss.mean().backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+        tl = int(model._engine_ent["keep"][0][2].shape[1])  # token columns the engine was given
+        model.eval()
+        acts = model.sample_actions("cuda", H.Obs(b, "cuda"), noise=b["noise"].cuda())
+        out[skip] = (loss.detach().clone(), acts.clone(), grads, tl)
+    assert out[True][3] == 24 and out[False][3] == oc.max_token_len  # longest prompt 19 -> rounded up to 24 of 40
+    e_loss, e_act = H.rel_err(out[True][0], out[False][0]), H.rel_err(out[True][1], out[False][1])
+    print(f"\n[padding] with vs without prompt padding removal: loss tensor {e_loss:.3e}, action chunk {e_act:.3e}")
+    assert e_loss < 2e-3 and e_act < 1e-3
+    worst = max((H.rel_err(out[True][2][n], g), n) for n, g in out[False][2].items() if float(g.norm()) > 1e-6
+                and not ("vision_tower" in n and n.endswith("self_attn.k_proj.bias")))
+    print(f"\n[padding] worst gradient difference with / without prompt padding removal: {worst[0]:.3e} ({worst[1]})")
+    assert worst[0] < 2e-3, worst
+    # a mask that is not left-aligned keeps the full length
+    model, _ = H.build_pair(oc, seed=12)
+    hole = b["token_mask"].clone()
+    hole[0, 2] = False
+    assert model._effective_token_len(hole.cuda()) == oc.max_token_len
+    assert model._effective_token_len(b["token_mask"].cuda()) == 24

@@ -224,3 +224,30 @@ def test_submodule_moves_and_assigning_loads_are_refused():
     p = m.action_in_proj.weight
     lo = m._flat[torch.float32].data_ptr()
     assert lo <= p.data_ptr() < lo + m._flat[torch.float32].numel() * 4
+
+
+def test_effective_token_len_rules():
+    """Host logic of the prompt padding removal (pi05_batch.token_len): longest left-aligned prompt rounded up to 8, the
+    full length for masks with holes, while taps are recorded, or when switched off."""
+    import torch
+
+    from kai0_b200.pi0_pytorch import GemmaVariant, PI0Pytorch, Pi05EngineConfig
+
+    cfg = Pi05EngineConfig(paligemma_variant=GemmaVariant(64, 2, 128, 8, 1, 16),
+                           action_expert_variant=GemmaVariant(32, 2, 64, 8, 1, 16), vit_width=32, vit_depth=1,
+                           vit_mlp_dim=64, vit_heads=2, image_size=28, vocab_size=64, max_token_len=40)
+    m = PI0Pytorch(cfg)
+    mask = torch.zeros(3, 40, dtype=torch.bool)
+    mask[0, :19] = True
+    mask[1, :3] = True
+    assert m._effective_token_len(mask) == 24
+    assert m._effective_token_len(torch.zeros(2, 40, dtype=torch.bool)) == 8
+    assert m._effective_token_len(torch.ones(2, 40, dtype=torch.bool)) == 40
+    hole = mask.clone()
+    hole[0, 5] = False
+    assert m._effective_token_len(hole) == 40
+    m.set_taps(True)
+    assert m._effective_token_len(mask.clone()) == 40
+    m.set_taps(False)
+    m.skip_prompt_padding = False
+    assert m._effective_token_len(mask.clone()) == 40
