@@ -45,6 +45,7 @@ struct KParams {
   const float* rowadd32;
   int rowadd_period;
   long long ld_rowadd;
+  int group_m;              // tile rasterisation: m-blocks per group (tiles of a group share their A panels in L2)
   int static_sched;         // 1: static `tile += grid` walk instead of the dynamic tile ring (PI05_GEMM_STATIC=1: A/B runs)
 };
 
@@ -59,10 +60,11 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const KParams& p) {
   c.z1 = c.z / p.nz0;
   c.z0 = c.z - c.z1 * p.nz0;
   const int t = tile - c.z * per_batch;
-  const int group_span = GROUP_M * p.num_n;
+  const int gm = p.group_m;
+  const int group_span = gm * p.num_n;
   const int group = t / group_span;
-  const int first_m = group * GROUP_M;
-  const int gsz = min(GROUP_M, p.num_m - first_m);
+  const int first_m = group * gm;
+  const int gsz = min(gm, p.num_m - first_m);
   const int r = t - group * group_span;
   c.m_blk = first_m + r % gsz;
   c.n_blk = r / gsz;

@@ -1029,6 +1029,8 @@ static int gemm_bf16_impl(const GemmArgs& a, cudaStream_t stream, char* err, int
   kp.mn_sbo = 1024;
   // Dynamic tile scheduling pays one atomic round trip per kernel (~0.3 us on a 3-10 us decode GEMM: measured +0.5 ms on
   // the 10-step decode), and buys nothing when no CTA / cluster gets more than one tile: those launches walk statically.
+  static const int group_m_env = getenv("PI05_GROUP_M") ? atoi(getenv("PI05_GROUP_M")) : 0;
+  kp.group_m = group_m_env > 0 ? group_m_env : GROUP_M;
   static const bool static_sched = getenv("PI05_GEMM_STATIC") != nullptr;
   {
     const long long tiles = use2 ? static_cast<long long>((kp.num_m + 1) / 2) * kp.num_n * kp.batch
