@@ -481,8 +481,8 @@ def main():
             exchange = {"payload_gb": payload / 1e9, "collectives_per_backward": overl_calls, "max_ctas": model._dp_max_ctas,
                         "standalone_ms": ms, "standalone_algbw_gbs": payload / 1e9 / (ms / 1e3),
                         "standalone_busbw_gbs": 2.0 * (world - 1) / world * payload / 1e9 / (ms / 1e3),
-                        "note": "standalone = the same payload as ONE un-overlapped exchange on an idle GPU through this "
-                                "communicator (few CTAs by design); in the step it runs chunk by chunk under backward"}
+                        "note": "standalone = the same payload as ONE exchange on an idle GPU through this communicator "
+                                "(max_ctas > 0: maxCTAs of the overlapped mode; < 0: minCTAs of the end-of-backward mode)"}
         barrier()
 
     if rank == 0 and os.environ.get("PI05_TORCH_PROFILE"):

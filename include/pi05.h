@@ -255,7 +255,8 @@ int pi05_allreduce_grads(pi05_engine* e, void* nccl_comm, int32_t nranks, int32_
 /* Communicator helpers for hosts without an NCCL binding of their own (the Python host uses them through ctypes):
  * rank 0 calls pi05_nccl_unique_id (128 bytes out) and ships the id to every rank by its own means (torch.distributed's
  * store here); every rank then calls pi05_nccl_comm_create (collective).  max_ctas > 0 bounds the SMs the communicator's
- * kernels may occupy (ncclConfig_t.maxCTAs); 0 = NCCL's default. */
+ * kernels may occupy (ncclConfig_t.maxCTAs, for the overlapped exchange); max_ctas < 0 asks for at least -max_ctas CTAs
+ * (ncclConfig_t.minCTAs, for the exchange at the end of backward); 0 = NCCL's defaults. */
 int pi05_nccl_unique_id(void* out128);
 int pi05_nccl_comm_create(const void* unique_id128, int32_t nranks, int32_t rank, int32_t max_ctas, void** comm_out);
 int pi05_nccl_comm_destroy(void* comm);

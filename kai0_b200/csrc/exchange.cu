@@ -285,14 +285,24 @@ extern "C" int pi05_nccl_comm_create(const void* unique_id128, int32_t nranks, i
   int rc = -1;
   int runtime_version = 0;
   if (api.get_version) reinterpret_cast<ncclResult_t (*)(int*)>(api.get_version)(&runtime_version);
-  if (max_ctas > 0 && api.init_rank_config && runtime_version >= NCCL_VERSION_CODE) {
-    // few CTAs: the exchange overlaps backward, its average demand is ~30 GB/s of the 900 GB/s NVLink 5 port
+  if (max_ctas != 0 && api.init_rank_config && runtime_version >= NCCL_VERSION_CODE) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
     cfg.blocking = 1;
-    cfg.minCTAs = 1;
-    cfg.maxCTAs = max_ctas;
+    if (max_ctas > 0) {
+      // few CTAs: the exchange overlaps backward, its average demand is ~30 GB/s of the 900 GB/s NVLink 5 port
+      cfg.minCTAs = 1;
+      cfg.maxCTAs = max_ctas;
+    } else {
+      // exchange at the end of backward on idle SMs: at least -max_ctas CTAs (measured on 8 B200s, 6.95 GB payload:
+      // 14.7 ms = 830 GB/s bus bandwidth with 32, tools/allreduce_probe.py)
+      cfg.minCTAs = -max_ctas;
+    }
     rc = reinterpret_cast<ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*)>(api.init_rank_config)(
         &comm, nranks, id, rank, &cfg);
+    if (rc != 0) {  // a configuration this NCCL build refuses must not cost the communicator: plain init
+      comm = nullptr;
+      rc = reinterpret_cast<ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int)>(api.init_rank)(&comm, nranks, id, rank);
+    }
   } else {
     rc = reinterpret_cast<ncclResult_t (*)(ncclComm_t*, int, ncclUniqueId, int)>(api.init_rank)(&comm, nranks, id, rank);
   }

@@ -536,7 +536,9 @@ class PI0Pytorch(nn.Module):
 
             dev = self._device()
             if max_ctas is None:
-                max_ctas = int(os.environ.get("PI05_NCCL_MAX_CTAS", "4")) if overlap else 0  # 0 = NCCL's default
+                # overlapped: at most 4 CTAs; at the end of backward: at least 32 (negative = minCTAs, include/pi05.h)
+                max_ctas = (int(os.environ.get("PI05_NCCL_MAX_CTAS", "4")) if overlap
+                            else -int(os.environ.get("PI05_NCCL_MIN_CTAS", "32")))
             rank = dist.get_rank(self._dp_group)
             uid = C.create_string_buffer(128)
             l = _lib.lib()
@@ -571,8 +573,8 @@ class PI0Pytorch(nn.Module):
             _lib.lib().pi05_grad_exchange_stats(h, C.byref(calls), C.byref(nbytes))
         how = ("per gradient group, overlapped with backward on a high-priority stream" if self._dp_overlap
                else "of the two gradient arenas at the end of pi05_backward")
-        return (f"engine-issued ncclAllReduce(sum) {how} (own communicator, maxCTAs "
-                f"{self._dp_max_ctas or 'default'}; last backward: {calls.value} collectives, {nbytes.value / 1e9:.2f} GB); "
+        ctas = f"maxCTAs {self._dp_max_ctas}" if self._dp_max_ctas > 0 else f"minCTAs {-self._dp_max_ctas}"
+        return (f"engine-issued ncclAllReduce(sum) {how} (own communicator, {ctas}; last backward: {calls.value} collectives, {nbytes.value / 1e9:.2f} GB); "
                 f"average {self._dp_average}")
 
     # ------------------------------------------------------------------ engine lifecycle
