@@ -251,3 +251,51 @@ def test_effective_token_len_rules():
     m.set_taps(False)
     m.skip_prompt_padding = False
     assert m._effective_token_len(mask.clone()) == 40
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_bookkeeping():
+    """bench.py's numbers that are not measured: both arms print the same `config`; executed FLOPs reduce to the documented
+    dense figure at 968 prefix rows and scale down with prompt padding removal; the ncu traffic table falls back to the same
+    GEMM class with the capture shape stated."""
+    b = _load_bench()
+    assert b.bench_config(8, 32, False) == b.bench_config(8, 32, False)
+    assert b.bench_config(1, 32, False)["parallelism"] == "dp1" and b.bench_config(8, 32, False)["global_batch"] == 256
+    dense = b.executed_train_tflop_per_sample(968)
+    assert abs(dense - b.EXECUTED_TRAIN_TFLOP_PER_SAMPLE) < 5e-3 and dense < b.TRAIN_TFLOP_PER_SAMPLE
+    assert 12.0 < b.executed_train_tflop_per_sample(864) < dense
+    v, note = b.ncu_traffic(32768, 2048, 30976, 0, 3)
+    assert v == b.NCU_TRAFFIC_BYTES[(32768, 2048, 30976, 0, 3)] and "this shape" in note
+    v2, note2 = b.ncu_traffic(32768, 2048, 27648, 0, 3)
+    assert v2 == v and "dense prefix" in note2
+    assert b.ncu_traffic(7, 7, 7, 0, 0)[0] is None
+
+
+def test_staged_reference_is_byte_identical_to_the_checkout():
+    """baseline/_ref (git-ignored; what bench.py's reference legs execute on the GPU box) must be the UNMODIFIED package."""
+    import filecmp
+
+    import pytest
+
+    src, dst = "/root/reference/src/openpi", os.path.join(ROOT, "baseline", "_ref", "openpi")
+    if not (os.path.isdir(src) and os.path.isdir(dst)):
+        pytest.skip("needs the reference checkout and a staged copy (tools/stage_reference.py)")
+    n = 0
+    for d, _, files in os.walk(src):
+        if "__pycache__" in d:
+            continue
+        for f in files:
+            if f.endswith(".pyc"):
+                continue
+            rel = os.path.relpath(os.path.join(d, f), src)
+            assert filecmp.cmp(os.path.join(d, f), os.path.join(dst, rel), shallow=False), rel
+            n += 1
+    assert n > 20
