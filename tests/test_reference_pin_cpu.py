@@ -147,3 +147,50 @@ def test_default_forward_consumes_random_numbers_in_the_reference_order():
         loss = O.forward_loss(params, oc, [imgs[k] for k in PIN.KEYS], b["img_masks"], b["tokens"], b["token_mask"],
                               b["actions"], noise, time)
     assert H.rel_err(loss, g["loss_default_float32"]) < 1e-5
+
+
+def test_full_size_reference_fixture_states_the_references_own_bf16_floor():
+    """tests/golden/reference_full.pt (the reference's own model at BASELINE.json's full architecture, both precisions;
+    tools/make_golden_reference_full.py): shapes, coverage and the figures DESIGN.md §0 / §3 quote from it -- the
+    reference's bf16 run is 2.6e-3 .. 2.8e-3 from its float32 run on the action chunk, differs from itself by ~2e-3 at
+    another batch shape, and leaves exactly the six unreachable parameters (and the lm_heads) without a gradient."""
+    import os
+
+    import torch
+
+    from oracle import pi05_oracle as O
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_full.pt"))
+    rel = lambda a, b: float((a - b).norm() / b.norm())  # noqa: E731
+    for r in (0, 1):
+        b16, f32 = g[f"actions_b1_row{r}_bfloat16"], g[f"actions_b1_row{r}_float32"]
+        assert b16.shape == f32.shape == (1, 50, 32)
+        assert 2.0e-3 < rel(b16, f32) < 3.5e-3
+        assert 1.5e-3 < rel(g["actions_b2_bfloat16"][r:r + 1], b16) < 3.0e-3
+    assert g["loss_bfloat16"].shape == g["loss_float32"].shape == (2, 50, 32)
+    assert 5e-3 < rel(g["loss_bfloat16"], g["loss_float32"]) < 1.2e-2
+    specs = O.param_specs(O.OracleConfig())
+    missing = sorted(k for k in specs if k not in g["grads_bfloat16"])
+    lm = "paligemma_with_expert.paligemma.model.language_model."
+    assert missing == sorted([lm + "layers.17.self_attn.o_proj.weight", lm + "layers.17.mlp.gate_proj.weight",
+                              lm + "layers.17.mlp.up_proj.weight", lm + "layers.17.mlp.down_proj.weight",
+                              lm + "layers.17.post_attention_layernorm.weight", lm + "norm.weight"])
+    assert len(g["grads_bfloat16"]) == 805
+
+
+def test_engine_host_rtc_helpers_equal_the_oracle():
+    """The host-side tables of pi05_denoise_rtc (prefix weights, per-step guidance weights) are the oracle's."""
+    import torch
+
+    from kai0_b200.pi0_pytorch import PI0Pytorch
+    from oracle import rtc_oracle as R
+
+    for sch in ("ones", "zeros", "linear", "exp"):
+        for start, end in ((0, 4), (2, 6), (3, 50), (9, 3)):
+            assert torch.equal(PI0Pytorch.rtc_prefix_weights(start, end, 50, sch), R.get_prefix_weights(start, end, 50, sch))
+    for steps, mx in ((10, 0.5), (10, 5.0), (5, 50.0)):
+        t, dt, ref = torch.tensor(1.0), torch.tensor(-1.0 / steps, dtype=torch.float32), []
+        for _ in range(steps):
+            ref.append(R.guidance_weight(float(t), mx))
+            t = t + dt
+        assert PI0Pytorch.rtc_guidance_weights(steps, mx) == pytest.approx(ref, rel=1e-6)
