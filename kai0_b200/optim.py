@@ -58,11 +58,77 @@ class FusedClipAdamW:
         _lib.check(rc, "pi05_fused_clip_adamw_scaled")
         return self._scratch[0]
 
-    def state_dict(self):
-        return {"step": self.step_count, "param_groups": self.param_groups,
-                "exp_avg": [t.clone() for t in self.m], "exp_avg_sq": [t.clone() for t in self.v]}
+    # ---- checkpoint interchange -----------------------------------------------------------------------------
+    def _named_slots(self):
+        """(index in list(model.parameters()), name, arena index, offset, numel, shape) of every parameter the update
+        touches AND the reference's autograd gives a gradient: the entries a stock torch.optim.AdamW over
+        model.parameters() holds state for (train_pytorch.py:469-475)."""
+        from .pi0_pytorch import _UNUSED
+
+        model = self.model
+        used_bf16 = self.flat[0].numel()
+        slots = []
+        for i, (name, p) in enumerate(model.named_parameters()):
+            dt, off, n, shape = model._offsets[name]
+            if name in _UNUSED or name in model._dead_grad_names or not p.requires_grad:
+                continue
+            arena = 0 if dt == torch.bfloat16 else 1
+            if arena == 0 and off + n > used_bf16:
+                continue
+            slots.append((i, name, arena, off, n, shape))
+        return slots
+
+    def state_dict(self, format: str = "flat"):
+        """format="flat": this class's own compact record (two moment arenas per statistic).
+        format="torch": the layout `torch.optim.AdamW(model.parameters(), ...).state_dict()` has -- per-parameter `step`,
+        `exp_avg`, `exp_avg_sq` keyed by the parameter's position in `model.parameters()` -- so an `optimizer.pt` written
+        here (train_pytorch.py:170) resumes under the reference's stock optimiser and vice versa."""
+        if format == "flat":
+            return {"step": self.step_count, "param_groups": self.param_groups,
+                    "exp_avg": [t.clone() for t in self.m], "exp_avg_sq": [t.clone() for t in self.v]}
+        if format != "torch":
+            raise ValueError("format must be 'flat' or 'torch'")
+        g = self.param_groups[0]
+        n_params = sum(1 for _ in self.model.parameters())
+        proto = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=g["lr"], betas=g["betas"], eps=g["eps"],
+                                  weight_decay=g["weight_decay"]).state_dict()["param_groups"][0]
+        group = {**proto, "params": list(range(n_params))}
+        state = {}
+        if self.step_count > 0:
+            for i, _, arena, off, n, shape in self._named_slots():
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[arena][off:off + n].view(shape).clone(),
+                            "exp_avg_sq": self.v[arena][off:off + n].view(shape).clone()}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
+        """Accepts both layouts of `state_dict` (a stock AdamW `optimizer.pt` of the reference included)."""
+        if "state" in sd and "exp_avg" not in sd:
+            groups = sd["param_groups"]
+            if len(groups) != 1:
+                raise ValueError("FusedClipAdamW holds one parameter group (train_pytorch.py:469-475 builds one)")
+            g = groups[0]
+            mine = self.param_groups[0]
+            self.param_groups = [dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"],
+                                      max_norm=mine["max_norm"])]
+            for t in (*self.m, *self.v):
+                t.zero_()
+            steps = set()
+            slots = {i: s for s in self._named_slots() for i in (s[0],)}
+            for key, rec in sd["state"].items():
+                slot = slots.get(int(key))
+                if slot is None:
+                    raise ValueError(f"optimizer state for parameter #{key}, which this engine does not update")
+                _, name, arena, off, n, shape = slot
+                if tuple(rec["exp_avg"].shape) != tuple(shape):
+                    raise ValueError(f"optimizer state of {name}: shape {tuple(rec['exp_avg'].shape)} != {tuple(shape)}")
+                self.m[arena][off:off + n].view(shape).copy_(rec["exp_avg"])
+                self.v[arena][off:off + n].view(shape).copy_(rec["exp_avg_sq"])
+                steps.add(int(float(rec["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused update keeps ONE step count")
+            self.step_count = steps.pop() if steps else 0
+            return
         self.step_count = int(sd["step"])
         self.param_groups = sd["param_groups"]
         for dst, src in zip(self.m, sd["exp_avg"]):

@@ -184,6 +184,66 @@ def parameter_table(cfg: Pi05EngineConfig, pg: GemmaVariant, ex: GemmaVariant, v
 
 _UNUSED = (_PWE + "gemma_expert.lm_head.weight",)  # parameters the path never reads (no gradient)
 
+# Order in which the reference's module tree REGISTERS its parameters, i.e. the order of `model.parameters()` /
+# `named_parameters()` of the reference `PI0Pytorch` (pi0_pytorch.py:92-109; gemma_pytorch.py:57-59;
+# modeling_paligemma.py:138-149,389-393; modeling_siglip.py:212-231 embeddings, :435-442 encoder layer = layer_norm1,
+# self_attn, layer_norm2, mlp, :348-369 attention = k_proj, v_proj, q_proj, out_proj, :420-426 mlp = fc1, fc2;
+# modeling_gemma.py:332-342 decoder layer = self_attn (q, k, v, o :256-280), mlp (gate, up, down :113-121),
+# input_layernorm, post_attention_layernorm; then the model's final norm and the causal-LM head).  It matters because
+# `torch.optim.AdamW.state_dict()` -- the `optimizer.pt` of a checkpoint directory (train_pytorch.py:170,236-243) --
+# keys its per-parameter state by POSITION in `model.parameters()`: with the same registration order a checkpoint
+# written by the reference resumes on this module and vice versa.  (The arenas keep their own layout: `parameter_table`.)
+_REG_TOP = ("paligemma_with_expert", "action_in_proj", "action_out_proj", "time_mlp_in", "time_mlp_out", "value_head")
+_REG_VIT_LAYER = ("layer_norm1", "self_attn.k_proj", "self_attn.v_proj", "self_attn.q_proj", "self_attn.out_proj",
+                  "layer_norm2", "mlp.fc1", "mlp.fc2")
+_REG_GEMMA_LAYER = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj",
+                    "mlp.up_proj", "mlp.down_proj", "input_layernorm", "post_attention_layernorm")
+
+
+def _registration_key(name: str):
+    """Sort key reproducing the reference's `named_parameters()` order (see _REG_* above)."""
+    wb = 1 if name.endswith(".bias") else 0
+    top = name.split(".", 1)[0]
+    if top != "paligemma_with_expert":
+        # nn.Linear / nn.Sequential heads: weight then bias, Sequential children by index
+        idx = int(name.split(".")[1]) if top == "value_head" else 0
+        return (_REG_TOP.index(top), idx, wb)
+
+    def in_layer(rest: str, stems):
+        i, tail = rest.split(".", 1)
+        stem = next(s for s in stems if tail.startswith(s + "."))
+        return (int(i), stems.index(stem), wb)
+
+    if name.startswith(_VT):
+        rest = name[len(_VT):]
+        if rest.startswith("embeddings.patch_embedding."):
+            k = (0, 0, 0, wb)
+        elif rest.startswith("embeddings.position_embedding."):
+            k = (0, 1, 0, 0)
+        elif rest.startswith("encoder.layers."):
+            k = (1, *in_layer(rest[len("encoder.layers."):], _REG_VIT_LAYER))
+        else:  # post_layernorm
+            k = (2, 0, 0, wb)
+        return (0, 0, 0, *k)
+    if name.startswith(_PWE + "paligemma.model.multi_modal_projector."):
+        return (0, 0, 1, wb)
+    for which, prefix in ((0, _LM), (1, _EX)):
+        if name.startswith(prefix):
+            rest = name[len(prefix):]
+            if rest.startswith("embed_tokens."):
+                k = (0, 0, 0, 0)
+            elif rest.startswith("layers."):
+                k = (1, *in_layer(rest[len("layers."):], _REG_GEMMA_LAYER))
+            else:  # final norm
+                k = (2, 0, 0, wb)
+            # paligemma: model.language_model is the third child of paligemma.model; expert: its own model
+            return (0, 0, 2, *k) if which == 0 else (0, 1, 0, *k)
+    if name == _PWE + "paligemma.lm_head.weight":
+        return (0, 0, 3)
+    if name == _PWE + "gemma_expert.lm_head.weight":
+        return (0, 1, 1)
+    raise KeyError(name)
+
 
 class _Node(nn.Module):
     """Parameter-only skeleton module: gives parameters the reference's dotted state_dict paths."""
@@ -355,7 +415,10 @@ class PI0Pytorch(nn.Module):
         }
         del n_bf16, n_f32
         self._flat_grad = {torch.bfloat16: None, torch.float32: None}
-        for name, shape, dt, _ in table:
+        # registered in the REFERENCE'S order (see _registration_key), independent of the arena layout above
+        specs = {name: (shape, dt) for name, shape, dt, _ in table}
+        for name in sorted(specs, key=_registration_key):
+            shape, dt = specs[name]
             _, o, n, _ = self._offsets[name]
             p = nn.Parameter(self._flat[dt][o : o + n].view(shape), requires_grad=True)
             _attach(self, name, p)

@@ -1,0 +1,495 @@
+"""Host side of the serving path (second half): kai0_b200/serving.py and kai0_b200/checkpoint.py against
+the reference's own code.
+
+Three kinds of checks:
+  * fixtures: tests/golden/serving_reference.npz holds what the REFERENCE'S `transforms.py`, `agilex_policy.py`,
+    `tokenizer.py`, `normalize.py` and `openpi_client/image_tools.py` produced on seeded requests
+    (tools/make_golden_serving.py); this module must reproduce every array bit for bit, dtype included;
+  * live: when /root/reference is present the reference code is executed again and compared the same way;
+  * the reference's own unit tests (transforms_test.py, shared/normalize_test.py) restated on this module.
+The request batcher, the checkpoint directory and the optimiser-state interchange have no counterpart to compare with
+and are tested for their contracts.
+"""
+import json
+import os
+import sys
+import threading
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from kai0_b200 import checkpoint as CK
+from kai0_b200 import serving as S
+from oracle import pi05_oracle as O
+
+sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+import make_golden_serving as MG  # noqa: E402
+import reference_serving_loader as RSL  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FIX = np.load(os.path.join(GOLD, "serving_reference.npz"))
+
+
+def _mine():
+    lib = types.SimpleNamespace(
+        compose=S.compose, InjectDefaultPrompt=S.InjectDefaultPrompt, DeltaActions=S.DeltaActions, Normalize=S.Normalize,
+        ResizeImages=S.ResizeImages, TokenizePrompt=S.TokenizePrompt, PadStatesAndActions=S.PadStatesAndActions,
+        Unnormalize=S.Unnormalize, AbsoluteActions=S.AbsoluteActions, make_bool_mask=S.make_bool_mask,
+        agilex_inputs=lambda d: S.AgilexInputs(action_dim=d, pi05=True), agilex_outputs=S.AgilexOutputs)
+    return lib, (lambda n: S.PaligemmaTokenizer(n, model_path=MG.SPM)), S.NormStats
+
+
+def _same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape, f"{what}: {a.dtype}{a.shape} vs {b.dtype}{b.shape}"
+    assert np.array_equal(a, b), f"{what}: max |diff| {np.abs(a.astype(np.float64) - b.astype(np.float64)).max()}"
+
+
+@pytest.mark.parametrize("name,quant", [("quantile", True), ("zscore", False)])
+def test_request_and_reply_transforms_reproduce_the_reference_outputs(name, quant):
+    lib, tok, ns = _mine()
+    inputs, replies = MG.run(lib, tok, ns, use_quantiles=quant)
+    got = {}
+    MG.flatten_case(name, inputs, replies, got)
+    keys = [k for k in FIX.files if k.startswith(name + "/")]
+    assert sorted(keys) == sorted(got)
+    for k in keys:
+        _same(got[k], FIX[k], k)
+    # what the chain is expected to have done (agilex_policy.py:95-97, tokenizer.py:24-30, image_tools.py:44-57)
+    assert inputs[0]["state"].shape == (32,) and replies[0]["actions"].shape == (MG.HORIZON, 14)
+    assert inputs[0]["image"]["base_0_rgb"].shape == (MG.IMAGE_SIZE, MG.IMAGE_SIZE, 3)
+    assert inputs[0]["image"]["base_0_rgb"].dtype == np.uint8
+    lens = [int(np.asarray(x["tokenized_prompt_mask"]).sum()) for x in inputs]
+    if quant:
+        assert max(lens) == MG.MAX_TOKEN_LEN and min(lens) < MG.MAX_TOKEN_LEN  # one truncated, the others padded
+    assert set(inputs[0]["image"]) == {"base_0_rgb", "left_wrist_0_rgb", "right_wrist_0_rgb"}
+
+
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+@pytest.mark.parametrize("quant", [True, False])
+def test_request_and_reply_transforms_equal_the_reference_run_live(quant):
+    R, rlib, rtok, rns = MG.reference_lib()
+    lib, tok, ns = _mine()
+    ri, ro = MG.run(rlib, rtok, rns, use_quantiles=quant)
+    mi, mo = MG.run(lib, tok, ns, use_quantiles=quant)
+    for i, (a, b) in enumerate(zip(mi, ri)):
+        fa, fb = S.flatten_dict(a), R.transforms.flatten_dict(b)
+        assert list(fa) == list(fb), (list(fa), list(fb))  # same keys in the same order
+        for k in fa:
+            _same(fa[k], fb[k], f"request {i} {k}")
+    for i, (a, b) in enumerate(zip(mo, ro)):
+        assert list(a) == list(b) == ["actions"]
+        _same(a["actions"], b["actions"], f"reply {i}")
+
+
+# ------------------------------------------------------------------ the reference's own unit tests, restated
+def test_repack_transform():  # transforms_test.py:8-17
+    t = S.RepackTransform(structure={"a": {"b": "b/c"}, "d": "e/f"})
+    assert t({"b": {"c": 1}, "e": {"f": 2}}) == {"a": {"b": 1}, "d": 2}
+
+
+def test_delta_and_absolute_actions():  # transforms_test.py:20-67
+    item = {"state": np.array([1, 2, 3]), "actions": np.array([[3, 4, 5], [5, 6, 7]])}
+    out = S.DeltaActions(mask=[False, True])(item)
+    assert np.all(out["state"] == np.array([1, 2, 3]))
+    assert np.all(out["actions"] == np.array([[3, 2, 5], [5, 4, 7]]))
+    item = {"state": np.array([1, 2, 3]), "actions": np.array([[3, 4, 5], [5, 6, 7]])}
+    out = S.AbsoluteActions(mask=[False, True])(item)
+    assert np.all(out["actions"] == np.array([[3, 6, 5], [5, 8, 7]]))
+    for cls in (S.DeltaActions, S.AbsoluteActions):
+        item = {"state": np.array([1, 2, 3]), "actions": np.array([[3, 4, 5], [5, 6, 7]])}
+        assert cls(mask=None)(item) is item
+        del item["actions"]
+        assert cls(mask=[True, False])(item) is item
+
+
+def test_make_bool_mask():  # transforms_test.py:70-72
+    assert S.make_bool_mask(2, -2, 2) == (True, True, False, False, True, True)
+    assert S.make_bool_mask(2, 0, 2) == (True, True, True, True)
+
+
+def test_tokenize_prompt():  # transforms_test.py:75-90
+    tok = S.PaligemmaTokenizer(max_len=12, model_path=MG.SPM)
+    data = S.TokenizePrompt(tok)({"prompt": "Hello, world!"})
+    t, m = tok.tokenize("Hello, world!")
+    assert np.allclose(t, data["tokenized_prompt"]) and np.allclose(m, data["tokenized_prompt_mask"])
+    assert len(t) == 12 and "prompt" not in data
+    with pytest.raises(ValueError, match="Prompt is required"):
+        S.TokenizePrompt(tok)({})
+    with pytest.raises(ValueError, match="State is required"):
+        S.TokenizePrompt(tok, discrete_state_input=True)({"prompt": "x"})
+    with pytest.raises(ValueError, match="exactly one"):
+        S.PaligemmaTokenizer(8)
+
+
+def test_pi05_prompt_carries_the_discretised_state():  # tokenizer.py:24-30
+    tok = S.PaligemmaTokenizer(max_len=200, model_path=MG.SPM)
+    import sentencepiece
+
+    sp = sentencepiece.SentencePieceProcessor(model_file=MG.SPM)
+    state = np.array([-1.0, -0.999, 0.0, 0.5, 0.9999, 1.0, 3.0])
+    ids, mask = tok.tokenize("pick_up the\ncup ", state)
+    text = sp.decode([int(i) for i in ids[mask]])
+    # 256 bins over [-1, 1): -1 -> 0, 0 -> 128, 0.5 -> 192, values >= 1 - 1/128 -> 255
+    # (this SentencePiece model strips the trailing blank of "Action: " when encoding)
+    assert text == "Task: pick up the cup, State: 0 0 128 192 255 255 255;\nAction:"
+    assert int(ids[0]) == sp.bos_id() and not mask[-1] and int(ids[-1]) == 0
+
+
+def test_running_stats():  # normalize_test.py:6-44
+    arr = np.arange(12).reshape(4, 3)
+    rs = S.RunningStats()
+    for i in range(len(arr)):
+        rs.update(arr[i: i + 1])
+    st = rs.get_statistics()
+    assert np.allclose(st.mean, arr.mean(0)) and np.allclose(st.std, arr.std(0))
+    arr = np.random.default_rng(0).random((2, 3, 4))
+    rs = S.RunningStats()
+    rs.update(arr)
+    st = rs.get_statistics()
+    assert np.allclose(st.mean, arr.reshape(-1, 4).mean(0)) and np.allclose(st.std, arr.reshape(-1, 4).std(0))
+    with pytest.raises(ValueError, match="less than 2"):
+        S.RunningStats().get_statistics()
+    with pytest.raises(ValueError, match="does not match"):
+        rs.update(np.zeros((2, 5)))
+
+
+def test_running_stats_equal_the_reference_bit_for_bit():
+    rs = S.RunningStats()
+    for b in MG.running_stats_batches():  # the second batch widens the range: histograms are re-binned
+        rs.update(b)
+    st = rs.get_statistics()
+    for f in ("mean", "std", "q01", "q99"):
+        _same(getattr(st, f), FIX[f"running/{f}"], f"running/{f}")
+
+
+# ------------------------------------------------------------------ norm_stats.json wire format
+def test_norm_stats_wire_format_is_the_references():
+    ref_json = FIX["norm_stats_json"].tobytes().decode()
+    stats = S.deserialize_json(ref_json)  # written by the reference's pydantic model
+    want = MG.norm_stats_arrays()
+    for k, rec in want.items():
+        for f, v in rec.items():
+            _same(getattr(stats[k], f), v, f"{k}.{f}")
+    assert stats["no_quantiles"].q01 is None and stats["no_quantiles"].q99 is None
+    # and what this module writes is, byte for byte, what the reference wrote
+    assert S.serialize_json(stats) == ref_json
+    with pytest.raises(ValueError):
+        S.deserialize_json(json.dumps({"norm_stats": {"state": {"mean": [0.0]}}}))
+
+
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_reference_reads_what_this_module_writes(tmp_path):
+    R = RSL.load()
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    S.save(tmp_path / "assets" / "agilex", stats)
+    back = R.normalize.load(tmp_path / "assets" / "agilex")
+    for k in stats:
+        for f in ("mean", "std", "q01", "q99"):
+            _same(getattr(back[k], f), getattr(stats[k], f), f"{k}.{f}")
+    R.normalize.save(tmp_path / "other", back)
+    again = S.load(tmp_path / "other")
+    assert (tmp_path / "other" / "norm_stats.json").read_text() == (tmp_path / "assets" / "agilex" / "norm_stats.json").read_text()
+    _same(again["state"].q99, stats["state"].q99, "round trip")
+    with pytest.raises(FileNotFoundError, match="Norm stats file not found"):
+        S.load(tmp_path / "missing")
+
+
+def test_normalize_edge_cases():
+    st = {"state": S.NormStats(mean=np.array([1.0, 2.0]), std=np.array([2.0, 4.0]))}
+    with pytest.raises(ValueError, match="missing q01 or q99"):
+        S.Normalize(st, use_quantiles=True)
+    with pytest.raises(ValueError, match="missing q01 or q99"):
+        S.Unnormalize(st, use_quantiles=True)
+    assert S.Normalize(None)({"state": 1}) == {"state": 1}
+    # statistics shorter than the leaf: z-score pads mean 0 / std 1, quantile passes the tail through (transforms.py:177-191)
+    x = {"state": np.array([3.0, 6.0, 5.0])}
+    out = S.Unnormalize(st)(dict(x))["state"]
+    assert np.allclose(out, [3 * (2 + 1e-6) + 1, 6 * (4 + 1e-6) + 2, 5 * (1 + 1e-6)])
+    stq = {"state": S.NormStats(mean=np.zeros(2), std=np.ones(2), q01=np.array([-1.0, 0.0]), q99=np.array([1.0, 4.0]))}
+    out = S.Unnormalize(stq, use_quantiles=True)(dict(x))["state"]
+    assert np.allclose(out, [(3 + 1) / 2 * (2 + 1e-6) - 1, (6 + 1) / 2 * (4 + 1e-6), 5.0])
+    with pytest.raises(ValueError, match="Selector key state not found"):
+        S.Unnormalize(st)({"actions": np.zeros(2)})
+    with pytest.raises(ValueError, match="Selector key state not found"):
+        S.Normalize(st, strict=True)({"actions": np.zeros(2)})
+    assert "actions" in S.Normalize(st)({"actions": np.zeros(2)})  # non-strict: untouched
+
+
+def test_agilex_inputs_errors_and_training_fields():
+    t = S.AgilexInputs(action_dim=32)
+    img = np.zeros((3, 8, 8), np.uint8)
+    good = {"images": {"top_head": img, "hand_left": img, "hand_right": img}, "state": np.zeros(14)}
+    with pytest.raises(ValueError, match="Expected images to contain"):
+        t({**good, "images": {**good["images"], "elbow": img}})
+    with pytest.raises(ValueError, match="Camera hand_right not found"):
+        t({**good, "images": {"top_head": img, "hand_left": img}})
+    out = t({**good, "actions": np.full((50, 14), 4.0), "progress": 0.5,
+             "images": {**good["images"], "his_-100_top_head": img}})
+    assert out["actions"].shape == (50, 32) and float(np.abs(out["actions"]).max()) == 0.0  # |x| > pi -> 0
+    assert "base_-100_rgb" in out["image"] and out["progress"] == 0.5 and "action_mask" not in out
+    assert S.AgilexInputs(action_dim=32, pi05=False)({**good, "actions": np.zeros((50, 14))})["action_mask"].all()
+    assert float(np.abs(S.AgilexInputs(action_dim=32, mask_state=True)({**good, "state": np.ones(14)})["state"]).max()) == 0
+
+
+# ------------------------------------------------------------------ Policy / batching (stub model on the CPU)
+class _StubModel:
+    """Stands in for PI0Pytorch on the CPU: a deterministic function of every input, so that routing mistakes show."""
+
+    def __init__(self):
+        self.calls = []
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def sample_actions(self, device, obs, noise=None, num_steps=10, **kw):
+        B = obs.state.shape[0]
+        self.calls.append({"B": B, "kw": {k: (v if not torch.is_tensor(v) else tuple(v.shape)) for k, v in kw.items()},
+                           "num_steps": num_steps, "img_dtype": obs.images["base_0_rgb"].dtype})
+        base = obs.state.to(torch.float32)[:, None, :].expand(B, MG.HORIZON, 32)
+        img = torch.stack([obs.images[k].to(torch.float32).mean(dim=(1, 2, 3)) for k in sorted(obs.images)], 1).sum(1)
+        tok = (obs.tokenized_prompt * obs.tokenized_prompt_mask).sum(1).to(torch.float32)
+        out = 0.1 * base + (img / 255.0)[:, None, None] + 1e-4 * tok[:, None, None]
+        out = out + torch.arange(MG.HORIZON)[None, :, None] * 0.01
+        if noise is not None:
+            out = out + noise
+        if "prev_action_chunk" in kw:
+            prev = torch.nn.functional.pad(kw["prev_action_chunk"], (0, 32 - kw["prev_action_chunk"].shape[-1]))
+            out = out + 0.5 * prev + kw.get("inference_delay", 0)
+        return out.to(torch.float32)
+
+
+def _policy(model=None, **kw):
+    tok = S.PaligemmaTokenizer(MG.MAX_TOKEN_LEN, model_path=MG.SPM)
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    ins, outs = S.agilex_pi05_transforms(action_dim=32, max_token_len=MG.MAX_TOKEN_LEN, tokenizer=tok, norm_stats=stats,
+                                         default_prompt=MG.DEFAULT_PROMPT, image_size=MG.IMAGE_SIZE)
+    model = model or _StubModel()
+    return S.Policy(model, transforms=ins, output_transforms=outs, pytorch_device="cpu", metadata={"robot": "agilex"}, **kw), model
+
+
+def test_policy_infer_is_the_reference_call_sequence():
+    """policy.py:68-124: copy -> input transforms -> batch of one -> from_dict -> sample_actions -> [0] -> output
+    transforms -> policy_timing; the caller's dict is left alone."""
+    pol, model = _policy()
+    req = MG.requests()[0]
+    keep = MG.copy_request(req)
+    out = pol.infer(req)
+    assert set(out) == {"actions", "policy_timing"} and out["actions"].shape == (MG.HORIZON, 14)
+    assert out["policy_timing"]["infer_ms"] >= 0 and pol.metadata == {"robot": "agilex"}
+    assert set(req) == set(keep) and all(np.array_equal(req["images"][c], keep["images"][c]) for c in keep["images"])
+    assert model.calls[0]["B"] == 1 and model.calls[0]["img_dtype"] == torch.uint8  # uint8 reaches the engine as is
+    # by hand
+    lib, tok, ns = _mine()
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    ins, outs = S.agilex_pi05_transforms(action_dim=32, max_token_len=MG.MAX_TOKEN_LEN, tokenizer=tok(MG.MAX_TOKEN_LEN),
+                                         norm_stats=stats, default_prompt=MG.DEFAULT_PROMPT, image_size=MG.IMAGE_SIZE)
+    x = S.compose(ins)(MG.copy_request(keep))
+    from kai0_b200.model import Observation
+
+    batch = {"image": {k: torch.from_numpy(v)[None] for k, v in x["image"].items()},
+             "image_mask": {k: torch.from_numpy(np.asarray(v))[None] for k, v in x["image_mask"].items()},
+             "state": torch.from_numpy(x["state"])[None], "tokenized_prompt": torch.from_numpy(x["tokenized_prompt"])[None],
+             "tokenized_prompt_mask": torch.from_numpy(x["tokenized_prompt_mask"])[None]}
+    acts = _StubModel().sample_actions("cpu", Observation.from_dict(batch, keep_uint8=True))[0].numpy()
+    want = S.compose(outs)({"state": x["state"], "actions": acts})
+    _same(out["actions"], want["actions"], "infer vs by hand")
+    # noise: [H, A] or [1, H, A] (policy.py:97-102)
+    nz = np.random.default_rng(1).normal(size=(MG.HORIZON, 32)).astype(np.float32)
+    a = pol.infer(req, noise=nz)["actions"]
+    b = pol.infer(req, noise=nz[None])["actions"]
+    _same(a, b, "noise rank")
+    assert not np.array_equal(a, out["actions"])
+
+
+def test_infer_batch_equals_one_by_one_and_groups_rtc_requests():
+    pol, model = _policy()
+    reqs = MG.requests()
+    single = [pol.infer(r)["actions"] for r in reqs]
+    model.calls.clear()
+    batched = pol.infer_batch(reqs)
+    assert len(model.calls) == 1 and model.calls[0]["B"] == 3  # ONE model call
+    for i in range(3):
+        _same(batched[i]["actions"], single[i], f"request {i}")
+        assert batched[i]["policy_timing"]["batch"] == 3
+    # real-time-chunking keys travel as sample_actions kwargs (policy.py:84-90); requests with different scalar settings
+    # cannot share a call
+    prev = np.random.default_rng(2).normal(size=(MG.HORIZON, 14)).astype(np.float32)
+    r = [dict(reqs[0], prev_action_chunk=prev, inference_delay=3, execute_horizon=25),
+         dict(reqs[1]),
+         dict(reqs[2], prev_action_chunk=2 * prev, inference_delay=3, execute_horizon=25),
+         dict(reqs[0], prev_action_chunk=prev, inference_delay=5, execute_horizon=25)]
+    model.calls.clear()
+    out = pol.infer_batch(r)
+    assert sorted(c["B"] for c in model.calls) == [1, 1, 2]
+    two = next(c for c in model.calls if c["B"] == 2)
+    assert two["kw"]["prev_action_chunk"] == (2, MG.HORIZON, 14) and two["kw"]["inference_delay"] == 3
+    _same(out[1]["actions"], single[1], "plain request inside a mixed batch")
+    alone = pol.infer(r[2])["actions"]
+    _same(out[2]["actions"], alone, "rtc request batched vs alone")
+    assert pol.infer_batch([]) == []
+    with pytest.raises(ValueError, match="one entry"):
+        pol.infer_batch(reqs, noise=[None])
+
+
+def test_staging_blocks_are_reused_and_grow():
+    st = S._Staging("cpu")
+    a = st.put("x", [np.arange(4, dtype=np.float32), np.arange(4, dtype=np.float32) + 1])
+    blk = st._blocks["x"]
+    b = st.put("x", [np.ones(4, dtype=np.float32)])
+    assert st._blocks["x"] is blk and tuple(b.shape) == (1, 4) and tuple(a.shape) == (2, 4)
+    assert float(a[1, 0]) == 1.0  # earlier result is its own tensor
+    st.put("x", [np.zeros(4, dtype=np.float32)] * 5)
+    assert st._blocks["x"].shape[0] == 5
+    assert st.put("m", [np.True_, np.False_]).dtype == torch.bool
+    with pytest.raises(ValueError, match="agree in shape"):
+        st.put("x", [np.zeros(4, np.float32), np.zeros(3, np.float32)])
+
+
+def test_request_batcher_serves_concurrent_clients_in_shared_calls():
+    pol, model = _policy()
+    reqs = MG.requests()
+    single = [pol.infer(r)["actions"] for r in reqs]
+    model.calls.clear()
+    results = {}
+    with S.RequestBatcher(pol, max_batch=4, max_wait_ms=200.0) as rb:
+        assert rb.metadata == {"robot": "agilex"}
+
+        def client(i):
+            results[i] = rb.infer(reqs[i % 3])["actions"]
+
+        ts = [threading.Thread(target=client, args=(i,)) for i in range(8)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=60)
+        assert len(results) == 8
+        for i in range(8):
+            _same(results[i], single[i % 3], f"client {i}")  # every client got ITS reply
+        assert rb.requests_served == 8 and rb.batches_served <= 4  # 8 requests, at most 4 per call, within 200 ms
+        assert max(c["B"] for c in model.calls) <= 4
+        # a bad request fails alone
+        bad = dict(reqs[0], images={"top_head": reqs[0]["images"]["top_head"]})
+        f_bad, f_ok = rb.submit(bad), rb.submit(reqs[1])
+        with pytest.raises(ValueError, match="not found"):
+            f_bad.result(timeout=60)
+        _same(f_ok.result(timeout=60)["actions"], single[1], "neighbour of a bad request")
+    with pytest.raises(RuntimeError, match="closed"):
+        rb.submit(reqs[0])
+    with pytest.raises(ValueError):
+        S.RequestBatcher(pol, max_batch=0)
+
+
+# ------------------------------------------------------------------ checkpoint directory
+def test_parameters_are_registered_in_the_references_order():
+    """optimizer.pt keys its state by position in model.parameters() (train_pytorch.py:170,236-243)."""
+    import reference_pin as PIN
+    from kai0_b200.pi0_pytorch import AdvantageEstimator, GemmaVariant, PI0Pytorch, Pi05EngineConfig
+
+    want = json.load(open(os.path.join(GOLD, "reference_param_order.json")))
+    cfg = Pi05EngineConfig(paligemma_variant=GemmaVariant(*PIN.PG), action_expert_variant=GemmaVariant(*PIN.EX),
+                           vit_depth=PIN.VIT_LAYERS, max_token_len=PIN.MAX_TOKEN_LEN, vocab_size=1024)
+    for cls in (PI0Pytorch, AdvantageEstimator):
+        m = cls(cfg, init_weights=False)
+        assert [n for n, _ in m.named_parameters()] == want[cls.__name__]
+        # the arenas keep their own layout: the never-trained expert lm_head stays last in the bf16 arena
+        last = max((v for v in m._offsets.values() if v[0] == torch.bfloat16), key=lambda v: v[1])
+        assert last is m._offsets["paligemma_with_expert.gemma_expert.lm_head.weight"]
+
+
+def test_checkpoint_directory_round_trip(tmp_path):
+    """train_pytorch.py:149-273: <dir>/<step>/{model.safetensors, optimizer.pt, metadata.pt, assets/<id>/norm_stats.json}."""
+    oc = O.tiny_config()
+    model, _ = H.build_pair(oc, device=None)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+    g = torch.Generator().manual_seed(0)
+    for p in model.parameters():
+        p.grad = torch.randn(p.shape, generator=g).to(p.dtype)
+    opt.step()
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    assert CK.get_latest_checkpoint_step(tmp_path / "nothing") is None
+    assert CK.save_checkpoint(model, opt, 10, tmp_path, is_main=False) is None and not os.listdir(tmp_path)
+    CK.save_checkpoint(model, opt, 10, tmp_path, norm_stats=stats, asset_id="agilex", config={"name": "pi05_test"})
+    os.makedirs(tmp_path / "tmp_30")  # a crashed save must not be mistaken for a step
+    final = CK.save_checkpoint(model, opt, 20, tmp_path, norm_stats=stats, asset_id="agilex")
+    assert sorted(os.listdir(final)) == ["assets", "metadata.pt", "model.safetensors", "optimizer.pt"]
+    assert os.path.exists(os.path.join(final, "assets", "agilex", "norm_stats.json"))
+    assert CK.get_latest_checkpoint_step(tmp_path) == 20
+    meta = torch.load(tmp_path / "10" / "metadata.pt", weights_only=False)
+    assert meta["global_step"] == 10 and meta["config"] == {"name": "pi05_test"} and "timestamp" in meta
+
+    model2, _ = H.build_pair(oc, seed=1, device=None)
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+    assert CK.load_checkpoint(model2, opt2, tmp_path, "cpu") == 20
+    for (n, a), (_, b) in zip(model.named_parameters(), model2.named_parameters()):
+        assert torch.equal(a, b), n
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert s1.keys() == s2.keys()
+    for k in s1:
+        assert torch.equal(s1[k]["exp_avg"], s2[k]["exp_avg"]) and torch.equal(s1[k]["exp_avg_sq"], s2[k]["exp_avg_sq"])
+    back = CK.load_norm_stats(tmp_path, "agilex")
+    _same(back["actions"].q01, stats["actions"].q01, "norm stats from the checkpoint")
+    _same(CK.load_norm_stats(final, "agilex")["state"].mean, stats["state"].mean, "step directory given directly")
+    with pytest.raises(FileNotFoundError):
+        CK.load_checkpoint(model2, opt2, tmp_path / "nothing", "cpu")
+
+
+def test_fused_optimizer_state_interchanges_with_stock_adamw():
+    """`FusedClipAdamW.state_dict(format="torch")` is what torch.optim.AdamW over model.parameters() would hold, and a
+    stock optimizer.pt loads into the fused optimiser (moments land in the right arena slices)."""
+    from kai0_b200.optim import FusedClipAdamW
+
+    oc = O.tiny_config()
+    model, _ = H.build_pair(oc, device=None)
+    stock = torch.optim.AdamW(model.parameters(), lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+    g = torch.Generator().manual_seed(3)
+    named = dict(model.named_parameters())
+    dead = set(model._dead_grad_names) | {"paligemma_with_expert.gemma_expert.lm_head.weight"}
+    for n, p in named.items():  # the reference's autograd leaves these without a gradient: no optimiser state
+        p.grad = None if n in dead else torch.randn(p.shape, generator=g).to(p.dtype)
+    stock.step()
+    stock.step()
+    sd = stock.state_dict()
+    fused = FusedClipAdamW(model, lr=1.0)
+    fused.load_state_dict(sd)
+    assert fused.step_count == 2 and fused.param_groups[0]["lr"] == 3e-4 and fused.param_groups[0]["max_norm"] == 1.0
+    names = [n for n, _ in model.named_parameters()]
+    for i, rec in sd["state"].items():
+        dt, off, n, shape = model._offsets[names[i]]
+        arena = 0 if dt == torch.bfloat16 else 1
+        assert torch.equal(fused.m[arena][off:off + n].view(shape), rec["exp_avg"]), names[i]
+        assert torch.equal(fused.v[arena][off:off + n].view(shape), rec["exp_avg_sq"]), names[i]
+    # everything outside the loaded slices is zero (alignment gaps, parameters without state)
+    total = sum(float(rec["exp_avg"].float().abs().sum()) for rec in sd["state"].values())
+    assert abs(sum(float(m.float().abs().sum()) for m in fused.m) - total) <= 1e-3 * total
+    # and back: the exported record loads into a fresh stock optimiser and equals the original
+    out = fused.state_dict(format="torch")
+    assert out["state"].keys() == sd["state"].keys()
+    assert out["param_groups"][0]["params"] == sd["param_groups"][0]["params"]
+    assert {k: v for k, v in out["param_groups"][0].items() if k != "params"} == \
+        {k: v for k, v in sd["param_groups"][0].items() if k != "params"}
+    fresh = torch.optim.AdamW(model.parameters(), lr=1.0)
+    fresh.load_state_dict(out)
+    s2 = fresh.state_dict()["state"]
+    for k, rec in sd["state"].items():
+        assert torch.equal(s2[k]["exp_avg"], rec["exp_avg"]) and float(s2[k]["step"]) == 2.0
+    # the compact layout still round-trips
+    flat = fused.state_dict()
+    other = FusedClipAdamW(model)
+    other.load_state_dict(flat)
+    assert other.step_count == 2 and torch.equal(other.m[0], fused.m[0]) and torch.equal(other.v[1], fused.v[1])
+    # a record that cannot be represented is refused
+    bad = {"state": {**sd["state"], 0: {**sd["state"][0], "step": torch.tensor(5.0)}}, "param_groups": sd["param_groups"]}
+    with pytest.raises(ValueError, match="step counts differ"):
+        fused.load_state_dict(bad)
+    dead_idx = names.index(next(iter(model._dead_grad_names)))
+    bad = {"state": {dead_idx: sd["state"][0]}, "param_groups": sd["param_groups"]}
+    with pytest.raises(ValueError, match="does not update"):
+        fused.load_state_dict(bad)
+    assert FusedClipAdamW(model).state_dict(format="torch")["state"] == {}  # no step taken yet: no state, like torch

@@ -1,0 +1,187 @@
+"""Execute the REFERENCE'S OWN serving-side host code in place (test infrastructure; needs /root/reference).
+
+Loads, from where they lie, `openpi/shared/normalize.py`, `openpi/transforms.py`, `openpi/models/tokenizer.py`,
+`openpi/policies/agilex_policy.py` and `packages/openpi-client/src/openpi_client/image_tools.py`, so that
+tests/test_serving_cpu.py and tools/make_golden_serving.py can pin kai0_b200/serving.py to the reference itself.
+Nothing is copied.  Third-party modules those files import that this image lacks are replaced by the smallest stand-in
+that reproduces the behaviour the files use (pinned versions from the reference's uv.lock):
+
+  flax 0.10.2  `traverse_util.flatten_dict(tree, sep=)/unflatten_dict(flat, sep=)`: depth-first walk over nested dicts,
+               keys joined with `sep`, empty sub-dicts dropped (keep_empty_nodes=False); inverse splits on `sep`.
+  jax          only `jax.tree.map(fn, tree)` over nested dicts of leaves.
+  numpydantic 1.6.9  `NDArray` as a pydantic field type: validates to `np.ndarray`, JSON-serialises as nested lists.
+  orbax, transformers.AutoProcessor, fsq_tokenizer: imported by tokenizer.py for classes this path never touches.
+  openpi.shared.download.maybe_download: returns the SentencePiece model path registered with `set_tokenizer_model`
+               (the reference fetches gs://big_vision/paligemma_tokenizer.model; no egress here).
+  openpi.models.model: only the `ModelType` enum (models/model.py:30-37); the real module imports jax/flax/orbax.
+"""
+from __future__ import annotations
+
+import enum
+import importlib.util
+import os
+import pathlib
+import sys
+import types
+import typing
+
+import numpy as np
+
+REPO = "/root/reference"
+SRC = os.path.join(REPO, "src", "openpi")
+CLIENT = os.path.join(REPO, "packages", "openpi-client", "src", "openpi_client")
+_loaded = None
+_tokenizer_model: dict = {"path": None}
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(SRC, "transforms.py")) and os.path.isfile(os.path.join(CLIENT, "image_tools.py"))
+
+
+def set_tokenizer_model(path: str) -> None:
+    _tokenizer_model["path"] = path
+
+
+def _exec_as(name: str, path: str):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _module(name: str, **attrs):
+    """Create the module unless a real/stub one is already registered; attributes are added either way when missing."""
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    for k, v in attrs.items():
+        if not hasattr(m, k):
+            setattr(m, k, v)
+    return m
+
+
+def _flatten(tree, sep="/", **_):
+    out = {}
+
+    def walk(node, prefix):
+        for k, v in node.items():
+            p = (*prefix, k)
+            if isinstance(v, dict):
+                walk(v, p)
+            else:
+                out[sep.join(p) if sep is not None else p] = v
+
+    walk(tree, ())
+    return out
+
+
+def _unflatten(flat, sep="/"):
+    root = {}
+    for path, v in flat.items():
+        parts = path.split(sep) if sep is not None else path
+        node = root
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = v
+    return root
+
+
+def _tree_map(fn, tree, *rest):
+    if isinstance(tree, dict):
+        return {k: _tree_map(fn, v, *(r[k] for r in rest)) for k, v in tree.items()}
+    return fn(tree, *rest)
+
+
+class _Anything:
+    def __getattr__(self, name):
+        return _Anything()
+
+    def __getitem__(self, item):
+        return self
+
+    def __or__(self, other):
+        return self
+
+    def __ror__(self, other):
+        return self
+
+    def __call__(self, *a, **k):
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]
+        return _Anything()
+
+
+class ModelType(enum.Enum):  # models/model.py:30-37 (values only)
+    PI0 = "pi0"
+    PI0_FAST = "pi0_fast"
+    PI05 = "pi05"
+    PI0_RTC = "pi0_rtc"
+    PI05_RTC = "pi05_rtc"
+
+
+def load():
+    """Returns a namespace with the reference's modules: .normalize, .transforms, .tokenizer, .agilex_policy,
+    .image_tools, .ModelType."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    import pydantic
+
+    # third-party stand-ins
+    nd = _module("numpydantic")
+    if not hasattr(nd, "NDArray"):
+        nd.NDArray = typing.Annotated[
+            typing.Any,
+            pydantic.BeforeValidator(lambda v: v if v is None else np.asarray(v)),
+            pydantic.PlainSerializer(lambda a: None if a is None else np.asarray(a).tolist(), when_used="json"),
+        ]
+    tu = _module("flax.traverse_util", flatten_dict=_flatten, unflatten_dict=_unflatten)
+    fl = _module("flax", traverse_util=tu)
+    fl.__path__ = getattr(fl, "__path__", [])
+    jx = _module("jax")
+    if not hasattr(jx, "tree"):
+        jx.tree = types.SimpleNamespace(map=_tree_map)
+    _module("orbax").__path__ = []
+    _module("orbax.checkpoint")
+    sys.modules["orbax"].checkpoint = sys.modules["orbax.checkpoint"]
+    oc = _module("openpi_client")
+    oc.__path__ = getattr(oc, "__path__", [])
+    oc.image_tools = _exec_as("openpi_client.image_tools", os.path.join(CLIENT, "image_tools.py"))
+
+    # openpi package skeleton (tools/reference_loader.py may have created parts of it already)
+    op = _module("openpi")
+    op.__path__ = getattr(op, "__path__", [])
+    sh = _module("openpi.shared")
+    sh.__path__ = getattr(sh, "__path__", [])
+    op.shared = sh
+    at = _module("openpi.shared.array_typing", typecheck=lambda f: f, PyTree=_Anything(), UInt8=_Anything(),
+                 Float=_Anything(), Array=_Anything())
+    if not hasattr(at, "PyTree"):
+        at.PyTree = _Anything()
+    sh.array_typing = at
+    dl = _module("openpi.shared.download")
+    dl.maybe_download = lambda url, **kw: pathlib.Path(_tokenizer_model["path"]) if str(url).endswith(
+        "paligemma_tokenizer.model") else pathlib.Path(str(url))
+    sh.download = dl
+    sh.normalize = _exec_as("openpi.shared.normalize", os.path.join(SRC, "shared", "normalize.py"))
+    md = _module("openpi.models")
+    md.__path__ = getattr(md, "__path__", [])
+    op.models = md
+    ut = _module("openpi.models.utils")
+    ut.__path__ = getattr(ut, "__path__", [])
+    md.utils = ut
+    ut.fsq_tokenizer = _module("openpi.models.utils.fsq_tokenizer")
+    mm = _module("openpi.models.model", ModelType=ModelType)
+    md.model = mm
+    md.tokenizer = _exec_as("openpi.models.tokenizer", os.path.join(SRC, "models", "tokenizer.py"))
+    op.transforms = _exec_as("openpi.transforms", os.path.join(SRC, "transforms.py"))
+    po = _module("openpi.policies")
+    po.__path__ = getattr(po, "__path__", [])
+    op.policies = po
+    po.agilex_policy = _exec_as("openpi.policies.agilex_policy", os.path.join(SRC, "policies", "agilex_policy.py"))
+    _loaded = types.SimpleNamespace(normalize=sh.normalize, transforms=op.transforms, tokenizer=md.tokenizer,
+                                    agilex_policy=po.agilex_policy, image_tools=oc.image_tools,
+                                    ModelType=getattr(mm, "ModelType", ModelType))
+    return _loaded
