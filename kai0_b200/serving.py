@@ -601,9 +601,15 @@ class Policy:
 
     def __init__(self, model, *, transforms: Sequence[Callable] = (), output_transforms: Sequence[Callable] = (),
                  sample_kwargs: dict | None = None, metadata: dict | None = None, pytorch_device: str = "cuda",
-                 keep_uint8: bool = True):
+                 keep_uint8: bool = True, max_batch: int | None = None):
         self._model = model.to(pytorch_device)
         self._model.eval()
+        # max_batch: the largest number of requests one model call may carry.  The engine plans its inference workspace
+        # for that batch up front (instead of re-planning the first time a larger batch shows up) and longer request
+        # lists are served in slices of this size.
+        self._max_batch = int(max_batch) if max_batch else None
+        if self._max_batch and hasattr(model, "_max_batch_hint"):
+            model._max_batch_hint = max(int(model._max_batch_hint or 0), self._max_batch)
         self._input_transform = compose(transforms)
         self._output_transform = compose(output_transforms)
         self._sample_kwargs = dict(sample_kwargs or {})
@@ -633,11 +639,14 @@ class Policy:
             groups.setdefault(key, []).append(i)
         results: list = [None] * len(observations)
         with self._lock:
-            for idx in groups.values():
-                outs = self._run_group([observations[i] for i in idx], [prepared[i] for i in idx],
-                                       None if noise is None else [noise[i] for i in idx])
-                for i, o in zip(idx, outs):
-                    results[i] = o
+            for members in groups.values():
+                step = self._max_batch or len(members)
+                for lo in range(0, len(members), step):
+                    idx = members[lo:lo + step]
+                    outs = self._run_group([observations[i] for i in idx], [prepared[i] for i in idx],
+                                           None if noise is None else [noise[i] for i in idx])
+                    for i, o in zip(idx, outs):
+                        results[i] = o
         return results
 
     def _run_group(self, raw, prepared, noise):
@@ -688,6 +697,8 @@ class RequestBatcher:
     def __init__(self, policy: Policy, *, max_batch: int = 8, max_wait_ms: float = 2.0):
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
+        if getattr(policy, "_max_batch", None):
+            max_batch = min(max_batch, policy._max_batch)
         self._policy = policy
         self._max_batch = int(max_batch)
         self._max_wait = float(max_wait_ms) / 1e3

@@ -334,6 +334,16 @@ def test_infer_batch_equals_one_by_one_and_groups_rtc_requests():
     alone = pol.infer(r[2])["actions"]
     _same(out[2]["actions"], alone, "rtc request batched vs alone")
     assert pol.infer_batch([]) == []
+    # max_batch: longer request lists are served in slices, and the engine is told to plan for that batch up front
+    m2 = _StubModel()
+    m2._max_batch_hint = None
+    pol2, _ = _policy(m2, max_batch=2)
+    model_calls = m2.calls
+    out = pol2.infer_batch(reqs)
+    assert [c["B"] for c in model_calls] == [2, 1] and m2._max_batch_hint == 2
+    for i in range(3):
+        _same(out[i]["actions"], single[i], f"sliced batch, request {i}")
+    assert S.RequestBatcher(pol2, max_batch=16)._max_batch == 2
     with pytest.raises(ValueError, match="one entry"):
         pol.infer_batch(reqs, noise=[None])
 
