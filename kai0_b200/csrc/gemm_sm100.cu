@@ -364,6 +364,10 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int major, long long rows, lon
     return false;
   }
   std::lock_guard<std::mutex> g(tmap_mutex());
+  // A descriptor is a pure function of its key (pointer + geometry), so entries never go stale; the bound only keeps a
+  // process that streams ever-new buffers through pi05_gemm from growing the map without limit (callers hold copies,
+  // never references, so dropping everything is safe).
+  if (tmap_cache().size() >= (1u << 16)) tmap_cache().clear();
   tmap_cache()[key] = *out;
   return true;
 }
