@@ -273,6 +273,21 @@ class InjectDefaultPrompt:
         return data
 
 
+@dataclasses.dataclass(frozen=True)
+class InsertAdvantageIntoPrompt:
+    """transforms.py:113-121 (AWBC, BASELINE.json configs[4]): the advantage label becomes part of the prompt text,
+    `<prompt>, Advantage: <a with 4 decimals>`; first input transform when the data config asks for it
+    (training/config.py:431-432)."""
+
+    def __call__(self, data):
+        if "advantage" not in data:
+            raise AssertionError(f"advantage is not in data, data_keys: {data.keys()}")
+        if "prompt" not in data:
+            raise AssertionError(f"prompt is not in data, data_keys: {data.keys()}")
+        data["prompt"] = data["prompt"] + f", Advantage: {data['advantage']:.4f}"
+        return data
+
+
 def _require_quantiles(norm_stats) -> None:
     for path, s in flatten_dict(norm_stats).items():
         if s.q01 is None or s.q99 is None:
@@ -791,11 +806,14 @@ class RequestBatcher:
 
 def agilex_pi05_transforms(*, action_dim: int, max_token_len: int, tokenizer, norm_stats, default_prompt: str | None = None,
                            use_delta_joint_actions: bool = True, image_size: int = 224, mask_state: bool = False,
-                           use_quantile_norm: bool = True, repack: Group | None = None):
+                           use_quantile_norm: bool = True, repack: Group | None = None,
+                           insert_advantage_into_prompt: bool = False):
     """The transform chain `create_trained_policy` assembles for a pi0.5 Agilex config (policy_config.py:75-90 over
     training/config.py:129-141,420-452): returns (input transforms, output transforms)."""
     repack = repack or Group()
     data = Group(inputs=[AgilexInputs(action_dim=action_dim, pi05=True, mask_state=mask_state)], outputs=[AgilexOutputs()])
+    if insert_advantage_into_prompt:  # training/config.py:431-432 (AWBC prompts)
+        data = Group(inputs=[InsertAdvantageIntoPrompt(), *data.inputs], outputs=data.outputs)
     if use_delta_joint_actions:
         m = make_bool_mask(6, -1, 6, -1)  # joints relative to the state, the two grippers absolute
         data = data.push(inputs=[DeltaActions(m)], outputs=[AbsoluteActions(m)])

@@ -106,6 +106,22 @@ def test_delta_and_absolute_actions():  # transforms_test.py:20-67
         assert cls(mask=[True, False])(item) is item
 
 
+def test_insert_advantage_into_prompt_is_the_awbc_prompt_format():  # transforms.py:113-121
+    out = S.InsertAdvantageIntoPrompt()({"prompt": "fold the cloth", "advantage": 0.123456})
+    assert out["prompt"] == "fold the cloth, Advantage: 0.1235"
+    with pytest.raises(AssertionError, match="advantage is not in data"):
+        S.InsertAdvantageIntoPrompt()({"prompt": "x"})
+    if RSL.available():
+        R = RSL.load()
+        for adv in (0.0, -1.0, 0.99995, np.float32(0.3)):
+            a = S.InsertAdvantageIntoPrompt()({"prompt": "p", "advantage": adv})["prompt"]
+            assert a == R.transforms.InsertAdvantageIntoPrompt()({"prompt": "p", "advantage": adv})["prompt"]
+    # first in the chain when the data config asks for it (training/config.py:431-432)
+    ins, _ = S.agilex_pi05_transforms(action_dim=32, max_token_len=8, tokenizer=None, norm_stats=None,
+                                      insert_advantage_into_prompt=True)
+    assert isinstance(ins[1], S.InsertAdvantageIntoPrompt) and isinstance(ins[2], S.AgilexInputs)
+
+
 def test_make_bool_mask():  # transforms_test.py:70-72
     assert S.make_bool_mask(2, -2, 2) == (True, True, False, False, True, True)
     assert S.make_bool_mask(2, 0, 2) == (True, True, True, True)
