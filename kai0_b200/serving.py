@@ -575,6 +575,14 @@ def _copy_structure(tree):
     return _tree_map_leaves(lambda x: x, tree)
 
 
+class _NullContext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class _Staging:
     """Pinned host blocks, one per field, reused across calls: a request batch is written into them with numpy and leaves
     for the device as ONE asynchronous copy per field (the reference issues a pageable, blocking copy per leaf)."""
@@ -653,7 +661,10 @@ class Policy:
             key += ("prev_action_chunk" in o, None if noise is None else noise[i] is not None)
             groups.setdefault(key, []).append(i)
         results: list = [None] * len(observations)
-        with self._lock:
+        # a server thread that never touched CUDA starts on device 0: make the engine's device current for the call
+        dev = torch.device(self._device)
+        on_dev = torch.cuda.device(dev) if dev.type == "cuda" and dev.index is not None else _NullContext()
+        with self._lock, on_dev:
             for members in groups.values():
                 step = self._max_batch or len(members)
                 for lo in range(0, len(members), step):
