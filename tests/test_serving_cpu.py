@@ -466,6 +466,32 @@ def test_checkpoint_directory_round_trip(tmp_path):
         CK.load_checkpoint(model2, opt2, tmp_path / "nothing", "cpu")
 
 
+def test_model_safetensors_loads_whichever_tied_name_the_file_carries(tmp_path):
+    """safetensors.save_model keeps ONE name of the tied embed_tokens / lm_head pair (train_pytorch.py:167); a file written
+    by either side, with either name, must restore the shared table."""
+    import safetensors.torch
+    from safetensors import safe_open
+
+    E = "paligemma_with_expert.paligemma.model.language_model.embed_tokens.weight"
+    L = "paligemma_with_expert.paligemma.lm_head.weight"
+    oc = O.tiny_config()
+    model, _ = H.build_pair(oc, device=None)
+    sd = model.state_dict()
+    safetensors.torch.save_model(model, str(tmp_path / "ours.safetensors"))
+    with safe_open(str(tmp_path / "ours.safetensors"), "pt") as f:
+        keys = set(f.keys())
+    assert (E in keys) != (L in keys) and len(keys) == len(sd) - 1
+    for drop in (E, L):
+        path = str(tmp_path / f"without_{drop.split('.')[-2]}.safetensors")
+        safetensors.torch.save_file({k: v.contiguous() for k, v in sd.items() if k != drop}, path)
+        other, _ = H.build_pair(oc, seed=9, device=None)
+        missing, unexpected = safetensors.torch.load_model(other, path)
+        assert not missing and not unexpected
+        named = dict(other.named_parameters())
+        assert torch.equal(named[E], sd[E])
+        assert other.paligemma_with_expert.paligemma.lm_head.weight is named[E]  # still ONE parameter
+
+
 def test_fused_optimizer_state_interchanges_with_stock_adamw():
     """`FusedClipAdamW.state_dict(format="torch")` is what torch.optim.AdamW over model.parameters() would hold, and a
     stock optimizer.pt loads into the fused optimiser (moments land in the right arena slices)."""
