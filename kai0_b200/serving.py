@@ -657,7 +657,7 @@ class Policy:
         prepared = [self._input_transform(_copy_structure(o)) for o in observations]
         groups: dict = {}
         for i, o in enumerate(observations):
-            key = tuple((k, None if k not in o or k == "prev_action_chunk" else int(o[k])) for k in _RTC_KEYS)
+            key = tuple((k, None if k not in o or k == "prev_action_chunk" or o[k] is None else int(o[k])) for k in _RTC_KEYS)
             key += ("prev_action_chunk" in o, None if noise is None else noise[i] is not None)
             groups.setdefault(key, []).append(i)
         results: list = [None] * len(observations)
