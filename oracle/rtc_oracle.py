@@ -1,5 +1,5 @@
-"""CPU restatement of the reference's real-time-chunking (RTC) guided decoding — TEST INFRASTRUCTURE ONLY, prepared for
-SURVEY.md §8 row f4 (not built in the engine yet; imported by tests/ only, never by the product).
+"""CPU restatement of the reference's real-time-chunking (RTC) guided decoding — TEST INFRASTRUCTURE ONLY (SURVEY.md §8
+row f4; imported by tests/ only, never by the product).
 
 The reference implements RTC only in its JAX model (src/openpi/models/pi0_rtc.py, "R:" below): `get_prefix_weights`
 R:47-61 and the guided Euler loop of `Pi0RTC.sample_actions` R:234-360.  This file restates that algorithm in plain torch
@@ -7,8 +7,15 @@ on top of the PyTorch-path network of oracle/pi05_oracle.py (prefill + KV-cache 
 asks for ("RTC guided decoding for the PyTorch path").  The vector-Jacobian product of R:331 (`jax.vjp(denoiser, x)`)
 is torch.autograd through the oracle's denoise step.
 
-PARITY UNPINNED: the JAX reference cannot run here (no jax) and ships no golden vector for RTC; the tests check
-known answers of the weight schedules, reduction to the unguided sampler, and properties of the guidance.
+PARITY PINNED to the reference's own sampler code: jax is not installed here, but tools/reference_rtc_loader.py executes
+pi0_rtc.py UNMODIFIED with `jax.numpy` mapped onto torch and the four flax sub-networks replaced by the PyTorch-path
+oracle network (itself pinned to the reference's PyTorch model), so `Pi0RTC.embed_prefix`, `make_attn_mask`, the KV-cache
+protocol, the scan and the whole guidance computation run as the reference wrote them.  On twelve seeded settings
+(schedules, delays, delay masking, 7 / 14 / 36-dim and NaN-carrying previous chunks, clipped arguments, 5 steps, RTC off)
+this file reproduces that run BIT FOR BIT in float32 (`tests/test_rtc_oracle_cpu.py`; outputs committed by
+tools/make_golden_rtc.py as tests/golden/rtc_reference.pt).  With the JAX-side `embed_suffix` left in place (its sincos
+embedding is float32, the PyTorch path's float64) the two differ by <= 7.4e-6 on O(5) values.  What stays unpinned is
+JAX's own network arithmetic (XLA dots), which the PyTorch path never matched bit for bit either.
 """
 from __future__ import annotations
 

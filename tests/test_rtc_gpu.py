@@ -1,7 +1,7 @@
 """Real-time-chunking guided decoding on the engine (pi05_denoise_rtc behind
 `PI0Pytorch.sample_actions(..., prev_action_chunk=...)`) against oracle/rtc_oracle.py, which restates
-src/openpi/models/pi0_rtc.py:234-360 on the PyTorch-path network (parity unpinned against JAX: the reference's RTC cannot run
-here; the oracle's VJP is pinned by finite differences in tests/test_rtc_oracle_cpu.py).
+src/openpi/models/pi0_rtc.py:234-360 on the PyTorch-path network and is pinned bit for bit to that file's own sampler executed
+in place (tools/reference_rtc_loader.py; tests/test_rtc_oracle_cpu.py, which also pins the VJP by finite differences).
 
 Tolerances: the velocity of a step is the ordinary decode step (<= 1e-3 on the action chunk, as tests/test_engine_gpu.py);
 the vector-Jacobian product is a bf16 backward through 2 x depth layers (1-3 % per tensor, as the training gradients); it

@@ -1,15 +1,84 @@
 """CPU checks of oracle/rtc_oracle.py (the engine side is tests/test_rtc_gpu.py).
-PARITY UNPINNED AGAINST JAX: the reference's RTC exists only in its JAX model (models/pi0_rtc.py) and cannot run here —
-these tests pin the restatement to known answers of the schedules, to properties of the guided sampler, and pin the
-vector-Jacobian product it relies on with central finite differences of the PyTorch-path denoise step in float32."""
+
+PINNED to the reference's own sampler: `Pi0RTC.sample_actions` of models/pi0_rtc.py is executed in place by
+tools/reference_rtc_loader.py (jax.numpy mapped onto torch, the flax sub-networks replaced by the PyTorch-path oracle
+network) -- live when /root/reference is present, and through the outputs committed in tests/golden/rtc_reference.pt.
+Further: known answers of the schedules, properties of the guided sampler, and the vector-Jacobian product against
+central finite differences of the PyTorch-path denoise step in float32."""
 import math
 
 import pytest
 import torch
 
+import os
+import sys
+
 import helpers as H  # noqa: F401
 from oracle import pi05_oracle as O
 from oracle import rtc_oracle as R
+
+sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+import make_golden_rtc as MGR  # noqa: E402
+import reference_rtc_loader as RRL  # noqa: E402
+
+GOLD_RTC = os.path.join(os.path.dirname(__file__), "golden", "rtc_reference.pt")
+
+
+def _oracle_run(oc, p, b, kw):
+    return R.sample_actions_rtc(p, oc, b["images"], b["img_masks"], b["tokens"], b["token_mask"], b["noise"], **kw)
+
+
+def test_oracle_reproduces_the_references_own_sampler_outputs():
+    """tests/golden/rtc_reference.pt: what pi0_rtc.py's `Pi0RTC.sample_actions` returned (tools/make_golden_rtc.py).
+    Same arithmetic on another CPU may group float32 sums differently, hence 2e-5 instead of equality (the live test
+    below asserts equality on the machine that runs both)."""
+    gold = torch.load(GOLD_RTC)
+    oc, p, b, plain, prev = MGR.setup("float32")
+    assert H.rel_err(plain, gold["plain"]) < 2e-5
+    worst = 0.0
+    for name, kw in MGR.cases(prev).items():
+        got = _oracle_run(oc, p, b, kw)
+        e = H.rel_err(got, gold[name])
+        worst = max(worst, e)
+        assert e < 2e-5, (name, e)
+        # the JAX-side suffix embedding (float32 sincos) instead of the PyTorch path's (float64): same answer to 1e-5
+        assert H.rel_err(got, gold[name + "/jax_suffix_embedding"]) < 1e-5, name
+        guided = name not in ("rtc_disabled", "no_previous_chunk")
+        assert (H.rel_err(got, plain) > 0.05) == guided, name  # the guidance really moves the chunk (7 .. 24 %)
+    print(f"rtc oracle vs the reference's sampler outputs: worst rel {worst:.1e}")
+
+
+@pytest.mark.skipif(not RRL.available(), reason="needs /root/reference (build container)")
+def test_oracle_equals_the_references_sampler_run_live():
+    oc, p, b, plain, prev = MGR.setup("float32")
+    for name, kw in MGR.cases(prev).items():
+        ref = RRL.sample_actions(p, oc, b, b["noise"], oracle_suffix_embedding=True, **kw)
+        got = _oracle_run(oc, p, b, kw)
+        assert torch.equal(got, ref), (name, float((got - ref).abs().max()))  # same operations in the same order
+    # a 2-D previous chunk (no batch axis) at batch 1 (pi0_rtc.py:310-311), and the bfloat16 dtype map
+    oc, p16, b, plain, prev = MGR.setup("bfloat16")
+    b1 = {k: ([t[:1] for t in v] if isinstance(v, list) else v[:1]) for k, v in b.items()}
+    kw = dict(prev_action_chunk=prev[0, :, :14], inference_delay=2, execute_horizon=6)
+    ref = RRL.sample_actions(p16, oc, b1, b1["noise"], oracle_suffix_embedding=True, **kw)
+    got = _oracle_run(oc, p16, b1, kw)
+    assert torch.equal(got, ref)
+
+
+def test_prefix_weights_equal_the_references_function():
+    """pi0_rtc.py:47-61 executed in place (fixture; live too when the checkout is present) against the oracle's and the
+    PRODUCT'S host-side schedule (kai0_b200.pi0_pytorch.PI0Pytorch.rtc_prefix_weights)."""
+    from kai0_b200.pi0_pytorch import PI0Pytorch
+
+    gold = torch.load(GOLD_RTC)["prefix_weights"]
+    assert len(gold) == 20
+    for key, want in gold.items():
+        sched, a, e, t = key.split("/")
+        a, e, t = int(a), int(e), int(t)
+        assert torch.allclose(R.get_prefix_weights(a, e, t, sched), want, rtol=0, atol=1e-7), key
+        assert torch.allclose(PI0Pytorch.rtc_prefix_weights(a, e, t, sched), want, rtol=0, atol=1e-7), key
+        if RRL.available():
+            live = RRL.load().get_prefix_weights(a, e, t, sched).as_subclass(torch.Tensor)
+            assert torch.equal(live, want), key
 
 
 def test_prefix_weight_schedules_known_answers():
