@@ -324,6 +324,99 @@ def test_policy_infer_is_the_reference_call_sequence():
     assert not np.array_equal(a, out["actions"])
 
 
+class _CanonicalStub(_StubModel):
+    """Same function of the inputs whether the images arrive as uint8 NHWC (this repo's Policy) or as the fp32 NCHW tensors
+    the reference's `Observation.from_dict` makes of them (models/model.py:129-133)."""
+
+    def sample_actions(self, device, obs, noise=None, num_steps=10, **kw):
+        imgs = {k: (v.to(torch.float32).permute(0, 3, 1, 2) / 255.0 * 2.0 - 1.0 if v.dtype == torch.uint8 else v)
+                for k, v in obs.images.items()}
+        B = obs.state.shape[0]
+        kw_seen = {k: (np.asarray(v.cpu()).tolist() if torch.is_tensor(v) else np.asarray(v).tolist()) for k, v in kw.items()}
+        self.calls.append({"B": B, "kw": kw_seen, "num_steps": num_steps, "state_dtype": obs.state.dtype})
+        img = torch.stack([imgs[k].mean(dim=(1, 2, 3)) for k in sorted(imgs)], 1).sum(1)
+        tok = (obs.tokenized_prompt * obs.tokenized_prompt_mask).sum(1).to(torch.float32)
+        out = 0.1 * obs.state.to(torch.float32)[:, None, :].expand(B, MG.HORIZON, 32) + img[:, None, None]
+        out = out + 1e-4 * tok[:, None, None] + torch.arange(MG.HORIZON)[None, :, None] * 0.01 + 0.001 * num_steps
+        if noise is not None:
+            out = out + noise
+        if "prev_action_chunk" in kw:
+            prev = torch.as_tensor(np.asarray(kw["prev_action_chunk"].cpu() if torch.is_tensor(kw["prev_action_chunk"])
+                                              else kw["prev_action_chunk"]), dtype=torch.float32)
+            prev = prev[None] if prev.dim() == 2 else prev
+            out = out + 0.5 * torch.nn.functional.pad(prev, (0, 32 - prev.shape[-1])) + kw.get("inference_delay", 0)
+        return out.to(torch.float32)
+
+
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_policy_infer_equals_the_references_own_policy_run_live():
+    """`openpi/policies/policy.py` and `openpi/models/model.py` executed in place (tools/reference_serving_loader.py):
+    the reference's `Policy.infer` with the reference's transforms against this repo's `Policy.infer` with this repo's
+    transforms, around the same stand-in model -- replies equal bit for bit, same keyword arguments reach the model."""
+    ref_policy, ref_model = RSL.load_policy()
+    R, rlib, rtok, rns = MG.reference_lib()
+    lib, tok, ns = _mine()
+    mask = S.make_bool_mask(*MG.DELTA_MASK_DIMS)
+
+    def chain(L, tokenizer, stats_cls):
+        stats = {k: stats_cls(**v) for k, v in MG.norm_stats_arrays().items()}
+        ins = [L.InjectDefaultPrompt(MG.DEFAULT_PROMPT), L.agilex_inputs(32), L.DeltaActions(mask),
+               L.Normalize(stats, use_quantiles=True), L.InjectDefaultPrompt(MG.DEFAULT_PROMPT),
+               L.ResizeImages(MG.IMAGE_SIZE, MG.IMAGE_SIZE), L.TokenizePrompt(tokenizer, discrete_state_input=True),
+               L.PadStatesAndActions(32)]
+        outs = [L.Unnormalize(stats, use_quantiles=True), L.AbsoluteActions(mask), L.agilex_outputs()]
+        return ins, outs
+
+    r_ins, r_outs = chain(rlib, rtok(MG.MAX_TOKEN_LEN), rns)
+    m_ins, m_outs = chain(lib, tok(MG.MAX_TOKEN_LEN), ns)
+    ref_stub, my_stub = _CanonicalStub(), _CanonicalStub()
+    kwargs = {"num_steps": 7}
+    ref = ref_policy.Policy(ref_stub, transforms=r_ins, output_transforms=r_outs, sample_kwargs=kwargs,
+                            metadata={"robot": "agilex"}, is_pytorch=True, pytorch_device="cpu")
+    mine = S.Policy(my_stub, transforms=m_ins, output_transforms=m_outs, sample_kwargs=kwargs,
+                    metadata={"robot": "agilex"}, pytorch_device="cpu")
+    assert ref.metadata == mine.metadata
+    nz = np.random.default_rng(4).normal(size=(MG.HORIZON, 32)).astype(np.float32)
+    prev = np.random.default_rng(5).normal(size=(MG.HORIZON, 14)).astype(np.float32)
+    for i, req in enumerate(MG.requests()):
+        for extra, noise in (({}, None), ({}, nz), ({}, nz[None]),
+                             ({"prev_action_chunk": prev, "inference_delay": 3, "execute_horizon": 20}, None)):
+            a = ref.infer({**MG.copy_request(req), **extra}, noise=noise)
+            b = mine.infer({**MG.copy_request(req), **extra}, noise=noise)
+            assert set(a) == set(b) == {"actions", "policy_timing"} and "infer_ms" in b["policy_timing"]
+            _same(b["actions"], a["actions"], f"request {i} {sorted(extra)} noise={noise is not None}")
+            ca, cb = ref_stub.calls[-1], my_stub.calls[-1]
+            assert ca["B"] == cb["B"] == 1 and ca["num_steps"] == cb["num_steps"] == 7
+            assert ca["state_dtype"] == cb["state_dtype"]  # float64 after Normalize on both sides
+            assert set(ca["kw"]) == set(cb["kw"])
+            for k in ("inference_delay", "execute_horizon"):
+                assert ca["kw"].get(k) == cb["kw"].get(k)
+            if "prev_action_chunk" in extra:  # the reference hands the raw [H, 14] array on, this repo a batch of one
+                assert np.array_equal(np.asarray(cb["kw"]["prev_action_chunk"])[0], np.asarray(ca["kw"]["prev_action_chunk"]))
+    # Observation.from_dict of the reference (models/model.py:122-157) vs kai0_b200.model.Observation.from_dict
+    from kai0_b200.model import Observation
+
+    g = torch.Generator().manual_seed(0)
+
+    def data():
+        return {"image": {"base_0_rgb": torch.randint(0, 256, (2, 8, 8, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(1)),
+                          "left_wrist_0_rgb": torch.rand(2, 3, 8, 8, generator=torch.Generator().manual_seed(2))},
+                "image_mask": {"base_0_rgb": torch.ones(2, dtype=torch.bool)}, "state": torch.zeros(2, 32),
+                "tokenized_prompt": torch.zeros(2, 4, dtype=torch.int64), "tokenized_prompt_mask": torch.ones(2, 4, dtype=torch.bool),
+                "progress": torch.rand(2, generator=g), "frame_index": torch.arange(2)}
+
+    ro, mo = ref_model.Observation.from_dict(data()), Observation.from_dict(data())
+    for k in ("base_0_rgb", "left_wrist_0_rgb"):
+        assert torch.equal(ro.images[k], mo.images[k]) and ro.images[k].dtype == mo.images[k].dtype
+    for f in ("state", "tokenized_prompt", "tokenized_prompt_mask", "frame_index", "token_ar_mask", "episode_length"):
+        x, y = getattr(ro, f), getattr(mo, f)
+        assert (x is None and y is None) or torch.equal(x, y), f
+    with pytest.raises(ValueError, match="must be provided together"):
+        ref_model.Observation.from_dict({k: v for k, v in data().items() if k != "tokenized_prompt_mask"})
+    with pytest.raises(ValueError, match="must be provided together"):
+        Observation.from_dict({k: v for k, v in data().items() if k != "tokenized_prompt_mask"})
+
+
 def test_infer_batch_equals_one_by_one_and_groups_rtc_requests():
     pol, model = _policy()
     reqs = MG.requests()

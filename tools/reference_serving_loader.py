@@ -13,7 +13,11 @@ that reproduces the behaviour the files use (pinned versions from the reference'
   orbax, transformers.AutoProcessor, fsq_tokenizer: imported by tokenizer.py for classes this path never touches.
   openpi.shared.download.maybe_download: returns the SentencePiece model path registered with `set_tokenizer_model`
                (the reference fetches gs://big_vision/paligemma_tokenizer.model; no egress here).
-  openpi.models.model: only the `ModelType` enum (models/model.py:30-37); the real module imports jax/flax/orbax.
+  openpi.models.model: only the `ModelType` enum (models/model.py:30-37) for `load()`; `load_policy()` executes the real
+               models/model.py (for `Observation.from_dict`, :122-157) and policies/policy.py (`Policy.infer`, :68-124)
+               in place, with augmax / flax.nnx / flax.struct / orbax / nnx_utils / the PyTorch model module stubbed
+               (`struct.dataclass` -> `dataclasses.dataclass`; only import-time names are needed, the JAX branches of
+               `Policy` are never taken with `is_pytorch=True`).
 """
 from __future__ import annotations
 
@@ -119,6 +123,78 @@ class ModelType(enum.Enum):  # models/model.py:30-37 (values only)
     PI05 = "pi05"
     PI0_RTC = "pi0_rtc"
     PI05_RTC = "pi05_rtc"
+
+
+_policy_loaded = None
+
+
+def load_policy():
+    """Returns (policy module, model module) of the reference: `openpi/policies/policy.py` and `openpi/models/model.py`
+    executed in place on top of `load()`."""
+    global _policy_loaded
+    if _policy_loaded is not None:
+        return _policy_loaded
+    import dataclasses
+
+    R = load()
+
+    class _StubModule(types.ModuleType):
+        def __getattr__(self, name):  # any other attribute (type names in annotations, unused helpers)
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything()
+
+    def stub(name, **attrs):
+        m = _StubModule(name)
+        m.__dict__.update(attrs)
+        return m
+
+    class _NnxModule:
+        pass
+
+    saved = {k: sys.modules.get(k) for k in ("augmax", "flax.nnx", "flax.struct", "jax", "jax.numpy", "openpi.models_pytorch",
+                                             "openpi.models_pytorch.pi0_pytorch", "openpi.shared.image_tools",
+                                             "openpi.shared.nnx_utils", "openpi.models.model", "openpi_client.base_policy",
+                                             "orbax.checkpoint")}
+    flax = sys.modules["flax"]
+    nnx = stub("flax.nnx", Module=_NnxModule)
+    struct = stub("flax.struct", dataclass=dataclasses.dataclass)
+    jnp = stub("jax.numpy")
+    # for these two files `jax` is: tree.map (used), plus names that only appear in annotations / JAX-only branches
+    jx = stub("jax", numpy=jnp, tree=types.SimpleNamespace(map=_tree_map))
+    try:
+        sys.modules.update({"augmax": stub("augmax"), "flax.nnx": nnx, "flax.struct": struct, "jax": jx, "jax.numpy": jnp,
+                            "orbax.checkpoint": stub("orbax.checkpoint")})
+        flax.nnx, flax.struct = nnx, struct
+        sys.modules["orbax"].checkpoint = sys.modules["orbax.checkpoint"]
+        mp = sys.modules.get("openpi.models_pytorch") or stub("openpi.models_pytorch")
+        mp.__path__ = getattr(mp, "__path__", [])
+        sys.modules["openpi.models_pytorch"] = mp
+        if "openpi.models_pytorch.pi0_pytorch" not in sys.modules:
+            sys.modules["openpi.models_pytorch.pi0_pytorch"] = stub("openpi.models_pytorch.pi0_pytorch")
+        mp.pi0_pytorch = sys.modules["openpi.models_pytorch.pi0_pytorch"]
+        sh = sys.modules["openpi.shared"]
+        if "openpi.shared.image_tools" not in sys.modules:
+            sys.modules["openpi.shared.image_tools"] = stub("openpi.shared.image_tools")
+        sh.image_tools = sys.modules["openpi.shared.image_tools"]
+        sys.modules["openpi.shared.nnx_utils"] = stub("openpi.shared.nnx_utils")
+        sh.nnx_utils = sys.modules["openpi.shared.nnx_utils"]
+        at = sys.modules["openpi.shared.array_typing"]
+        for name in ("Float", "Bool", "Int", "Real", "UInt8", "Array", "PyTree", "KeyArrayLike", "Params"):
+            if not hasattr(at, name):
+                setattr(at, name, _Anything())
+        model = _exec_as("openpi.models.model", os.path.join(SRC, "models", "model.py"))
+        sys.modules["openpi.models"].model = model
+        oc = sys.modules["openpi_client"]
+        oc.base_policy = _exec_as("openpi_client.base_policy", os.path.join(CLIENT, "base_policy.py"))
+        policy = _exec_as("openpi.policies.policy", os.path.join(SRC, "policies", "policy.py"))
+        sys.modules["openpi.policies"].policy = policy
+    finally:
+        for k, v in saved.items():  # leave the stubs of other loaders (tools/reference_loader.py) as they were
+            if v is not None:
+                sys.modules[k] = v
+    _policy_loaded = (policy, model)
+    return _policy_loaded
 
 
 def load():
