@@ -559,6 +559,148 @@ def test_checkpoint_directory_round_trip(tmp_path):
         CK.load_checkpoint(model2, opt2, tmp_path / "nothing", "cpu")
 
 
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_checkpoint_directory_interchanges_with_the_references_own_functions(tmp_path):
+    """scripts/train_pytorch.py executed in place: ITS `save_checkpoint` writes a step this repo's `load_checkpoint`
+    restores, and the other way round (weights, stock-AdamW state keyed by parameter position, global step, norm stats)."""
+    import dataclasses
+    import pathlib
+
+    T = RSL.load_train_script()
+    R = RSL.load()
+
+    @dataclasses.dataclass
+    class Cfg:  # the fields the three functions read from TrainConfig (train_pytorch.py:155-183)
+        checkpoint_dir: pathlib.Path
+        save_interval: int = 10
+        num_train_steps: int = 100
+        wandb_enabled: bool = False
+        name: str = "pi05_test"
+
+    oc = O.tiny_config()
+
+    def fresh(seed):
+        m, _ = H.build_pair(oc, seed=seed, device=None)
+        return m, torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+
+    def step(m, opt, seed):
+        g = torch.Generator().manual_seed(seed)
+        for n, p in m.named_parameters():
+            p.grad = None if n in m._dead_grad_names or "gemma_expert.lm_head" in n else torch.randn(p.shape, generator=g).to(p.dtype)
+        opt.step()
+
+    def same(m1, o1, m2, o2):
+        for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+            assert torch.equal(a, b), n
+        s1, s2 = o1.state_dict()["state"], o2.state_dict()["state"]
+        assert s1.keys() == s2.keys() and len(s1) > 50
+        for k in s1:
+            assert torch.equal(s1[k]["exp_avg"], s2[k]["exp_avg"]) and torch.equal(s1[k]["exp_avg_sq"], s2[k]["exp_avg_sq"])
+            assert float(s1[k]["step"]) == float(s2[k]["step"])
+
+    ref_stats = {k: R.normalize.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    my_stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    data_config = types.SimpleNamespace(norm_stats=ref_stats, asset_id="agilex")
+
+    # the reference writes, this repo reads
+    d1 = tmp_path / "by_reference"
+    m, opt = fresh(1)
+    step(m, opt, 7)
+    cfg = Cfg(checkpoint_dir=d1)
+    T.save_checkpoint(m, opt, 15, cfg, True, data_config)  # not on the schedule (15 % 10): nothing written
+    assert not d1.exists() or not os.listdir(d1)
+    T.save_checkpoint(m, opt, 20, cfg, True, data_config)
+    assert sorted(os.listdir(d1 / "20")) == ["assets", "metadata.pt", "model.safetensors", "optimizer.pt"]
+    m2, opt2 = fresh(2)
+    assert CK.load_checkpoint(m2, opt2, d1, "cpu") == 20
+    same(m, opt, m2, opt2)
+    _same(CK.load_norm_stats(d1, "agilex")["actions"].q99, my_stats["actions"].q99, "norm stats written by the reference")
+
+    # this repo writes, the reference reads
+    d2 = tmp_path / "by_this_repo"
+    step(m2, opt2, 8)
+    CK.save_checkpoint(m2, opt2, 30, d2, norm_stats=my_stats, asset_id="agilex", config=Cfg(checkpoint_dir=d2))
+    os.makedirs(d2 / "tmp_40")
+    os.makedirs(d2 / "notes")
+    assert T.get_latest_checkpoint_step(d2) == CK.get_latest_checkpoint_step(d2) == 30
+    m3, opt3 = fresh(3)
+    assert T.load_checkpoint(m3, opt3, d2, torch.device("cpu")) == 30
+    same(m2, opt2, m3, opt3)
+    back = R.normalize.load(d2 / "30" / "assets" / "agilex")
+    _same(back["state"].q01, my_stats["state"].q01, "norm stats read by the reference")
+    # the files themselves: same names, and the norm-stats JSON is byte-identical
+    assert (d1 / "20" / "assets" / "agilex" / "norm_stats.json").read_text() == \
+        (d2 / "30" / "assets" / "agilex" / "norm_stats.json").read_text()
+    meta1 = torch.load(d1 / "20" / "metadata.pt", weights_only=False)
+    meta2 = torch.load(d2 / "30" / "metadata.pt", weights_only=False)
+    assert set(meta1) == set(meta2) == {"global_step", "config", "timestamp"}
+    assert set(meta1["config"]) == set(meta2["config"])
+
+
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_a_checkpoint_of_the_references_own_model_and_optimizer_resumes_on_this_module(tmp_path):
+    """End to end: the REFERENCE'S `PI0Pytorch` (pin configuration, executed in place) + stock AdamW, saved by the
+    reference's own `save_checkpoint`; restored with kai0_b200.checkpoint into this repo's module + stock AdamW, and into
+    the fused optimiser.  Every parameter and every optimiser moment must land on the parameter of the SAME NAME --
+    optimizer.pt is keyed by position in model.parameters(), hence the reference registration order of this module."""
+    import dataclasses
+    import pathlib
+
+    import make_golden_reference as G
+    import reference_pin as PIN
+    from kai0_b200.optim import FusedClipAdamW
+    from kai0_b200.pi0_pytorch import GemmaVariant, PI0Pytorch, Pi05EngineConfig
+
+    p0, ref = G.build_reference("bfloat16")
+    pw = ref.paligemma_with_expert.paligemma
+    pw.lm_head.weight = pw.model.language_model.embed_tokens.weight  # tie_weights() of transformers 4.53.2 (5.5 here skips it)
+    names = [n for n, _ in ref.named_parameters()]
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for _, p in ref.named_parameters():
+            p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+    for n, p in ref.named_parameters():  # the unused expert head never gets a gradient (find_unused_parameters, :441-447)
+        p.grad = None if "gemma_expert.lm_head" in n else (torch.randn(p.shape, generator=g) * 1e-2).to(p.dtype)
+    opt.step()
+
+    @dataclasses.dataclass
+    class Cfg:
+        checkpoint_dir: pathlib.Path
+        save_interval: int = 10
+        num_train_steps: int = 100
+        wandb_enabled: bool = False
+
+    T = RSL.load_train_script()
+    T.save_checkpoint(ref, opt, 10, Cfg(tmp_path), True, types.SimpleNamespace(norm_stats=None, asset_id=None))
+    cfg = Pi05EngineConfig(paligemma_variant=GemmaVariant(*PIN.PG), action_expert_variant=GemmaVariant(*PIN.EX),
+                           vit_depth=PIN.VIT_LAYERS, max_token_len=PIN.MAX_TOKEN_LEN)
+    mine = PI0Pytorch(cfg, init_weights=False)
+    mopt = torch.optim.AdamW(mine.parameters(), lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=1e-10)
+    assert CK.load_checkpoint(mine, mopt, tmp_path, "cpu") == 10
+    rp, mp = dict(ref.named_parameters()), dict(mine.named_parameters())
+    assert set(rp) == set(mp)
+    for n in mp:
+        assert mp[n].dtype == rp[n].dtype and torch.equal(mp[n], rp[n]), n
+    rs, ms = opt.state_dict()["state"], mopt.state_dict()["state"]
+    my_names = [n for n, _ in mine.named_parameters()]
+    assert my_names == names and rs.keys() == ms.keys() and len(rs) == len(names) - 1
+    for i in rs:
+        assert ms[i]["exp_avg"].shape == mp[names[i]].shape
+        assert torch.equal(ms[i]["exp_avg"], rs[i]["exp_avg"]) and torch.equal(ms[i]["exp_avg_sq"], rs[i]["exp_avg_sq"]), names[i]
+    # the fused optimiser takes the same file
+    sd = torch.load(tmp_path / "10" / "optimizer.pt", weights_only=False)
+    for n in mine._dead_grad_names:  # parameters this engine gives no gradient have state in THIS synthetic file only
+        sd["state"].pop(names.index(n), None)
+    fused = FusedClipAdamW(mine)
+    fused.load_state_dict(sd)
+    assert fused.step_count == 1
+    for i, rec in sd["state"].items():
+        dt, off, n, shape = mine._offsets[names[i]]
+        arena = 0 if dt == torch.bfloat16 else 1
+        assert torch.equal(fused.m[arena][off:off + n].view(shape), rec["exp_avg"]), names[i]
+
+
 def test_model_safetensors_loads_whichever_tied_name_the_file_carries(tmp_path):
     """safetensors.save_model keeps ONE name of the tied embed_tokens / lm_head pair (train_pytorch.py:167); a file written
     by either side, with either name, must restore the shared table."""

@@ -126,6 +126,52 @@ class ModelType(enum.Enum):  # models/model.py:30-37 (values only)
 
 
 _policy_loaded = None
+_train_loaded = None
+
+
+def load_train_script():
+    """`scripts/train_pytorch.py` of the reference executed in place as a module (its `save_checkpoint` :149-189,
+    `load_checkpoint` :192-273, `get_latest_checkpoint_step` :276-283 are what kai0_b200/checkpoint.py mirrors).  jax,
+    wandb and the openpi config / data-loader / model modules it imports at the top are stubbed: none of them is touched
+    by those three functions, which use torch, safetensors and the reference's own `openpi.shared.normalize` (real, loaded
+    in place by `load()`)."""
+    global _train_loaded
+    if _train_loaded is not None:
+        return _train_loaded
+    load()
+
+    class _StubModule(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything()
+
+    names = ("jax", "wandb", "openpi.models.pi0_config", "openpi.models_pytorch", "openpi.models_pytorch.pi0_pytorch",
+             "openpi.training", "openpi.training.config", "openpi.training.data_loader")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            m = _StubModule(k)
+            m.__path__ = []
+            sys.modules[k] = m
+        op = sys.modules["openpi"]
+        op.models_pytorch, op.training = sys.modules["openpi.models_pytorch"], sys.modules["openpi.training"]
+        sys.modules["openpi.models"].pi0_config = sys.modules["openpi.models.pi0_config"]
+        sys.modules["openpi.models_pytorch"].pi0_pytorch = sys.modules["openpi.models_pytorch.pi0_pytorch"]
+        sys.modules["openpi.training"].config = sys.modules["openpi.training.config"]
+        sys.modules["openpi.training"].data_loader = sys.modules["openpi.training.data_loader"]
+        spec = importlib.util.spec_from_file_location("_kai0_reference_train_pytorch",
+                                                      os.path.join(REPO, "scripts", "train_pytorch.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _train_loaded = mod
+    return mod
 
 
 def load_policy():
