@@ -8,6 +8,8 @@ Mirrors, for the PyTorch pi0.5 policy of the reference:
   * `AgilexInputs` / `AgilexOutputs`           (src/openpi/policies/agilex_policy.py)
   * `PaligemmaTokenizer`                       (src/openpi/models/tokenizer.py:13-47)
   * the norm-stats wire format                 (src/openpi/shared/normalize.py:123-146)     -> `NormStats`, `save`, `load`
+  * the server's message format and loop       (openpi_client/msgpack_numpy.py, serving/websocket_policy_server.py:48-83)
+                                                                                             -> `packb` / `unpackb`, `MessageHandler`
 
 What is B200-native here is the request path around the engine, not the arithmetic (which is a few hundred host flops):
 the reference serves ONE observation per model call and moves every leaf to the device with its own blocking copy
@@ -808,6 +810,91 @@ class RequestBatcher:
                 f.set_result(r)
         self.batches_served += 1
         self.requests_served += len(live)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wire format of the policy server: msgpack with numpy framing, and the per-connection message loop
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def pack_array(obj):
+    """packages/openpi-client/src/openpi_client/msgpack_numpy.py:21-41: an ndarray travels as
+    {__ndarray__: True, data: raw bytes, dtype: dtype.str, shape}, a numpy scalar as {__npgeneric__: True, data, dtype};
+    void / object / complex dtypes are refused."""
+    if isinstance(obj, (np.ndarray, np.generic)) and obj.dtype.kind in ("V", "O", "c"):
+        raise ValueError(f"Unsupported dtype: {obj.dtype}")
+    if isinstance(obj, np.ndarray):
+        return {b"__ndarray__": True, b"data": obj.tobytes(), b"dtype": obj.dtype.str, b"shape": obj.shape}
+    if isinstance(obj, np.generic):
+        return {b"__npgeneric__": True, b"data": obj.item(), b"dtype": obj.dtype.str}
+    return obj
+
+
+def unpack_array(obj):
+    """msgpack_numpy.py:44-51."""
+    if b"__ndarray__" in obj:
+        return np.ndarray(buffer=obj[b"data"], dtype=np.dtype(obj[b"dtype"]), shape=obj[b"shape"])
+    if b"__npgeneric__" in obj:
+        return np.dtype(obj[b"dtype"]).type(obj[b"data"])
+    return obj
+
+
+def packb(obj) -> bytes:
+    import msgpack
+
+    return msgpack.packb(obj, default=pack_array)
+
+
+def unpackb(data: bytes):
+    import msgpack
+
+    return msgpack.unpackb(data, object_hook=unpack_array)
+
+
+class MessageHandler:
+    """The per-connection protocol of `WebsocketPolicyServer._handler` (src/openpi/serving/websocket_policy_server.py:
+    48-83) without the socket: `greeting()` is the first frame a client receives (the policy metadata); `handle(frame)`
+    turns one request frame into one reply frame -- unpack, `policy.infer`, attach `server_timing` (`infer_ms`, and
+    `prev_total_ms` of the previous exchange), pack.  A failing request yields the traceback as a TEXT frame and marks the
+    session closed, as the reference sends it before closing with INTERNAL_ERROR.  `policy` is anything with
+    `infer(obs)` -- a `Policy` or a `RequestBatcher` shared by all connections.  Put it under any transport, e.g.
+
+        async def handler(ws):                                   # websockets.asyncio.server, as the reference uses
+            h = MessageHandler(policy, metadata)
+            await ws.send(h.greeting())
+            async for frame in ws:
+                reply = await asyncio.get_running_loop().run_in_executor(None, h.handle, frame)
+                await ws.send(reply)
+                if h.closed: await ws.close(code=1011, reason="Internal server error. Traceback included in previous frame."); break
+    """
+
+    def __init__(self, policy, metadata: dict | None = None):
+        self._policy = policy
+        self._metadata = metadata or {}
+        self._prev_total = None
+        self.closed = False
+
+    def greeting(self) -> bytes:
+        return packb(self._metadata)
+
+    def handle(self, frame: bytes):
+        import traceback
+
+        start = time.monotonic()
+        try:
+            obs = unpackb(frame)
+            t0 = time.monotonic()
+            action = self._policy.infer(obs)
+            timing = {"infer_ms": (time.monotonic() - t0) * 1000}
+            if self._prev_total is not None:
+                timing["prev_total_ms"] = self._prev_total * 1000
+            action["server_timing"] = timing
+            reply = packb(action)
+            self._prev_total = time.monotonic() - start
+            return reply
+        except Exception:  # noqa: BLE001
+            self.closed = True
+            return traceback.format_exc()
 
 
 # ---------------------------------------------------------------------------------------------------------------

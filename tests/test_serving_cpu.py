@@ -505,6 +505,58 @@ def test_request_batcher_serves_concurrent_clients_in_shared_calls():
         S.RequestBatcher(pol, max_batch=0)
 
 
+# ------------------------------------------------------------------ server wire format
+def _reference_msgpack_numpy():
+    import importlib.util
+
+    path = os.path.join(RSL.CLIENT, "msgpack_numpy.py")
+    spec = importlib.util.spec_from_file_location("_kai0_reference_msgpack_numpy", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_message_framing_and_session_loop():
+    """openpi_client/msgpack_numpy.py + websocket_policy_server.py:48-83."""
+    req = MG.requests()[0]
+    payload = {"images": req["images"], "state": req["state"], "prompt": req["prompt"], "k": np.float32(1.5),
+               "flag": np.True_, "nested": {"ids": np.arange(6, dtype=np.int64).reshape(2, 3)}, "plain": [1, 2.5, "x"]}
+    frame = S.packb(payload)
+    back = S.unpackb(frame)
+    assert back["prompt"] == req["prompt"] and back["plain"] == [1, 2.5, "x"]
+    _same(back["images"]["top_head"], req["images"]["top_head"], "uint8 image")
+    _same(back["state"], req["state"], "state")
+    _same(back["nested"]["ids"], payload["nested"]["ids"], "nested int64")
+    assert type(back["k"]) is np.float32 and back["k"] == np.float32(1.5) and type(back["flag"]) is np.bool_
+    with pytest.raises(ValueError, match="Unsupported dtype"):
+        S.packb({"z": np.zeros(2, dtype=np.complex64)})
+    with pytest.raises(ValueError, match="Unsupported dtype"):
+        S.packb({"o": np.array([None, 1], dtype=object)})
+    if RSL.available():  # byte-identical frames, and each side reads the other's
+        ref = _reference_msgpack_numpy()
+        assert ref.packb(payload) == frame
+        assert ref.Packer().pack(payload) == frame
+        theirs = ref.unpackb(frame)
+        _same(theirs["nested"]["ids"], payload["nested"]["ids"], "reference reads this repo's frame")
+        assert type(theirs["k"]) is np.float32
+
+    pol, model = _policy()
+    h = S.MessageHandler(pol, {"robot": "agilex"})
+    assert S.unpackb(h.greeting()) == {"robot": "agilex"}
+    wire = {"images": req["images"], "state": req["state"], "prompt": req["prompt"]}
+    r1 = S.unpackb(h.handle(S.packb(wire)))
+    _same(r1["actions"], pol.infer(MG.copy_request(req))["actions"], "reply over the wire")
+    assert set(r1["server_timing"]) == {"infer_ms"} and "infer_ms" in r1["policy_timing"]
+    r2 = S.unpackb(h.handle(S.packb(wire)))
+    assert set(r2["server_timing"]) == {"infer_ms", "prev_total_ms"} and not h.closed
+    bad = h.handle(S.packb({"images": {}, "state": req["state"]}))  # a failing request: traceback as text, session closed
+    assert isinstance(bad, str) and "Traceback" in bad and "not found" in bad and h.closed
+    # a RequestBatcher shared by several connections speaks the same protocol
+    with S.RequestBatcher(pol, max_batch=4, max_wait_ms=50.0) as rb:
+        h2 = S.MessageHandler(rb, rb.metadata)
+        _same(S.unpackb(h2.handle(S.packb(wire)))["actions"], r1["actions"], "through the batcher")
+
+
 # ------------------------------------------------------------------ checkpoint directory
 def test_parameters_are_registered_in_the_references_order():
     """optimizer.pt keys its state by position in model.parameters() (train_pytorch.py:170,236-243)."""
