@@ -753,6 +753,41 @@ def test_a_checkpoint_of_the_references_own_model_and_optimizer_resumes_on_this_
         assert torch.equal(fused.m[arena][off:off + n].view(shape), rec["exp_avg"]), names[i]
 
 
+def test_create_trained_policy_from_a_checkpoint_directory(tmp_path):
+    """policy_config.py:16-94: weights from model.safetensors, dtype map, norm stats FROM THE CHECKPOINT (not the config's
+    assets), the transform chain in the reference's order; and the engine-backed policy has no CPU fallback."""
+    oc = O.tiny_config()
+    trained, _ = H.build_pair(oc, seed=11, device=None)
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    step_dir = CK.save_checkpoint(trained, None, 500, tmp_path, norm_stats=stats, asset_id="agilex")
+    assert not os.path.exists(os.path.join(step_dir, "optimizer.pt"))  # optimizer=None: weights + metadata + assets only
+    from kai0_b200.pi0_pytorch import PI0Pytorch
+
+    fresh = PI0Pytorch(H.engine_config(oc))
+    tok = S.PaligemmaTokenizer(oc.max_token_len, model_path=MG.SPM)
+    pol = S.create_trained_policy(fresh, step_dir, asset_id="agilex", tokenizer=tok, default_prompt="fold the cloth",
+                                  pytorch_device="cpu", metadata={"reset_pose": [0.0] * 14}, sample_kwargs={"num_steps": 10})
+    for (n, a), (_, b) in zip(trained.named_parameters(), fresh.named_parameters()):
+        assert torch.equal(a, b), n
+    assert pol.metadata == {"reset_pose": [0.0] * 14}
+    ins = [type(t).__name__ for t in pol._input_transform.__closure__[0].cell_contents]
+    outs = [type(t).__name__ for t in pol._output_transform.__closure__[0].cell_contents]
+    assert ins == ["InjectDefaultPrompt", "AgilexInputs", "DeltaActions", "Normalize", "InjectDefaultPrompt", "ResizeImages",
+                   "TokenizePrompt", "PadStatesAndActions"]                      # policy_config.py:75-81
+    assert outs == ["Unnormalize", "AbsoluteActions", "AgilexOutputs"]            # :82-87
+    norm = pol._input_transform.__closure__[0].cell_contents[3]
+    assert norm.use_quantiles and np.array_equal(norm.norm_stats["state"].q01, stats["state"].q01)
+    req = MG.requests()[2]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pol.infer(req)  # the request went through every transform and reached the engine, which refuses to run on a CPU
+    with pytest.raises(ValueError, match="Asset id is required"):
+        S.create_trained_policy(fresh, step_dir, asset_id=None, tokenizer=tok, pytorch_device="cpu")
+    with pytest.raises(FileNotFoundError, match="model.safetensors"):
+        S.create_trained_policy(fresh, tmp_path / "nowhere", asset_id="agilex", tokenizer=tok, pytorch_device="cpu")
+    with pytest.raises(FileNotFoundError, match="Norm stats file not found"):
+        S.create_trained_policy(fresh, step_dir, asset_id="other_robot", tokenizer=tok, pytorch_device="cpu")
+
+
 def test_model_safetensors_loads_whichever_tied_name_the_file_carries(tmp_path):
     """safetensors.save_model keeps ONE name of the tied embed_tokens / lm_head pair (train_pytorch.py:167); a file written
     by either side, with either name, must restore the shared table."""
