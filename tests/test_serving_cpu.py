@@ -557,6 +557,71 @@ def test_message_framing_and_session_loop():
         _same(S.unpackb(h2.handle(S.packb(wire)))["actions"], r1["actions"], "through the batcher")
 
 
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_the_references_own_websocket_client_talks_to_this_serving_stack():
+    """openpi_client/websocket_client_policy.py executed in place against tools/serve_policy_b200.py (MessageHandler +
+    RequestBatcher under the `websockets` library) on 127.0.0.1: metadata on connect, replies equal to a direct
+    `Policy.infer`, a failing request surfaces as the client's RuntimeError with the server's traceback."""
+    import asyncio
+    import importlib.util
+
+    pytest.importorskip("websockets")
+    import serve_policy_b200 as SRV
+
+    RSL.load()  # registers openpi_client (+ image_tools); add its two remaining pure-python modules from where they lie
+    for name in ("msgpack_numpy", "base_policy", "websocket_client_policy"):
+        full = f"openpi_client.{name}"
+        if full not in sys.modules:
+            spec = importlib.util.spec_from_file_location(full, os.path.join(RSL.CLIENT, name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            spec.loader.exec_module(mod)
+            setattr(sys.modules["openpi_client"], name, mod)
+    client_mod = sys.modules["openpi_client.websocket_client_policy"]
+
+    pol, model = _policy()
+    reqs = MG.requests()
+    direct = [pol.infer(MG.copy_request(r))["actions"] for r in reqs]
+    state = {}
+    started = threading.Event()
+
+    def run_server():
+        loop = asyncio.new_event_loop()
+        asyncio.set_event_loop(loop)
+        state["loop"], state["stop"] = loop, asyncio.Event()
+        with S.RequestBatcher(pol, max_batch=4, max_wait_ms=20.0) as rb:
+            loop.run_until_complete(SRV.serve(rb, "127.0.0.1", 0, {"robot": "agilex"},
+                                              ready=lambda port: (state.__setitem__("port", port), started.set()),
+                                              stop=state["stop"]))
+        loop.close()
+
+    th = threading.Thread(target=run_server, daemon=True)
+    th.start()
+    assert started.wait(30)
+    try:
+        client = client_mod.WebsocketClientPolicy("127.0.0.1", state["port"])
+        assert client.get_server_metadata() == {"robot": "agilex"}
+        for i, r in enumerate(reqs):
+            wire = {"images": r["images"], "state": r["state"]}
+            if "prompt" in r:
+                wire["prompt"] = str(np.asarray(r["prompt"]).item()) if not isinstance(r["prompt"], str) else r["prompt"]
+            out = client.infer(wire)
+            _same(out["actions"], direct[i], f"request {i} through the reference's client")
+            assert "infer_ms" in out["server_timing"] and "infer_ms" in out["policy_timing"]
+        second = client_mod.WebsocketClientPolicy("127.0.0.1", state["port"])  # a second connection shares the batcher
+        _same(second.infer({"images": reqs[0]["images"], "state": reqs[0]["state"], "prompt": reqs[0]["prompt"]})["actions"],
+              direct[0], "second connection")
+        with pytest.raises(RuntimeError, match="Error in inference server"):
+            second.infer({"images": {}, "state": reqs[0]["state"]})
+        import urllib.request
+
+        assert urllib.request.urlopen(f"http://127.0.0.1:{state['port']}/healthz", timeout=10).read() == b"OK\n"
+    finally:
+        state["loop"].call_soon_threadsafe(state["stop"].set)
+        th.join(timeout=30)
+    assert not th.is_alive()
+
+
 # ------------------------------------------------------------------ checkpoint directory
 def test_parameters_are_registered_in_the_references_order():
     """optimizer.pt keys its state by position in model.parameters() (train_pytorch.py:170,236-243)."""
