@@ -502,6 +502,7 @@ class AgilexInputs:
     action_dim: int
     pi05: bool = True
     mask_state: bool = False
+    zero_out_of_range_state: bool = True  # agilex_policy.py:92-94; the ARX variant (arx_policy.py) leaves the state alone
 
     REQUIRED = {"top_head": "base_0_rgb", "hand_left": "left_wrist_0_rgb", "hand_right": "right_wrist_0_rgb"}
     OPTIONAL = {"his_-100_top_head": "base_-100_rgb", "his_-100_hand_left": "left_wrist_-100_rgb",
@@ -528,8 +529,9 @@ class AgilexInputs:
             if img.shape[0] == 3:
                 img = np.transpose(img, (1, 2, 0))
             images[key], masks[key] = img, np.True_
-        state = np.where(state > np.pi, 0, state)
-        state = np.where(state < -np.pi, 0, state)
+        if self.zero_out_of_range_state:
+            state = np.where(state > np.pi, 0, state)
+            state = np.where(state < -np.pi, 0, state)
         out = {"image": images, "image_mask": masks, "state": np.zeros_like(state) if self.mask_state else state}
         if "actions" in data:
             actions = pad_to_dim(data["actions"], self.action_dim)
@@ -557,12 +559,21 @@ class AgilexInputs:
         return out
 
 
+def ARXInputs(action_dim: int, pi05: bool = True, mask_state: bool = False) -> AgilexInputs:
+    """policies/arx_policy.py:14-135: the Agilex transform without the out-of-range filter on the STATE (actions are
+    still filtered); kai0's second robot (training/config.py:457-545)."""
+    return AgilexInputs(action_dim=action_dim, pi05=pi05, mask_state=mask_state, zero_out_of_range_state=False)
+
+
 @dataclasses.dataclass(frozen=True)
 class AgilexOutputs:
     """agilex_policy.py:156-162: the 14 real joint dimensions of the chunk."""
 
     def __call__(self, data):
         return {"actions": np.asarray(data["actions"][:, :14])}
+
+
+ARXOutputs = AgilexOutputs  # arx_policy.py:138-144: the same 14 dimensions
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -251,6 +251,32 @@ def test_agilex_inputs_errors_and_training_fields():
     assert float(np.abs(S.AgilexInputs(action_dim=32, mask_state=True)({**good, "state": np.ones(14)})["state"]).max()) == 0
 
 
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_arx_inputs_equal_the_references_arx_policy_live():
+    """policies/arx_policy.py executed in place: the ARX robot's transform keeps out-of-range state values."""
+    import importlib.util
+
+    R = RSL.load()
+    spec = importlib.util.spec_from_file_location("openpi.policies.arx_policy", os.path.join(RSL.SRC, "policies", "arx_policy.py"))
+    arx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(arx)
+    ref_in, my_in = arx.ARXInputs(action_dim=32, model_type=R.ModelType.PI05), S.ARXInputs(32)
+    for r in MG.requests():
+        r = dict(MG.copy_request(r), actions=np.random.default_rng(0).uniform(-4, 4, (MG.HORIZON, 14)))
+        a, b = ref_in(MG.copy_request(r)), my_in(MG.copy_request(r))
+        fa, fb = R.transforms.flatten_dict(a), S.flatten_dict(b)
+        assert list(fa) == list(fb)
+        for k in fa:
+            if isinstance(fa[k], str):
+                assert fa[k] == fb[k]
+            else:
+                _same(fb[k], fa[k], k)
+    out = my_in(MG.copy_request(MG.requests()[0]))
+    assert float(out["state"][3]) == 4.0  # the Agilex transform would have zeroed it
+    chunk = {"actions": np.arange(MG.HORIZON * 32, dtype=np.float32).reshape(MG.HORIZON, 32)}
+    _same(S.ARXOutputs()(dict(chunk))["actions"], arx.ARXOutputs()(dict(chunk))["actions"], "ARXOutputs")
+
+
 # ------------------------------------------------------------------ Policy / batching (stub model on the CPU)
 class _StubModel:
     """Stands in for PI0Pytorch on the CPU: a deterministic function of every input, so that routing mistakes show."""
