@@ -299,3 +299,36 @@ def test_staged_reference_is_byte_identical_to_the_checkout():
             assert filecmp.cmp(os.path.join(d, f), os.path.join(dst, rel), shallow=False), rel
             n += 1
     assert n > 20
+
+
+def test_shipped_library_is_blackwell_native_sass():
+    """Static evidence in the built library (B200_PROFILING.md "What proves a Blackwell-native kernel"): every embedded
+    cubin is sm_100a; the tensor-core work is tcgen05 (`UTCHMMA`, incl. the 2-CTA form) fed by TMA (`UTMALDG`) with TMEM
+    read-back (`LDTM`); no legacy `mma.sync` / `wmma` (`HMMA`) and no Hopper `wgmma` (`HGMMA`) anywhere; no kernel spills to
+    local memory and stack frames stay tiny."""
+    import re
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    so = os.path.join(ROOT, "kai0_b200", "libpi05.so")
+    if not os.path.exists(cuobjdump) or not os.path.exists(so):
+        pytest.skip("needs cuobjdump and the built kai0_b200/libpi05.so")
+    elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True, check=True).stdout
+    names = re.findall(r"ELF file\s+\d+:\s+(\S+)", elfs)
+    assert len(names) >= 15 and all(n.endswith(".sm_100a.cubin") for n in names), names
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    ops = set(re.findall(r"\b([A-Z][A-Z0-9]+(?:\.[A-Za-z0-9_]+)*)\b", sass))
+    base = {o.split(".")[0] for o in ops}
+    assert "UTCHMMA" in base and any(o.startswith("UTCHMMA.2CTA") for o in ops)       # tcgen05.mma, cta_group::1 and ::2
+    assert any(o.startswith("UTMALDG") for o in ops) and any(o.startswith("UTMALDG") and "2CTA" in o for o in ops)  # TMA loads
+    assert any(o.startswith("LDTM") for o in ops)                                      # tcgen05.ld (TMEM -> registers)
+    assert any(o.startswith("UTCBAR") and "MULTICAST" in o for o in ops)               # tcgen05.commit multicast to the CTA pair
+    assert not base & {"HMMA", "HGMMA", "QGMMA", "IGMMA", "IMMA", "BMMA"}, base & {"HMMA", "HGMMA", "QGMMA", "IGMMA", "IMMA", "BMMA"}
+    usage = subprocess.run([cuobjdump, "-res-usage", so], capture_output=True, text=True, check=True).stdout
+    recs = re.findall(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", usage)
+    assert len(recs) >= 150
+    assert all(int(local) == 0 for _, _, _, local in recs)         # nothing spills
+    assert max(int(stack) for _, stack, _, _ in recs) <= 64        # parameter-copy frames only
+    assert max(int(reg) for reg, _, _, _ in recs) <= 255
+
