@@ -625,6 +625,15 @@ class _Staging:
         return host.to(self.device, non_blocking=True)
 
 
+class _Prepared:
+    """One request after its input transforms: what `Policy.infer_prepared` batches."""
+
+    __slots__ = ("raw", "data", "noise", "key")
+
+    def __init__(self, raw, data, noise, key):
+        self.raw, self.data, self.noise, self.key = raw, data, noise, key
+
+
 class Policy:
     """`openpi.policies.policy.Policy` for the PyTorch pi0.5 engine (policy.py:23-129).
 
@@ -663,17 +672,28 @@ class Policy:
         return self.infer_batch([obs], noise=None if noise is None else [noise])[0]
 
     def infer_batch(self, observations: Sequence[dict], *, noise: Sequence[np.ndarray | None] | None = None) -> list:
-        if len(observations) == 0:
-            return []
         if noise is not None and len(noise) != len(observations):
             raise ValueError("noise must hold one entry (or None) per observation")
-        prepared = [self._input_transform(_copy_structure(o)) for o in observations]
+        return self.infer_prepared([self.prepare(o, None if noise is None else noise[i]) for i, o in enumerate(observations)])
+
+    def prepare(self, obs: dict, noise: np.ndarray | None = None) -> "_Prepared":
+        """The host half of a request that needs no device and no lock: copy + input transforms (policy.py:70-71).  Safe to
+        call from any thread; `RequestBatcher` runs it in the client's thread so that the transforms of the next batch overlap
+        the model call of the current one."""
+        data = self._input_transform(_copy_structure(obs))
+        key = tuple((k, None if k not in obs or k == "prev_action_chunk" or obs[k] is None else int(obs[k])) for k in _RTC_KEYS)
+        key += ("prev_action_chunk" in obs, noise is not None)
+        return _Prepared(obs, data, noise, key)
+
+    def infer_prepared(self, items: Sequence["_Prepared"]) -> list:
+        """The device half: requests that can share a `sample_actions` call (same RTC scalars, noise given or not) are
+        staged, copied, run and read back together, in slices of at most `max_batch`."""
+        if len(items) == 0:
+            return []
         groups: dict = {}
-        for i, o in enumerate(observations):
-            key = tuple((k, None if k not in o or k == "prev_action_chunk" or o[k] is None else int(o[k])) for k in _RTC_KEYS)
-            key += ("prev_action_chunk" in o, None if noise is None else noise[i] is not None)
-            groups.setdefault(key, []).append(i)
-        results: list = [None] * len(observations)
+        for i, it in enumerate(items):
+            groups.setdefault(it.key, []).append(i)
+        results: list = [None] * len(items)
         # a server thread that never touched CUDA starts on device 0: make the engine's device current for the call
         dev = torch.device(self._device)
         on_dev = torch.cuda.device(dev) if dev.type == "cuda" and dev.index is not None else _NullContext()
@@ -682,8 +702,9 @@ class Policy:
                 step = self._max_batch or len(members)
                 for lo in range(0, len(members), step):
                     idx = members[lo:lo + step]
-                    outs = self._run_group([observations[i] for i in idx], [prepared[i] for i in idx],
-                                           None if noise is None else [noise[i] for i in idx])
+                    has_noise = items[idx[0]].noise is not None
+                    outs = self._run_group([items[i].raw for i in idx], [items[i].data for i in idx],
+                                           [items[i].noise for i in idx] if has_noise else None)
                     for i, o in zip(idx, outs):
                         results[i] = o
         return results
@@ -729,7 +750,9 @@ class Policy:
 
 class RequestBatcher:
     """Drop-in `infer(obs)` for a server with many clients: requests arriving within `max_wait_ms` of each other are
-    served by one `Policy.infer_batch` call (at most `max_batch` per call).  A lone request waits at most `max_wait_ms`."""
+    served by one model call (at most `max_batch` per call).  A lone request waits at most `max_wait_ms`.  The input
+    transforms of a request run in the thread that submits it (`Policy.prepare`), the worker thread only stages, runs
+    and unpacks batches (`Policy.infer_prepared`)."""
 
     _STOP = object()
 
@@ -756,7 +779,12 @@ class RequestBatcher:
         if self._closed:
             raise RuntimeError("RequestBatcher is closed")
         fut: Future = Future()
-        self._q.put((obs, fut))
+        try:
+            item = self._policy.prepare(obs)  # in the CLIENT'S thread: transforms of many clients run side by side, and
+        except Exception as e:  # noqa: BLE001  overlap the model call in flight; a bad request fails here, alone
+            fut.set_exception(e)
+            return fut
+        self._q.put((item, fut))
         return fut
 
     def infer(self, obs: dict) -> dict:
@@ -805,15 +833,15 @@ class RequestBatcher:
                 item[1].set_exception(RuntimeError("RequestBatcher is closed"))
 
     def _serve(self, pending):
-        live = [(o, f) for o, f in pending if f.set_running_or_notify_cancel()]
+        live = [(it, f) for it, f in pending if f.set_running_or_notify_cancel()]
         if not live:
             return
         try:
-            replies = self._policy.infer_batch([o for o, _ in live])
+            replies = self._policy.infer_prepared([it for it, _ in live])
         except Exception:  # noqa: BLE001  -- one bad request must not take its neighbours down: retry one by one
-            for o, f in live:
+            for it, f in live:
                 try:
-                    f.set_result(self._policy.infer(o))
+                    f.set_result(self._policy.infer_prepared([it])[0])
                 except Exception as e:  # noqa: BLE001
                     f.set_exception(e)
         else:
