@@ -299,6 +299,8 @@ def test_staged_reference_is_byte_identical_to_the_checkout():
             assert filecmp.cmp(os.path.join(d, f), os.path.join(dst, rel), shallow=False), rel
             n += 1
     assert n > 20
+    staged_script = os.path.join(ROOT, "baseline", "_ref", "scripts", "train_pytorch.py")
+    assert filecmp.cmp("/root/reference/scripts/train_pytorch.py", staged_script, shallow=False)
 
 
 def test_shipped_library_is_blackwell_native_sass():

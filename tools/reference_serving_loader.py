@@ -117,6 +117,20 @@ class _Anything:
         return _Anything()
 
 
+def numpydantic_stub():
+    """numpydantic 1.6.9's `NDArray` as normalize.py uses it: a pydantic field type that validates to `np.ndarray` and
+    JSON-serialises as nested lists."""
+    import pydantic
+
+    m = types.ModuleType("numpydantic")
+    m.NDArray = typing.Annotated[
+        typing.Any,
+        pydantic.BeforeValidator(lambda v: v if v is None else np.asarray(v)),
+        pydantic.PlainSerializer(lambda a: None if a is None else np.asarray(a).tolist(), when_used="json"),
+    ]
+    return m
+
+
 class ModelType(enum.Enum):  # models/model.py:30-37 (values only)
     PI0 = "pi0"
     PI0_FAST = "pi0_fast"
@@ -254,11 +268,7 @@ def load():
     # third-party stand-ins
     nd = _module("numpydantic")
     if not hasattr(nd, "NDArray"):
-        nd.NDArray = typing.Annotated[
-            typing.Any,
-            pydantic.BeforeValidator(lambda v: v if v is None else np.asarray(v)),
-            pydantic.PlainSerializer(lambda a: None if a is None else np.asarray(a).tolist(), when_used="json"),
-        ]
+        nd.NDArray = numpydantic_stub().NDArray
     tu = _module("flax.traverse_util", flatten_dict=_flatten, unflatten_dict=_unflatten)
     fl = _module("flax", traverse_util=tu)
     fl.__path__ = getattr(fl, "__path__", [])

@@ -19,6 +19,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/src/openpi"
 DST = os.path.join(ROOT, "baseline", "_ref", "openpi")
+SCRIPT_SRC = "/root/reference/scripts/train_pytorch.py"
+SCRIPTS_DST = os.path.join(ROOT, "baseline", "_ref", "scripts")
 
 
 def stage() -> bool:
@@ -27,6 +29,10 @@ def stage() -> bool:
     if os.path.isdir(DST):
         shutil.rmtree(DST)
     shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    # the training entry point itself (not part of the wheel, staged beside it): tests/test_zzzz_train_script_gpu.py runs ITS
+    # `train_loop` around the engine on the GPU box (tools/reference_train_harness.py)
+    os.makedirs(SCRIPTS_DST, exist_ok=True)
+    shutil.copyfile(SCRIPT_SRC, os.path.join(SCRIPTS_DST, "train_pytorch.py"))
     h = hashlib.sha256()
     n = 0
     for d, _, files in sorted(os.walk(DST)):
