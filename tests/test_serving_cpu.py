@@ -443,6 +443,62 @@ def test_policy_infer_equals_the_references_own_policy_run_live():
         Observation.from_dict({k: v for k, v in data().items() if k != "tokenized_prompt_mask"})
 
 
+class _CheckpointableStub(torch.nn.Module):
+    """A stand-in with the constructor / checkpoint surface `create_trained_policy` needs (policy_config.py:52-55)."""
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = config
+        self.w = torch.nn.Parameter(torch.zeros(3))
+        self.paligemma_with_expert = types.SimpleNamespace(to_bfloat16_for_selected_params=lambda p: setattr(self, "cast", p))
+        self._impl = _CanonicalStub()
+        self._max_batch_hint = None
+        self.ecfg = types.SimpleNamespace(action_dim=32, max_token_len=MG.MAX_TOKEN_LEN, image_size=MG.IMAGE_SIZE)
+
+    def sample_actions(self, device, obs, noise=None, num_steps=10, **kw):
+        return self._impl.sample_actions(device, obs, noise=noise, num_steps=num_steps, **kw) + self.w.sum()
+
+
+@pytest.mark.skipif(not RSL.available(), reason="needs /root/reference (build container)")
+def test_the_references_own_create_trained_policy_builds_the_same_policy(tmp_path):
+    """policies/policy_config.py executed in place (tools/reference_serve_harness.py): ITS `create_trained_policy` -- model
+    through the reference's `load_pytorch`, dtype cast, norm stats from the checkpoint, the Agilex chain assembled as
+    training/config.py does -- against `serving.create_trained_policy` on the same checkpoint directory."""
+    import safetensors.torch
+
+    import reference_serve_harness as RSH
+
+    stats = {k: S.NormStats(**v) for k, v in MG.norm_stats_arrays().items()}
+    trained = _CheckpointableStub()
+    with torch.no_grad():
+        trained.w.copy_(torch.tensor([0.25, -0.5, 1.0]))
+    step_dir = tmp_path / "7"
+    os.makedirs(step_dir)
+    safetensors.torch.save_model(trained, str(step_dir / "model.safetensors"))
+    S.save(step_dir / "assets" / "agilex", stats)
+    R, rlib, rtok, rns = MG.reference_lib()
+    mod = types.ModuleType("stand_in")
+    mod.PI0Pytorch = _CheckpointableStub
+    fields = dict(action_dim=32, action_horizon=MG.HORIZON, max_token_len=MG.MAX_TOKEN_LEN)
+    ref = RSH.reference_policy(mod, fields, step_dir, asset_id="agilex", tokenizer=rtok(MG.MAX_TOKEN_LEN),
+                               default_prompt=MG.DEFAULT_PROMPT, sample_kwargs={"num_steps": 5}, pytorch_device="cpu",
+                               image_size=MG.IMAGE_SIZE, metadata={"robot": "agilex"})
+    assert type(ref).__module__ == "openpi.policies.policy" and ref.metadata == {"robot": "agilex"}
+    assert ref._model.cast == "bfloat16" and torch.equal(ref._model.w.detach(), trained.w.detach())  # loaded, then cast (:53-55)
+    mine = S.create_trained_policy(_CheckpointableStub(), step_dir, asset_id="agilex",
+                                   tokenizer=S.PaligemmaTokenizer(MG.MAX_TOKEN_LEN, model_path=MG.SPM),
+                                   default_prompt=MG.DEFAULT_PROMPT, sample_kwargs={"num_steps": 5}, pytorch_device="cpu",
+                                   metadata={"robot": "agilex"})
+    nz = np.random.default_rng(9).normal(size=(MG.HORIZON, 32)).astype(np.float32)
+    for i, req in enumerate(MG.requests()):
+        a = ref.infer(MG.copy_request(req), noise=nz)
+        b = mine.infer(MG.copy_request(req), noise=nz)
+        _same(b["actions"], a["actions"], f"request {i}")
+    assert ref._model._impl.calls[-1]["num_steps"] == mine._model._impl.calls[-1]["num_steps"] == 5
+    with pytest.raises(ValueError, match="Asset id is required"):
+        RSH.reference_policy(mod, fields, step_dir, asset_id=None, tokenizer=rtok(MG.MAX_TOKEN_LEN), pytorch_device="cpu")
+
+
 def test_infer_batch_equals_one_by_one_and_groups_rtc_requests():
     pol, model = _policy()
     reqs = MG.requests()

@@ -105,3 +105,77 @@ def test_the_references_own_train_loop_runs_on_the_engine(tmp_path):
     assert moved > 50  # training moved (nearly) every tensor between step 1 and step 3
     state = last_opt.state_dict()["state"]
     assert len(state) > 50 and all(float(s["step"]) == STEPS for s in state.values())
+
+
+class _HashTokenizer:
+    """Ragged prompts inside the tiny configuration's 24 slots (as tests/test_zzz_serving_gpu.py)."""
+
+    def __init__(self, max_len, vocab):
+        self.max_len, self.vocab = max_len, vocab
+
+    def tokenize(self, prompt, state=None):
+        import numpy as np
+
+        bins = np.digitize(state, bins=np.linspace(-1, 1, 257)[:-1]) - 1
+        n = 7 + (sum(map(ord, prompt)) % (self.max_len - 9))
+        ids = [2] + [int((ord(prompt[i % len(prompt)]) * 7 + int(bins[i % len(bins)]) + 3 * i) % (self.vocab - 1)) + 1
+                     for i in range(n - 1)]
+        pad = self.max_len - n
+        return np.asarray(ids + [0] * pad), np.asarray([True] * n + [False] * pad)
+
+
+def test_the_references_own_create_trained_policy_serves_from_the_engine(tmp_path):
+    """north_star: "scripts/serve_policy.py call it unchanged".  The reference's OWN `create_trained_policy`
+    (policies/policy_config.py, executed in place by tools/reference_serve_harness.py) loads a checkpoint directory into
+    `kai0_b200.pi0_pytorch.PI0Pytorch` through the reference's `load_pytorch`, and the reference's OWN `Policy.infer`
+    (policies/policy.py: per-leaf copies, `Observation.from_dict`, `sample_actions`) serves Agilex requests from it; the
+    replies must agree with `kai0_b200.serving`'s policy on the same checkpoint (same engine, same inputs up to the image
+    format -- fp32 NCHW from the reference's from_dict vs uint8 NHWC -- which the engine converts identically)."""
+    import numpy as np
+
+    import reference_serve_harness as RSH
+    import kai0_b200.pi0_pytorch as b200
+    from kai0_b200 import checkpoint as CK
+    from kai0_b200 import serving as S
+
+    if not RSH.available():
+        pytest.skip("needs the reference's serving files (checkout or staged copy)")
+    oc = O.tiny_config()
+    trained, _ = H.build_pair(oc, seed=21, device=None)
+    g = np.random.default_rng(11)
+    stats = {}
+    for key in ("state", "actions"):
+        mean = g.normal(0, 0.3, 32)
+        q01, q99 = mean - g.uniform(1.0, 2.0, 32), mean + g.uniform(1.0, 2.0, 32)
+        for a in (mean, q01, q99):
+            a[14:] = 0.0
+        stats[key] = S.NormStats(mean=mean, std=np.ones(32), q01=q01, q99=q99)
+    step_dir = CK.save_checkpoint(trained, None, 100, tmp_path, norm_stats=stats, asset_id="agilex")
+    tok = _HashTokenizer(oc.max_token_len, oc.vocab_size)
+    fields = dataclass_fields(_model_config(oc))
+    ref = RSH.reference_policy(b200, fields, step_dir, asset_id="agilex", tokenizer=tok, default_prompt="fold the cloth",
+                               pytorch_device="cuda", image_size=oc.image_size)
+    assert type(ref).__module__ == "openpi.policies.policy" and isinstance(ref._model, b200.PI0Pytorch)
+    mine = S.create_trained_policy(b200.PI0Pytorch(_model_config(oc)), step_dir, asset_id="agilex", tokenizer=tok,
+                                   default_prompt="fold the cloth", pytorch_device="cuda")
+    for (n, a), (_, b) in zip(ref._model.named_parameters(), mine._model.named_parameters()):
+        assert torch.equal(a, b) and torch.equal(a.cpu(), dict(trained.named_parameters())[n]), n
+    cams = ("top_head", "hand_left", "hand_right")
+    prompts = ["fold the cloth", "hang the shirt on the hanger"]
+    for i in range(2):
+        req = {"images": {c: g.integers(0, 256, (3, 90, 120), dtype=np.uint8) for c in cams},
+               "state": g.uniform(-1, 1, 14).astype(np.float32), "prompt": prompts[i]}
+        nz = g.normal(size=(oc.action_horizon, oc.action_dim)).astype(np.float32)
+        a = ref.infer({**req, "images": dict(req["images"])}, noise=nz)
+        b = mine.infer({**req, "images": dict(req["images"])}, noise=nz)
+        assert a["actions"].shape == b["actions"].shape == (oc.action_horizon, 14) and np.isfinite(a["actions"]).all()
+        err = H.rel_err(torch.from_numpy(np.asarray(b["actions"])), torch.from_numpy(np.asarray(a["actions"])))
+        print(f"reference Policy on the engine vs kai0_b200.serving.Policy, request {i}: rel {err:.2e}")
+        assert err < 2e-3, (i, err)
+
+
+def dataclass_fields(cfg):
+    import dataclasses
+
+    return {f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)}
+

@@ -31,9 +31,22 @@ import typing
 
 import numpy as np
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_STAGED = os.path.join(_ROOT, "baseline", "_ref")
+
+
+def _first(*candidates):
+    """The read-only checkout of the build container, else the byte-for-byte staged copy under baseline/_ref
+    (tools/stage_reference.py; it travels to the GPU box, where /root/reference does not exist)."""
+    if os.environ.get("KAI0_REFERENCE_STAGED_ONLY"):  # exercise the GPU-box situation in the build container
+        candidates = candidates[1:]
+    return next((c for c in candidates if os.path.exists(c)), candidates[0])
+
+
 REPO = "/root/reference"
-SRC = os.path.join(REPO, "src", "openpi")
-CLIENT = os.path.join(REPO, "packages", "openpi-client", "src", "openpi_client")
+SRC = _first(os.path.join(REPO, "src", "openpi"), os.path.join(_STAGED, "openpi"))
+CLIENT = _first(os.path.join(REPO, "packages", "openpi-client", "src", "openpi_client"), os.path.join(_STAGED, "openpi_client"))
+TRAIN_SCRIPT = _first(os.path.join(REPO, "scripts", "train_pytorch.py"), os.path.join(_STAGED, "scripts", "train_pytorch.py"))
 _loaded = None
 _tokenizer_model: dict = {"path": None}
 
@@ -141,6 +154,59 @@ class ModelType(enum.Enum):  # models/model.py:30-37 (values only)
 
 _policy_loaded = None
 _train_loaded = None
+_policy_config_loaded = None
+
+
+def load_policy_config():
+    """`openpi/policies/policy_config.py` executed in place on top of `load_policy()`: the reference's own
+    `create_trained_policy` (:16-94).  Supplied: `openpi.shared.download.maybe_download` (returns the local path),
+    `openpi.training.checkpoints.load_norm_stats` (training/checkpoints.py:110-114: `normalize.load(assets_dir / asset_id)`,
+    here through the reference's own normalize module; the real file imports orbax / jax at its top) and an empty
+    `openpi.training.config` (type annotations only).  Returns (policy_config module, policy module, model module)."""
+    global _policy_config_loaded
+    if _policy_config_loaded is not None:
+        return _policy_config_loaded
+    policy, model = load_policy()
+    R = load()
+
+    class _StubModule(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything()
+
+    names = ("jax", "jax.numpy", "openpi.shared.download", "openpi.training", "openpi.training.checkpoints",
+             "openpi.training.config", "openpi.models.model", "openpi.policies.policy")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        jnp = _StubModule("jax.numpy")
+        jx = _StubModule("jax")
+        jx.numpy = jnp
+        dl = _StubModule("openpi.shared.download")
+        dl.maybe_download = lambda url, **kw: pathlib.Path(str(url))
+        ck = _StubModule("openpi.training.checkpoints")
+        ck.load_norm_stats = lambda assets_dir, asset_id: R.normalize.load(pathlib.Path(assets_dir) / asset_id)
+        tr = _StubModule("openpi.training")
+        tr.__path__ = []
+        tr.checkpoints, tr.config = ck, _StubModule("openpi.training.config")
+        sys.modules.update({"jax": jx, "jax.numpy": jnp, "openpi.shared.download": dl, "openpi.training": tr,
+                            "openpi.training.checkpoints": ck, "openpi.training.config": tr.config,
+                            "openpi.models.model": model, "openpi.policies.policy": policy})
+        sys.modules["openpi.shared"].download = dl
+        sys.modules["openpi"].training = tr
+        sys.modules["openpi.models"].model = model
+        sys.modules["openpi.policies"].policy = policy
+        spec = importlib.util.spec_from_file_location("_kai0_reference_policy_config", os.path.join(SRC, "policies", "policy_config.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _policy_config_loaded = (mod, policy, model)
+    return _policy_config_loaded
 
 
 def load_train_script():
@@ -174,8 +240,7 @@ def load_train_script():
         sys.modules["openpi.models_pytorch"].pi0_pytorch = sys.modules["openpi.models_pytorch.pi0_pytorch"]
         sys.modules["openpi.training"].config = sys.modules["openpi.training.config"]
         sys.modules["openpi.training"].data_loader = sys.modules["openpi.training.data_loader"]
-        spec = importlib.util.spec_from_file_location("_kai0_reference_train_pytorch",
-                                                      os.path.join(REPO, "scripts", "train_pytorch.py"))
+        spec = importlib.util.spec_from_file_location("_kai0_reference_train_pytorch", TRAIN_SCRIPT)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:

@@ -41,6 +41,8 @@ _STAGED = (os.path.join(_ROOT, "baseline", "_ref", "scripts", "train_pytorch.py"
 
 def paths(prefer_staged: bool = False):
     order = (_STAGED, _CHECKOUT) if prefer_staged else (_CHECKOUT, _STAGED)
+    if os.environ.get("KAI0_REFERENCE_STAGED_ONLY"):
+        order = (_STAGED,)
     for cand in order:
         if all(os.path.isfile(p) for p in cand):
             return cand

@@ -21,6 +21,8 @@ SRC = "/root/reference/src/openpi"
 DST = os.path.join(ROOT, "baseline", "_ref", "openpi")
 SCRIPT_SRC = "/root/reference/scripts/train_pytorch.py"
 SCRIPTS_DST = os.path.join(ROOT, "baseline", "_ref", "scripts")
+CLIENT_SRC = "/root/reference/packages/openpi-client/src/openpi_client"
+CLIENT_DST = os.path.join(ROOT, "baseline", "_ref", "openpi_client")
 
 
 def stage() -> bool:
@@ -33,6 +35,10 @@ def stage() -> bool:
     # `train_loop` around the engine on the GPU box (tools/reference_train_harness.py)
     os.makedirs(SCRIPTS_DST, exist_ok=True)
     shutil.copyfile(SCRIPT_SRC, os.path.join(SCRIPTS_DST, "train_pytorch.py"))
+    # the client-side helper package the serving code imports (image_tools, msgpack_numpy, base_policy, websocket client)
+    if os.path.isdir(CLIENT_DST):
+        shutil.rmtree(CLIENT_DST)
+    shutil.copytree(CLIENT_SRC, CLIENT_DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
     h = hashlib.sha256()
     n = 0
     for d, _, files in sorted(os.walk(DST)):
