@@ -85,3 +85,45 @@ def test_the_references_train_loop_runs_in_place_around_a_stand_in(tmp_path, cap
     (resumed,) = _StandIn.created
     assert resumed.calls == 2 and "6" in os.listdir(tmp_path / "run")
     assert script.get_latest_checkpoint_step(tmp_path / "run") == 6
+
+
+@pytest.mark.skipif(not TH.available(), reason="needs the reference script (/root/reference or the staged copy)")
+def test_fine_tune_and_advantage_estimator_branches_of_the_references_loop(tmp_path):
+    """train_pytorch.py:449-460 (`pytorch_weight_path`: safetensors weights loaded before training, strict unless the
+    advantage estimator is trained) and :366-368,402-405 (`advantage_estimator=True` builds `AdvantageEstimator`)."""
+    import safetensors.torch
+
+    class _Value(_StandIn):
+        pass
+
+    mod = types.ModuleType("stand_in_pi0_pytorch")
+    mod.PI0Pytorch, mod.AdvantageEstimator = _StandIn, _Value
+    pretrained = _StandIn(TH.Pi0Config(action_horizon=5))
+    with torch.no_grad():
+        pretrained.lin.weight.fill_(0.125)
+    os.makedirs(tmp_path / "init")
+    safetensors.torch.save_model(pretrained, str(tmp_path / "init" / "model.safetensors"))
+    seen = {}
+    orig = _StandIn.forward
+
+    def spy(self, observation, actions, noise=None, time=None):
+        seen.setdefault("first_weight", self.lin.weight.detach().clone())
+        return orig(self, observation, actions, noise, time)
+
+    _StandIn.forward = spy
+    try:
+        _StandIn.created.clear()
+        cfg = TH.TrainConfig(checkpoint_dir=tmp_path / "ft", model=TH.Pi0Config(action_horizon=5), num_train_steps=2,
+                             pytorch_weight_path=str(tmp_path / "init"))
+        TH.run(mod, cfg, TH.ListLoader(_batches(2)))
+        assert type(_StandIn.created[-1]) is _StandIn and torch.all(seen["first_weight"] == 0.125)  # trained FROM the weights
+        _StandIn.created.clear()
+        cfg = TH.TrainConfig(checkpoint_dir=tmp_path / "adv", model=TH.AdvantageEstimatorConfig(action_horizon=5),
+                             num_train_steps=2, advantage_estimator=True)
+        TH.run(mod, cfg, TH.ListLoader(_batches(2)))
+        assert type(_StandIn.created[-1]) is _Value and _StandIn.created[-1].calls == 2
+        # :155 as written: off the save interval only `global_step == num_train_steps - 1` is saved, i.e. step 1 of 2
+        assert sorted(os.listdir(tmp_path / "adv")) == ["1"]
+    finally:
+        _StandIn.forward = orig
+
