@@ -269,6 +269,30 @@ def _cpu_port(steps: int, warmup: int, budget_s: float):
                                      f"{threads} threads"}
 
 
+def serving_leg(timeout_s: float = 150.0):
+    """SURVEY §8 row f4 (serving side), reported beside the decode latency: `tools/serving_probe.py` in a CHILD process (its
+    own CUDA context: nothing it does can touch the measured line) -- the full architecture behind
+    `kai0_b200.serving.Policy.infer_batch`, request dicts in host memory in, reply dicts out, for batches of 1 and 8."""
+    import subprocess
+    import tempfile
+
+    out = os.path.join(tempfile.mkdtemp(prefix="kai0_serving_"), "probe.jsonl")
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "serving_probe.py"), "--out", out, "--batches", "1,8",
+                        "--iters", "8"], timeout=timeout_s, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        recs = [json.loads(ln) for ln in open(out) if ln.strip()]
+        by_batch = {r["batch"]: r for r in recs if "batch" in r}
+        if not by_batch or any("error" in r for r in by_batch.values()):
+            return {"unavailable": str([r.get("error") for r in by_batch.values()])[:300]}
+        return {"what": "Policy.infer_batch at the full architecture: host request dicts -> transforms -> pinned staging -> "
+                        "H2D -> sample_actions (10 steps, CUDA graph) -> D2H -> reply transforms (tools/serving_probe.py)",
+                "batches": {str(b): {k: r[k] for k in ("p50_ms", "min_ms", "max_ms", "iters", "model_call_p50_ms",
+                                                      "requests_per_s", "rel_err_vs_batch_of_one", "finite")}
+                            for b, r in sorted(by_batch.items())}}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 def bench_config(world: int, B: int, small: bool):
     """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
     return {"workload": ("pi0.5 full fine-tune bf16, 3-cam 224x224, batch 32 per GPU (BASELINE.json configs[1]; configs[2] "
@@ -299,6 +323,9 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the reference_gpu anchor (the reference's own eager module timed on this GPU, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-serving", action="store_true",
+                    help="skip the serving leg (tools/serving_probe.py in a child process: request batches of 1 and 8 "
+                         "through kai0_b200.serving.Policy.infer_batch, host dicts in / host replies out)")
     ap.add_argument("--small", action="store_true", help="debug: tiny architecture (not a valid bench number)")
     ap.add_argument("--per-param-optimizer", action="store_true",
                     help="AdamW/clip over model.parameters() exactly as the unchanged script (slower: ~1400 launches)")
@@ -619,6 +646,8 @@ def main():
             model._destroy_engine()
             del model
             torch.cuda.empty_cache()
+        if world == 1 and not args.small and not args.no_serving:
+            line["serving"] = serving_leg()
         if world == 1 and not args.no_cpu_baseline:
             try:  # a failure of the reported CPU context must not cost the measured GPU line
                 info = cpu_reference(host_d, host_a, 2, 1, 0.0, whole_first=False)

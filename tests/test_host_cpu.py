@@ -277,6 +277,10 @@ def test_bench_bookkeeping():
     v2, note2 = b.ncu_traffic(32768, 2048, 27648, 0, 3)
     assert v2 == v and "dense prefix" in note2
     assert b.ncu_traffic(7, 7, 7, 0, 0)[0] is None
+    # the serving leg runs in a child process and can only ever ADD a record: without a GPU it reports why, nothing raises
+    if not torch.cuda.is_available():
+        leg = b.serving_leg(timeout_s=120)
+        assert set(leg) == {"unavailable"} and "serving_probe.py" in leg["unavailable"]
 
 
 def test_staged_reference_is_byte_identical_to_the_checkout():
